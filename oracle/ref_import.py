@@ -1,0 +1,83 @@
+"""Import the UNMODIFIED reference modules from /root/reference through stubs.
+
+Test infrastructure (see oracle/__init__.py).  Only usable in the build
+container: /root/reference does not exist on the GPU box, so nothing that runs
+there may call this.  It is used by tests/golden/gen_golden.py to produce the
+committed fixtures and by tests (skipped when the reference is absent) to
+re-check the oracle against the live reference.
+
+The reference cannot be imported as-is: reward_func.py:6
+needs `rouge_score` (used only by ans_acc_reward, out of scope) and
+grpo_trainer.py:59-62 needs `trl`.  Both are replaced by empty stub modules;
+no reference source is copied or modified.
+"""
+import importlib
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("O3V_REFERENCE_ROOT", "/root/reference")
+_R1V = os.path.join(REFERENCE_ROOT, "src", "r1-v")
+_OPEN_R1 = os.path.join(_R1V, "src", "open_r1")
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(_OPEN_R1, "reward_func.py"))
+
+
+def _stub(name, **attrs):
+    if name in sys.modules:
+        return sys.modules[name]
+    m = types.ModuleType(name)
+    for k, v in attrs.items():
+        setattr(m, k, v)
+    sys.modules[name] = m
+    return m
+
+
+def load_reward_func():
+    """The reference's reward_func module (reward_func.py), rouge stubbed."""
+    if not reference_available():
+        raise RuntimeError("reference not present at %s" % REFERENCE_ROOT)
+    _stub("rouge_score", rouge_scorer=None)
+    if _OPEN_R1 not in sys.path:
+        sys.path.insert(0, _OPEN_R1)
+    return importlib.import_module("reward_func")
+
+
+def load_trainer_class():
+    """The reference's Qwen2VLGRPOTrainer class (grpo_trainer.py), trl stubbed.
+
+    Only `_get_per_token_logps` (grpo_trainer.py:371-384) is callable without a
+    live model: it never touches `self`, so it is used unbound.
+    """
+    if not reference_available():
+        raise RuntimeError("reference not present at %s" % REFERENCE_ROOT)
+    _stub("trl")
+    _stub("trl.data_utils", apply_chat_template=None, is_conversational=None,
+          maybe_apply_chat_template=None)
+    _stub("trl.models", create_reference_model=None, prepare_deepspeed=None,
+          unwrap_model_for_generation=None)
+    _stub("trl.trainer")
+    _stub("trl.trainer.grpo_config", GRPOConfig=object)
+    _stub("trl.trainer.utils", generate_model_card=None, get_comet_experiment_url=None)
+    if _R1V not in sys.path:
+        sys.path.insert(0, _R1V)
+    mod = importlib.import_module("src.open_r1.trainer.grpo_trainer")
+    return mod.Qwen2VLGRPOTrainer
+
+
+class FakeLMHeadModel:
+    """Stands in for the HF model: `model(input_ids).logits = hidden @ W^T`.
+
+    The backbone is out of scope; the reference's `model(...)` ends in
+    `lm_head = nn.Linear(H, V, bias=False)` (transformers
+    modeling_qwen2_5_vl.py), which is all the hot path sees.
+    """
+
+    def __init__(self, hidden, weight):
+        self.hidden, self.weight = hidden, weight
+
+    def __call__(self, input_ids, **kwargs):
+        import torch.nn.functional as F
+        return types.SimpleNamespace(logits=F.linear(self.hidden, self.weight))

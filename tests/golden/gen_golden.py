@@ -1,0 +1,92 @@
+"""Generate the golden fixtures in this directory by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+    python tests/golden/gen_golden.py
+Outputs (committed):
+    logps_small.npz      reference _get_per_token_logps (grpo_trainer.py:371-384) on seeded inputs
+    rewards_small.json   reference reward_func.py functions on rendered synthetic rollouts
+    rewards_kat.json     the known-answer cases of SURVEY.md Appendix B, re-run here
+Inputs are regenerated from the seed by the tests (oracle/synth.py); only outputs
+(and, for rewards, the small structured inputs) are stored.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import ref_import, synth, rewards as orw  # noqa: E402
+
+
+def gen_logps():
+    Trainer = ref_import.load_trainer_class()
+    out = {}
+    for name, (B, L, H, V, planted) in {
+        "a": (2, 9, 64, 1000, False),
+        "b": (3, 33, 128, 5003, True),
+        "c": (1, 17, 256, 151936 // 16, False),
+    }.items():
+        hidden, weight, _ = synth.head_inputs(B * L, H, V, seed=synth.SEED + ord(name), planted=planted)
+        g = torch.Generator().manual_seed(synth.SEED + 100 + ord(name))
+        ids = torch.randint(0, V, (B, L), generator=g, dtype=torch.int64)
+        model = ref_import.FakeLMHeadModel(hidden.view(B, L, H), weight)
+        with torch.no_grad():
+            lp = Trainer._get_per_token_logps(None, model, ids)
+        out["logp_" + name] = lp.numpy()
+        out["shape_" + name] = np.array([B, L, H, V, int(planted)])
+    np.savez_compressed(os.path.join(HERE, "logps_small.npz"), **out)
+    print("logps_small.npz", {k: v.shape for k, v in out.items()})
+
+
+def gen_rewards():
+    rf = ref_import.load_reward_func()
+    rollouts = synth.rollouts(n_prompts=60, G=4, P=16, K=8, O=4, Gb=2, Bc=2)
+    ref = orw.reference_rewards(rf, rollouts)
+    with open(os.path.join(HERE, "rewards_small.json"), "w") as f:
+        json.dump(dict(seed=synth.SEED, gen=dict(n_prompts=60, G=4, P=16, K=8, O=4, Gb=2, Bc=2),
+                       names=list(orw.REWARD_NAMES),
+                       expected=[[repr(float(x)) for x in row] for row in ref]), f)
+    print("rewards_small.json", ref.shape, "nonzero per column", (ref != 0).sum(0))
+
+    # Appendix B known answers, recomputed from the live reference
+    base = dict(has_think=True, has_answer=True, ans_seg=None, ans_box=None, think_boxes=[],
+                gt_seg=[10.0, 20.0], gt_vbox=None,
+                key_frames=[{"idx": 3, "time": 5.4}, {"idx": 9, "time": 12.0}],
+                key_items={"3": {"dog": [[.2, .2, .6, .6]]},
+                           "9": {"cat": [[.4, .4, .8, .8]], "mouse": [[0, 0, .1, .1]]}},
+                image_size=(500, 500), image_size_refine=(500, 500), step_percent=0.0)
+    cases = []
+
+    def add(name, **kw):
+        r = dict(base); r.update(kw); cases.append((name, r))
+    claims3 = [(5.0, [[100, 100, 300, 300]]), (12.5, [[10, 10, 50, 50], [200, 200, 400, 400]]),
+               (0.5, [[0, 0, 10, 10]])]
+    for sp in (0.0, 0.25, 0.74, 0.75, 1.0):
+        add("tsfree_sp%s" % sp, task="temporal-spatial free-form QA", claims=claims3,
+            think_times=[5.0, 12.5, 0.5], step_percent=sp)
+    add("single_t99", task="temporal-spatial free-form QA", claims=[(99.0, [[100, 100, 300, 300]])], think_times=[99.0])
+    add("single_t1", task="temporal-spatial free-form QA", claims=[(1.0, [[100, 100, 300, 300]])], think_times=[1.0])
+    add("tiou_fwd", task="temporal QA", claims=[], think_times=[12.0, 25.5], ans_seg=[15.0, 30.0])
+    add("tiou_rev", task="temporal QA", claims=[], think_times=[], ans_seg=[30.0, 15.0])
+    add("tiou_mcq", task="temporal QA (MCQ)", claims=[], think_times=[10.0, 20.0, 20.01], ans_seg=[12.0, 18.0])
+    add("vqa", task="visual QA", claims=[], think_times=[], think_boxes=[[10, 10, 60, 60], [100, 120, 300, 310]],
+        ans_box=[100, 100, 300, 300], gt_vbox=[110.0, 90.0, 320.0, 300.0], image_size=(640, 360),
+        image_size_refine=(448, 252))
+    ref = orw.reference_rewards(rf, [c[1] for c in cases])
+    with open(os.path.join(HERE, "rewards_kat.json"), "w") as f:
+        json.dump([dict(name=n, rollout=r, expected=[repr(float(x)) for x in row])
+                   for (n, r), row in zip(cases, ref)], f, indent=1)
+    for (n, _), row in zip(cases, ref):
+        print(n, row.tolist())
+    iou = [rf.calculate_iou([0, 0, 1, 1], [0, 0, 1, 1]), rf.calculate_iou([0, 0, 1, 1], [2, 2, 3, 3]),
+           rf.calculate_iou([1, 1, 1, 1], [1, 1, 1, 1]), rf.calculate_iou([0, 0, 1, 1], [0, 0, 1])]
+    print("calculate_iou KAT", iou, type(iou[0]))
+
+
+if __name__ == "__main__":
+    gen_logps()
+    gen_rewards()
