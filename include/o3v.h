@@ -1,0 +1,208 @@
+/*
+ * o3v.h -- C ABI of libo3v.so: the B200 (sm_100a) implementation of Open-o3-Video's
+ * RL policy-objective hot path.
+ *
+ * Every entry point replaces a piece of the reference's Python/PyTorch path; the
+ * reference file:line it replaces is cited on each declaration (paths relative to
+ * /root/reference/src/r1-v/src/open_r1/).  The reference has no FFI of its own (it is
+ * pure Python); the binding a maintainer adds is the ctypes stub in INTEGRATION.md,
+ * which is what `open-o3-video_b200/_lib.py` implements.
+ *
+ * Conventions
+ *  - POD arguments only: raw DEVICE pointers, sizes, scalars and a CUDA stream handle
+ *    (`void*`, i.e. cudaStream_t / CUstream; NULL = legacy default stream).
+ *  - The caller owns every buffer (inputs, outputs, workspace).  The library never
+ *    allocates or frees device memory and keeps no pointer past the call.  Outputs are
+ *    fully overwritten unless an `accumulate` flag says otherwise.
+ *  - All work is enqueued on `stream`; no call synchronises the device.
+ *  - Return 0 on success; negative = O3V_ERR_* argument/shape/alignment/arch violation;
+ *    positive = cudaError_t.  Nothing throws or aborts across this boundary.
+ *  - sm_100 only: on any other device every compute entry returns
+ *    O3V_ERR_UNSUPPORTED_ARCH (there is no fallback path).
+ *  - bf16 tensors are row-major, 16-byte aligned, leading dimension a multiple of 8.
+ */
+#ifndef O3V_H_
+#define O3V_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define O3V_VERSION 100 /* major*10000 + minor*100 + patch */
+
+#define O3V_OK 0
+#define O3V_ERR_INVALID_ARG (-1)      /* null pointer, non-positive size, bad flag */
+#define O3V_ERR_ALIGNMENT (-2)        /* pointer / leading dimension alignment */
+#define O3V_ERR_UNSUPPORTED_ARCH (-3) /* device is not sm_100 */
+#define O3V_ERR_WORKSPACE (-4)        /* workspace too small */
+#define O3V_ERR_DRIVER (-5)           /* cuTensorMapEncodeTiled / driver entry point failed */
+#define O3V_ERR_SHAPE (-6)            /* unsupported shape (e.g. H % 64 != 0) */
+
+int o3v_version(void);
+const char* o3v_strerror(int code);
+/* 0 if the CURRENT device is sm_100, else O3V_ERR_UNSUPPORTED_ARCH. */
+int o3v_check_device(void);
+/* Diagnostic knobs for bench sweeps (defaults are the shipped configuration):
+ *   "cta_pair"   1 = one CTA per 128-row tile, 2 = cta_group::2 pairs (256-row tiles)
+ *   "fwd_groups" vocab splits per token block in K1 (0 = auto)
+ *   "max_ctas"   cap on the persistent grid (0 = all SMs) */
+int o3v_set_tunable(const char* name, int value);
+
+/* ------------------------------------------------------------------------------------
+ * K3a  first-EOS mask.   Replaces trainer/grpo_trainer.py:590-596.
+ *   eos_idx[n] = first t with ids[n,t] == eos_id, else Tc      (int64, bit-exact)
+ *   mask[n,t]  = (t <= eos_idx[n])                             (int32)
+ * ---------------------------------------------------------------------------------- */
+int o3v_eos_mask(const int64_t* completion_ids, int64_t N, int64_t Tc, int64_t eos_id,
+                 int64_t* eos_idx, int32_t* completion_mask, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K1  fused lm_head GEMM + online log-softmax statistics + target gather.
+ * Replaces trainer/grpo_trainer.py:375 (`model(...).logits`, i.e. transformers'
+ * lm_head = nn.Linear(H, V, bias=False)) and :380-383 (log_softmax + gather) for one
+ * vocabulary slice [v_offset, v_offset + V) of the head.
+ *
+ *   hidden  [T, H] bf16 (each row already paired with its NEXT token id, i.e. the
+ *           caller applied grpo_trainer.py:376-377's shift)
+ *   weight  [V, H] bf16 (rows v_offset.. of lm_head.weight)
+ *   targets [T] int64 GLOBAL vocab ids
+ *   stats   [3, T] fp32 out: row max m, sum exp(z - m), target logit (0 if the target
+ *           is outside this slice).  The [T, V] logits never reach HBM unless
+ *   logits  != NULL: then bf16 logits are also stored to logits[t * ld_logits + v]
+ *           (needed only by the chunked backward, see o3v_lmhead_dlogits).
+ * ---------------------------------------------------------------------------------- */
+size_t o3v_lmhead_fwd_workspace_bytes(int64_t T, int64_t V, int64_t H);
+int o3v_lmhead_fwd(const void* hidden, const void* weight, const int64_t* targets,
+                   int64_t T, int64_t V, int64_t H, int64_t v_offset,
+                   float* stats, void* logits, int64_t ld_logits,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* Merge P partial statistics (vocab slices of one GPU or of several GPUs after an
+ * all-gather) into per-token log-probs: parts [P, 3, T] ->
+ *   lse[t] = M + log(sum_p s_p * exp(m_p - M)),  logp[t] = sum_p z_p - lse[t].
+ * Deterministic (fixed p order).  Finishes grpo_trainer.py:381-382. */
+int o3v_lmhead_merge_stats(const float* parts, int64_t P, int64_t T,
+                           float* logp, float* lse, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K2  chunked fused backward of K1 (replaces the autograd backward of
+ * grpo_trainer.py:375-383: softmax-backward + two GEMMs).
+ *
+ * o3v_lmhead_dlogits: in place on the bf16 logits stored by o3v_lmhead_fwd,
+ *   P[t,v] = g[t] * ( [v + v_offset == targets[t]] - exp(z[t,v] - lse[t]) )
+ * where g[t] = dLoss/dlogp[t] (from o3v_gspo_fwd_bwd).
+ * o3v_lmhead_bwd_dhidden:  dH[T,H]  = P[T,V] . W[V,H]          (bf16 or fp32 out)
+ * o3v_lmhead_bwd_dweight:  dW[V,H] (+)= P^T[V,T] . hidden[T,H]  (fp32, optional accumulate)
+ * ---------------------------------------------------------------------------------- */
+int o3v_lmhead_dlogits(void* logits, int64_t T, int64_t V, int64_t ld_logits,
+                       const float* lse, const float* grad_logp, const int64_t* targets,
+                       int64_t v_offset, void* stream);
+int o3v_lmhead_bwd_dhidden(const void* dlogits, int64_t ld_dlogits, const void* weight,
+                           int64_t T, int64_t V, int64_t H,
+                           void* d_hidden, int32_t out_is_fp32, void* stream);
+int o3v_lmhead_bwd_dweight(const void* dlogits, int64_t ld_dlogits, const void* hidden,
+                           int64_t T, int64_t V, int64_t H,
+                           float* d_weight, int32_t accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K3  KL + group advantages + GSPO (or token-level) ratio / clip / loss, forward and
+ * backward in one launch.  Replaces grpo_trainer.py:635-636, 658, 675-681, 691-706 and
+ * the metrics at :711, :737.
+ *
+ * One call handles the sequences [seq_offset, seq_offset + n_seq) of a step of N sequences
+ * (n_seq = N, seq_offset = 0 for the whole step at once; the chunked fused fwd+bwd calls it
+ * once per token chunk, in ascending seq_offset order starting at 0, on the same workspace).
+ *   logp, ref_logp [n_seq, Tc] fp32; old_logp [n_seq, Tc] fp32 or NULL (= logp.detach(),
+ *   the reference's behaviour at :691); mask [n_seq, Tc] int32: rows of THIS call;
+ *   rewards_per_func [N, F] fp32: the whole step; groups are contiguous blocks of G rows
+ *   (`view(-1, G)`, :675).
+ * Outputs (any may be NULL except loss):
+ *   loss [1], mean_kl [1]: written by the call that completes sequence N (means over N);
+ *   advantages [N], reward_std [N], completion_len [N] int32: indexed globally;
+ *   grad_logp [n_seq, Tc] = dLoss/dlogp, per_token_kl [n_seq, Tc]: rows of this call.
+ * workspace: o3v_gspo_workspace_bytes(N) bytes, the same buffer for every call of a step.
+ * ---------------------------------------------------------------------------------- */
+size_t o3v_gspo_workspace_bytes(int64_t N);
+int o3v_gspo_fwd_bwd(const float* logp, const float* old_logp, const float* ref_logp,
+                     const int32_t* mask, const float* rewards_per_func,
+                     int64_t N, int64_t Tc, int64_t F, int64_t G,
+                     int64_t seq_offset, int64_t n_seq,
+                     float beta, float eps_low, float eps_high, int32_t gspo,
+                     float* loss, float* mean_kl, float* advantages, float* reward_std,
+                     int32_t* completion_len, float* grad_logp, float* per_token_kl,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K4  grounded rewards on parsed rollouts (struct of arrays, fp64).
+ * Replaces the numeric cores of reward_func.py: ans_tiou_reward :128-143,
+ * ans_viou_reward :210-226, thk_temporal_segment_reward :417-421,
+ * thk_temporal_point_reward :453-467, thk_spatial_reward :490-525 and :542-603,
+ * calculate_iou :356-386, convert_coord_format(_gqa) :337-354, with the task gating of
+ * :99-103, :196, :396, :439, :484-531.  Text extraction stays in Python.
+ *
+ * Rollout r belongs to prompt q = r / G; ground truth is stored once per prompt.
+ * out [R, 5] fp64 = (ans_tiou, ans_viou, thk_temporal_segment, thk_temporal_point,
+ * thk_spatial).
+ * ---------------------------------------------------------------------------------- */
+#define O3V_TASK_VISUAL_QA 0          /* "visual QA" */
+#define O3V_TASK_TEMPORAL_QA 1        /* "temporal QA" */
+#define O3V_TASK_TEMPORAL_QA_MCQ 2    /* "temporal QA (MCQ)" */
+#define O3V_TASK_TS_FREEFORM 3        /* "temporal-spatial free-form QA" */
+#define O3V_TASK_GENERAL_MCQ 4        /* "General video QA MCQ" */
+#define O3V_TASK_GENERAL_FREEFORM 5   /* "General video QA Free-form" */
+
+#define O3V_RF_HAS_THINK 1   /* <think>..</think> matched            (reward_func.py:392) */
+#define O3V_RF_HAS_ANSWER 2  /* <answer>..</answer> matched          (reward_func.py:482) */
+#define O3V_RF_ANS_SEG 4     /* answer holds "<t>s</t>s to <t>e</t>s" (reward_func.py:119) */
+#define O3V_RF_ANS_BOX 8     /* answer holds a <box> that parsed to 4 numbers (:212, :361) */
+#define O3V_GF_VBOX 1        /* GT answer holds a <box>              (reward_func.py:204) */
+
+typedef struct o3v_rewards_soa {
+  int64_t R;  /* rollouts */
+  int64_t G;  /* rollouts per prompt; GT arrays have Q = R / G rows */
+  int32_t P;  /* max think timestamps per rollout */
+  int32_t C;  /* max claims per rollout */
+  int32_t Bc; /* max boxes per claim (<= 32) */
+  int32_t Tb; /* max think boxes per rollout, visual-QA branch (<= 32) */
+  int32_t K;  /* max key frames per prompt */
+  int32_t O;  /* max objects per key frame */
+  int32_t Gb; /* max GT boxes per object */
+  int32_t pad_;
+  double step_percent; /* kwargs['step_percent'][0] (reward_func.py:431) */
+  /* per rollout */
+  const int32_t* flags;       /* [R] O3V_RF_* */
+  const double* ans_seg;      /* [R, 2] */
+  const double* ans_box;      /* [R, 4] */
+  const int32_t* n_times;     /* [R] */
+  const double* think_times;  /* [R, P] */
+  const int32_t* n_claims;    /* [R] (= len(parsed_claims), the divisor at :603) */
+  const double* claim_t;      /* [R, C] */
+  const int32_t* claim_nbox;  /* [R, C] */
+  const uint32_t* claim_valid;/* [R, C] bit b: box b is a list of 4 numbers (:361) */
+  const double* claim_box;    /* [R, C, Bc, 4] pixels */
+  const int32_t* n_tboxes;    /* [R] */
+  const uint32_t* tbox_valid; /* [R] */
+  const double* think_box;    /* [R, Tb, 4] pixels */
+  /* per prompt */
+  const int32_t* task;        /* [Q] O3V_TASK_* */
+  const int32_t* gt_flags;    /* [Q] O3V_GF_* */
+  const double* gt_seg;       /* [Q, 2] */
+  const double* gt_vbox;      /* [Q, 4] */
+  const double* image_size;   /* [Q, 2] (W, H) */
+  const double* image_refine; /* [Q, 2] */
+  const int32_t* n_kf;        /* [Q] */
+  const double* kf_time;      /* [Q, K] in key_frames order */
+  const int32_t* n_obj;       /* [Q, K] */
+  const int32_t* n_gtbox;     /* [Q, K, O] */
+  const double* gt_box;       /* [Q, K, O, Gb, 4] normalised */
+} o3v_rewards_soa;
+
+int o3v_grounded_rewards(const o3v_rewards_soa* soa, double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* O3V_H_ */

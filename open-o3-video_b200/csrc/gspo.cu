@@ -1,0 +1,252 @@
+// K3a (first-EOS mask) and K3 (KL + group advantages + GSPO ratio/clip/loss, fwd+bwd).
+//
+// Replaces trainer/grpo_trainer.py:590-596 and :635-636, 658, 675-681, 691-706, 711, 737
+// of the reference.  Both kernels are HBM/launch bound (about 20 B per token): one CTA
+// per sequence, 128-bit loads, warp-shuffle reductions, and a deterministic last-CTA
+// reduction for the two scalars so that results are run-to-run bit-stable.
+#include "common.cuh"
+
+namespace o3v {
+
+constexpr int kGspoThreads = 256;
+
+// ------------------------------------------------------------------------------------
+// K3a: eos_idx[n] = first t with ids[n,t]==eos else Tc; mask[n,t] = (t <= eos_idx[n]).
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGspoThreads)
+eos_mask_kernel(const int64_t* __restrict__ ids, int64_t Tc, int64_t eos_id,
+                int64_t* __restrict__ eos_idx, int32_t* __restrict__ mask) {
+  __shared__ int s_min[kGspoThreads / 32];
+  const int64_t n = blockIdx.x;
+  const int64_t* row = ids + n * Tc;
+  int first = (int)Tc;
+  // strided scan; a thread can stop at its first hit because its indices ascend
+  for (int64_t t = threadIdx.x; t < Tc; t += kGspoThreads) {
+    if (row[t] == eos_id) { first = (int)t; break; }
+  }
+  first = warp_min_i(first);
+  if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = first;
+  __syncthreads();
+  first = s_min[0];
+#pragma unroll
+  for (int w = 1; w < kGspoThreads / 32; ++w) first = min(first, s_min[w]);
+  if (threadIdx.x == 0) eos_idx[n] = (int64_t)first;
+  int32_t* mrow = mask + n * Tc;
+  for (int64_t t = threadIdx.x; t < Tc; t += kGspoThreads) mrow[t] = (t <= (int64_t)first) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------
+// K3
+// ------------------------------------------------------------------------------------
+struct GspoParams {
+  const float* logp; const float* old_logp; const float* ref; const int32_t* mask;
+  const float* rpf;
+  int64_t N, Tc, F, G;      // N = TOTAL sequences of the step (loss is a mean over N)
+  int64_t seq_offset;       // this launch handles global sequences [seq_offset, seq_offset + gridDim.x)
+  float beta, eps_lo, eps_hi; int gspo;
+  float* loss; float* mean_kl; float* adv; float* rstd; int32_t* clen;
+  float* grad; float* kl_out;
+  float* seq_loss; float* seq_kl; unsigned int* ticket;   // workspace
+};
+
+__device__ __forceinline__ float block_sum(float v, float* smem) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+#pragma unroll
+  for (int w = 0; w < kGspoThreads / 32; ++w) r += smem[w];   // fixed order: deterministic
+  return r;
+}
+
+// KL term of grpo_trainer.py:635-636 and its derivative w.r.t. logp.
+__device__ __forceinline__ void kl_and_grad(float lp, float rf, float& kl, float& dkl) {
+  const float x = rf - lp;
+  const float xc = fminf(fmaxf(x, -10.f), 10.f);
+  const float e = expf(xc);
+  kl = e - xc - 1.f;
+  // clamp passes gradient on the closed interval [-10, 10]; d(e^x - x - 1)/dlogp = 1 - e^x
+  dkl = (x >= -10.f && x <= 10.f) ? (1.f - e) : 0.f;
+}
+
+__global__ void __launch_bounds__(kGspoThreads)
+gspo_kernel(const GspoParams p) {
+  __shared__ float s_red[kGspoThreads / 32];
+  __shared__ float s_bcast[4];
+  __shared__ bool s_last;
+  const int64_t nl = blockIdx.x;                  // row in this launch's [n_seq, Tc] buffers
+  const int64_t n = p.seq_offset + nl;            // global sequence index (rewards, per-sequence outputs)
+  const int64_t Tc = p.Tc;
+  const float* lp_row = p.logp + nl * Tc;
+  const float* old_row = p.old_logp ? p.old_logp + nl * Tc : nullptr;
+  const float* ref_row = p.ref + nl * Tc;
+  const int32_t* m_row = p.mask + nl * Tc;
+
+  // ---- group advantage (grpo_trainer.py:658, 675-681); G is small, one thread does it
+  if (threadIdx.x == 0) {
+    const int64_t g0 = (n / p.G) * p.G;
+    float mine = 0.f, mean = 0.f;
+    for (int64_t j = 0; j < p.G; ++j) {
+      float r = 0.f;
+      for (int64_t f = 0; f < p.F; ++f) r += p.rpf[(g0 + j) * p.F + f];
+      if (g0 + j == n) mine = r;
+      mean += r;
+    }
+    mean /= (float)p.G;
+    float var = 0.f;
+    for (int64_t j = 0; j < p.G; ++j) {
+      float r = 0.f;
+      for (int64_t f = 0; f < p.F; ++f) r += p.rpf[(g0 + j) * p.F + f];
+      var += (r - mean) * (r - mean);
+    }
+    const float sd = sqrtf(var / (float)(p.G - 1));   // unbiased; G == 1 -> NaN like torch.std
+    const float a = (mine - mean) / (sd + 1e-4f);
+    s_bcast[0] = a;
+    if (p.adv) p.adv[n] = a;
+    if (p.rstd) p.rstd[n] = sd;
+  }
+  __syncthreads();
+  const float A = s_bcast[0];
+
+  // ---- pass 1: masked sums
+  float cnt = 0.f, sum_lr = 0.f, sum_kl = 0.f, sum_obj = 0.f;
+  for (int64_t t = threadIdx.x; t < Tc; t += kGspoThreads) {
+    const float lp = lp_row[t], rf = ref_row[t];
+    const float m = (float)m_row[t];
+    float kl, dkl;
+    kl_and_grad(lp, rf, kl, dkl);
+    if (p.kl_out) p.kl_out[nl * Tc + t] = kl;
+    const float lr = old_row ? (lp - old_row[t]) : 0.f;     // :691 (x - x.detach() == 0 exactly)
+    cnt += m;
+    sum_lr += lr * m;
+    sum_kl += kl * m;
+    if (!p.gspo) {                                          // token-level branch :696
+      const float c1 = expf(lr);
+      const float c2 = fminf(fmaxf(c1, 1.f - p.eps_lo), 1.f + p.eps_hi);
+      sum_obj += -fminf(c1 * A, c2 * A) * m;
+    }
+  }
+  cnt = block_sum(cnt, s_red);
+  sum_lr = block_sum(sum_lr, s_red);
+  sum_kl = block_sum(sum_kl, s_red);
+  if (!p.gspo) sum_obj = block_sum(sum_obj, s_red);
+
+  const float denom = fmaxf(cnt, 1.f);                      // .clamp(min=1.0) :693, :706
+  float c1_seq = 1.f, gate_seq = 1.f;
+  if (p.gspo) {
+    const float s = sum_lr / denom;                         // :693
+    c1_seq = expf(s);                                       // :698
+    const float c2 = fminf(fmaxf(c1_seq, 1.f - p.eps_lo), 1.f + p.eps_hi);   // :699
+    const float obj = -fminf(c1_seq * A, c2 * A);           // :701-703 (constant over t)
+    sum_obj = obj * cnt;
+    // d(-min(c1 A, clamp(c1) A))/dc1 = -A * gate  (torch.minimum splits ties, clamp passes
+    // gradient on the closed interval, so inside the clip range the two halves add up)
+    gate_seq = (A > 0.f) ? (c1_seq <= 1.f + p.eps_hi ? 1.f : 0.f)
+             : (A < 0.f) ? (c1_seq >= 1.f - p.eps_lo ? 1.f : 0.f) : 1.f;
+  }
+  if (threadIdx.x == 0) {
+    p.seq_loss[n] = (sum_obj + p.beta * sum_kl) / denom;    // :704-706
+    p.seq_kl[n] = sum_kl / cnt;                             // :737 (no clamp: 0/0 -> NaN as reference)
+    if (p.clen) p.clen[n] = (int32_t)cnt;                   // :711
+  }
+
+  // ---- pass 2: d loss / d logp
+  if (p.grad) {
+    const float scale = 1.f / (denom * (float)p.N);
+    for (int64_t t = threadIdx.x; t < Tc; t += kGspoThreads) {
+      const float lp = lp_row[t], rf = ref_row[t];
+      const float m = (float)m_row[t];
+      float kl, dkl;
+      kl_and_grad(lp, rf, kl, dkl);
+      float dobj;
+      if (p.gspo) {
+        dobj = -A * c1_seq * gate_seq;       // chain through s = sum(lr*mask)/denom handled by `scale`
+      } else {
+        const float lr = old_row ? (lp - old_row[t]) : 0.f;
+        const float c1 = expf(lr);
+        const float gate = (A > 0.f) ? (c1 <= 1.f + p.eps_hi ? 1.f : 0.f)
+                         : (A < 0.f) ? (c1 >= 1.f - p.eps_lo ? 1.f : 0.f) : 1.f;
+        dobj = -A * c1 * gate;
+      }
+      // GSPO: the per-token objective is constant over t, its masked mean is obj*cnt/denom,
+      // and ds/dlogp_t = mask_t/denom, so the factor is (cnt/denom) * mask_t/denom.
+      const float w = p.gspo ? (cnt / denom) : 1.f;
+      p.grad[nl * Tc + t] = m * scale * (dobj * w + p.beta * dkl);
+    }
+  }
+
+  // ---- deterministic final reduction by the last CTA to finish
+  __threadfence();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(p.ticket, 1u);
+    s_last = (done == (unsigned int)(p.N - 1));
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    float a = 0.f, b = 0.f;
+    for (int64_t i = threadIdx.x; i < p.N; i += kGspoThreads) {
+      a += __ldcg(p.seq_loss + i);
+      b += __ldcg(p.seq_kl + i);
+    }
+    a = block_sum(a, s_red);
+    b = block_sum(b, s_red);
+    if (threadIdx.x == 0) {
+      *p.loss = a / (float)p.N;                             // .mean() :706
+      if (p.mean_kl) *p.mean_kl = b / (float)p.N;           // .mean() :737
+      *p.ticket = 0u;                                       // re-arm for the next call
+    }
+  }
+}
+
+}  // namespace o3v
+
+extern "C" int o3v_eos_mask(const int64_t* completion_ids, int64_t N, int64_t Tc, int64_t eos_id,
+                            int64_t* eos_idx, int32_t* completion_mask, void* stream) {
+  if (!completion_ids || !eos_idx || !completion_mask) return O3V_ERR_INVALID_ARG;
+  if (N < 0 || Tc < 0 || Tc > 0x7fffffff) return O3V_ERR_INVALID_ARG;
+  int rc = o3v::check_device();
+  if (rc) return rc;
+  if (N == 0) return O3V_OK;
+  o3v::eos_mask_kernel<<<(unsigned)N, o3v::kGspoThreads, 0, (cudaStream_t)stream>>>(
+      completion_ids, Tc, eos_id, eos_idx, completion_mask);
+  O3V_LAUNCH_CHECK();
+  return O3V_OK;
+}
+
+extern "C" size_t o3v_gspo_workspace_bytes(int64_t N) {
+  if (N < 0) return 0;
+  return (size_t)(2 * N + 4) * sizeof(float);
+}
+
+extern "C" int o3v_gspo_fwd_bwd(const float* logp, const float* old_logp, const float* ref_logp,
+                                const int32_t* mask, const float* rewards_per_func,
+                                int64_t N, int64_t Tc, int64_t F, int64_t G,
+                                int64_t seq_offset, int64_t n_seq,
+                                float beta, float eps_low, float eps_high, int32_t gspo,
+                                float* loss, float* mean_kl, float* advantages, float* reward_std,
+                                int32_t* completion_len, float* grad_logp, float* per_token_kl,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  if (!logp || !ref_logp || !mask || !rewards_per_func || !loss || !workspace) return O3V_ERR_INVALID_ARG;
+  if (N <= 0 || Tc <= 0 || F <= 0 || G <= 0 || (N % G) != 0) return O3V_ERR_INVALID_ARG;
+  if (seq_offset < 0 || n_seq <= 0 || seq_offset + n_seq > N) return O3V_ERR_INVALID_ARG;
+  if (workspace_bytes < o3v_gspo_workspace_bytes(N)) return O3V_ERR_WORKSPACE;
+  int rc = o3v::check_device();
+  if (rc) return rc;
+  o3v::GspoParams p;
+  p.logp = logp; p.old_logp = old_logp; p.ref = ref_logp; p.mask = mask; p.rpf = rewards_per_func;
+  p.N = N; p.Tc = Tc; p.F = F; p.G = G; p.seq_offset = seq_offset;
+  p.beta = beta; p.eps_lo = eps_low; p.eps_hi = eps_high; p.gspo = gspo ? 1 : 0;
+  p.loss = loss; p.mean_kl = mean_kl; p.adv = advantages; p.rstd = reward_std; p.clen = completion_len;
+  p.grad = grad_logp; p.kl_out = per_token_kl;
+  float* ws = (float*)workspace;
+  p.seq_loss = ws; p.seq_kl = ws + N; p.ticket = (unsigned int*)(ws + 2 * N);
+  cudaStream_t st = (cudaStream_t)stream;
+  // the ticket counts finished sequences ACROSS the range calls of one step; the CTA that
+  // finishes sequence number N reduces loss / mean_kl over all N in index order
+  if (seq_offset == 0) O3V_CUDA_TRY(cudaMemsetAsync(p.ticket, 0, sizeof(unsigned int), st));
+  o3v::gspo_kernel<<<(unsigned)n_seq, o3v::kGspoThreads, 0, st>>>(p);
+  O3V_LAUNCH_CHECK();
+  return O3V_OK;
+}

@@ -1,0 +1,300 @@
+// Host side of K1 / K2 (C ABI in include/o3v.h) + the small elementwise kernels around the
+// tcgen05 GEMMs: partial-statistics merge and the in-place softmax backward (dlogits).
+#include <algorithm>
+#include <mutex>
+#include <string>
+
+#include "lmhead_gemm.cuh"
+
+namespace o3v {
+
+// ------------------------------------------------------------------------------------
+// Tunables (diagnostics / bench sweeps; defaults are what the product uses)
+// ------------------------------------------------------------------------------------
+static int g_cta_pair = 1;      // 1: one CTA per tile (UMMA M=128); 2: cta_group::2 pairs (M=256)
+static int g_fwd_groups = 0;    // n-groups (vocab splits) per m-block in K1; 0 = auto
+static int g_max_ctas = 0;      // cap on the persistent grid; 0 = all SMs
+
+// ------------------------------------------------------------------------------------
+// TMA descriptors (driver entry point fetched through the runtime: no libcuda link)
+// ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 row-major tensor [outer, inner] with row pitch `ld` elements; box = [box_outer, 64]
+// with the 128-byte swizzle; out-of-bounds elements read as zero.
+static int make_tmap_bf16(CUtensorMap* tm, const void* base, int64_t inner, int64_t outer, int64_t ld,
+                          int box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return O3V_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) || ((ld * 2) & 15)) return O3V_ERR_ALIGNMENT;
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? O3V_OK : O3V_ERR_DRIVER;
+}
+
+// ------------------------------------------------------------------------------------
+// launch
+// ------------------------------------------------------------------------------------
+template <bool kAMN, bool kBMN, int kNCta, int kEpi>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+  using S = GemmShape<kNCta>;
+  auto kern = lmhead_gemm_kernel<kAMN, kBMN, kNCta, kEpi>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES);
+  });
+  if (attr_err != cudaSuccess) return (int)attr_err;
+  int sms = num_sms();
+  if (g_max_ctas > 0 && g_max_ctas < sms) sms = g_max_ctas;
+  const int64_t items = (int64_t)p.num_m_blocks * p.num_n_groups;
+  int workers = (int)std::min<int64_t>(sms / kNCta, items);
+  if (workers < 1) workers = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(workers * kNCta));
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = S::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kNCta;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  O3V_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  return O3V_OK;
+}
+
+static void plan_tiles(GemmParams& p, int ncta, int n_groups_hint) {
+  p.num_m_blocks = (int32_t)ceil_div(p.M, 128 * ncta);
+  p.num_n_tiles = (int32_t)ceil_div(p.N, 256);
+  int groups = n_groups_hint < 1 ? 1 : n_groups_hint;
+  if (groups > p.num_n_tiles) groups = p.num_n_tiles;
+  p.tiles_per_group = (int32_t)ceil_div(p.num_n_tiles, groups);
+  p.num_n_groups = (int32_t)ceil_div(p.num_n_tiles, p.tiles_per_group);
+}
+
+// Number of vocab splits per m-block in K1.  Few splits keep the concurrently swept A panels
+// (hidden rows) L2-resident and W re-reads low; enough splits fill the persistent grid.
+static int fwd_groups(int64_t T, int64_t V, int ncta) {
+  if (g_fwd_groups > 0) return g_fwd_groups;
+  const int64_t num_m = ceil_div(T, 128 * ncta);
+  const int64_t n_tiles = ceil_div(V, 256);
+  const int64_t workers = num_sms() / ncta;
+  int64_t g = 4;
+  while (num_m * g < 2 * workers && g < n_tiles) g *= 2;     // small T: split the vocab further
+  if (g > n_tiles) g = n_tiles;
+  return (int)g;
+}
+
+// ------------------------------------------------------------------------------------
+// merge of partial statistics
+// ------------------------------------------------------------------------------------
+// parts [P, 3, T] -> either one merged triple [3, T] (triple_out) or (logp, lse).
+__global__ void merge_stats_kernel(const float* __restrict__ parts, int64_t P, int64_t T,
+                                   float* __restrict__ triple_out, float* __restrict__ logp,
+                                   float* __restrict__ lse) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  float M = -INFINITY;
+  for (int64_t i = 0; i < P; ++i) M = fmaxf(M, parts[(i * 3 + 0) * T + t]);
+  float s = 0.f, z = 0.f;
+  for (int64_t i = 0; i < P; ++i) {            // fixed order: deterministic
+    const float m = parts[(i * 3 + 0) * T + t];
+    const float e = (m == -INFINITY) ? 0.f : expf(m - M);
+    s += parts[(i * 3 + 1) * T + t] * e;
+    z += parts[(i * 3 + 2) * T + t];           // non-zero in the owner slice only
+  }
+  if (triple_out) {
+    triple_out[t] = M;
+    triple_out[T + t] = s;
+    triple_out[2 * T + t] = z;
+  } else {
+    const float l = M + logf(s);
+    if (lse) lse[t] = l;
+    if (logp) logp[t] = z - l;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// dlogits: P[t,v] = g[t] * ([v + v_offset == target[t]] - exp(z[t,v] - lse[t])), in place, bf16
+// ------------------------------------------------------------------------------------
+constexpr int kDlThreads = 256;
+__global__ void __launch_bounds__(kDlThreads)
+dlogits_kernel(__nv_bfloat16* __restrict__ z, int64_t T, int64_t V, int64_t ld, const float* __restrict__ lse,
+               const float* __restrict__ g, const int64_t* __restrict__ targets, int64_t v_offset,
+               int rows_per_cta) {
+  const int64_t t0 = (int64_t)blockIdx.x * rows_per_cta;
+  for (int r = 0; r < rows_per_cta; ++r) {
+    const int64_t t = t0 + r;
+    if (t >= T) return;
+    const float gt = g[t];
+    const float neg_l = -lse[t] * kLog2e;
+    const int64_t tc = targets[t] - v_offset;
+    uint4* row = reinterpret_cast<uint4*>(z + t * ld);
+    const int64_t nvec = V >> 3;                       // V % 8 == 0 (checked by the API)
+    for (int64_t i = threadIdx.x; i < nvec; i += kDlThreads) {
+      uint4 pk = (gt == 0.f) ? make_uint4(0, 0, 0, 0) : row[i];
+      if (gt != 0.f) {
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(h[j]);
+          float a = -gt * exp2f(fmaf(f.x, kLog2e, neg_l));
+          float b = -gt * exp2f(fmaf(f.y, kLog2e, neg_l));
+          const int64_t c = i * 8 + j * 2;
+          if (c == tc) a += gt;
+          if (c + 1 == tc) b += gt;
+          h[j] = __floats2bfloat162_rn(a, b);
+        }
+      }
+      row[i] = pk;
+    }
+  }
+}
+
+}  // namespace o3v
+
+using namespace o3v;
+
+extern "C" int o3v_set_tunable(const char* name, int value) {
+  if (!name) return O3V_ERR_INVALID_ARG;
+  std::string n(name);
+  if (n == "cta_pair") { if (value != 1 && value != 2) return O3V_ERR_INVALID_ARG; g_cta_pair = value; }
+  else if (n == "fwd_groups") g_fwd_groups = value;
+  else if (n == "max_ctas") g_max_ctas = value;
+  else return O3V_ERR_INVALID_ARG;
+  return O3V_OK;
+}
+
+extern "C" size_t o3v_lmhead_fwd_workspace_bytes(int64_t T, int64_t V, int64_t H) {
+  (void)H;
+  if (T <= 0 || V <= 0) return 0;
+  // worst case over the tunables: one part per n-tile
+  const int64_t groups = ceil_div(V, 256);
+  return (size_t)(groups * 3 * T) * sizeof(float);
+}
+
+extern "C" int o3v_lmhead_fwd(const void* hidden, const void* weight, const int64_t* targets,
+                              int64_t T, int64_t V, int64_t H, int64_t v_offset,
+                              float* stats, void* logits, int64_t ld_logits,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  if (!hidden || !weight || !targets || !stats || !workspace) return O3V_ERR_INVALID_ARG;
+  if (T <= 0 || V <= 0 || H <= 0 || v_offset < 0) return O3V_ERR_INVALID_ARG;
+  if (H % 64 != 0) return O3V_ERR_SHAPE;
+  if (T > 0x7fffffffLL - 512 || V > 0x7fffffffLL - 512) return O3V_ERR_SHAPE;
+  if (logits) {
+    if (V % 8 != 0 || ld_logits % 8 != 0 || ld_logits < V) return O3V_ERR_SHAPE;
+    if (reinterpret_cast<uintptr_t>(logits) & 15u) return O3V_ERR_ALIGNMENT;
+  }
+  int rc = check_device();
+  if (rc) return rc;
+  const int ncta = g_cta_pair;
+  GemmParams p = {};
+  p.M = T; p.N = V; p.K = H;
+  plan_tiles(p, ncta, fwd_groups(T, V, ncta));
+  if (workspace_bytes < (size_t)p.num_n_groups * 3 * T * sizeof(float)) return O3V_ERR_WORKSPACE;
+  p.targets = targets; p.v_offset = v_offset; p.parts = reinterpret_cast<float*>(workspace);
+  p.logits = reinterpret_cast<__nv_bfloat16*>(logits); p.ld_logits = ld_logits;
+  CUtensorMap tmA, tmB;
+  if ((rc = make_tmap_bf16(&tmA, hidden, H, T, H, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tmB, weight, H, V, H, 256 / ncta))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = (ncta == 1) ? launch_gemm<false, false, 1, EPI_STATS>(tmA, tmB, p, st)
+                   : launch_gemm<false, false, 2, EPI_STATS>(tmA, tmB, p, st);
+  if (rc) return rc;
+  merge_stats_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, st>>>(p.parts, p.num_n_groups, T, stats, nullptr, nullptr);
+  O3V_LAUNCH_CHECK();
+  return O3V_OK;
+}
+
+extern "C" int o3v_lmhead_merge_stats(const float* parts, int64_t P, int64_t T, float* logp, float* lse,
+                                      void* stream) {
+  if (!parts || (!logp && !lse) || P <= 0 || T <= 0) return O3V_ERR_INVALID_ARG;
+  int rc = check_device();
+  if (rc) return rc;
+  merge_stats_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, (cudaStream_t)stream>>>(parts, P, T, nullptr, logp, lse);
+  O3V_LAUNCH_CHECK();
+  return O3V_OK;
+}
+
+extern "C" int o3v_lmhead_dlogits(void* logits, int64_t T, int64_t V, int64_t ld_logits, const float* lse,
+                                  const float* grad_logp, const int64_t* targets, int64_t v_offset,
+                                  void* stream) {
+  if (!logits || !lse || !grad_logp || !targets || T <= 0 || V <= 0) return O3V_ERR_INVALID_ARG;
+  if (V % 8 != 0 || ld_logits % 8 != 0 || ld_logits < V) return O3V_ERR_SHAPE;
+  if (reinterpret_cast<uintptr_t>(logits) & 15u) return O3V_ERR_ALIGNMENT;
+  int rc = check_device();
+  if (rc) return rc;
+  // several waves of one-row CTAs; rows are 300 KB each so a CTA streams plenty of bytes
+  const int rows_per_cta = 1;
+  dlogits_kernel<<<(unsigned)ceil_div(T, rows_per_cta), kDlThreads, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<__nv_bfloat16*>(logits), T, V, ld_logits, lse, grad_logp, targets, v_offset, rows_per_cta);
+  O3V_LAUNCH_CHECK();
+  return O3V_OK;
+}
+
+extern "C" int o3v_lmhead_bwd_dhidden(const void* dlogits, int64_t ld_dlogits, const void* weight,
+                                      int64_t T, int64_t V, int64_t H, void* d_hidden, int32_t out_is_fp32,
+                                      void* stream) {
+  if (!dlogits || !weight || !d_hidden || T <= 0 || V <= 0 || H <= 0) return O3V_ERR_INVALID_ARG;
+  if (H % 8 != 0 || ld_dlogits % 8 != 0 || ld_dlogits < V) return O3V_ERR_SHAPE;
+  if (T > 0x7fffffffLL - 512 || V > 0x7fffffffLL - 512) return O3V_ERR_SHAPE;
+  if (reinterpret_cast<uintptr_t>(d_hidden) & 15u) return O3V_ERR_ALIGNMENT;
+  int rc = check_device();
+  if (rc) return rc;
+  const int ncta = g_cta_pair;
+  GemmParams p = {};
+  p.M = T; p.N = H; p.K = V;                       // dH[t,h] = sum_v P[t,v] W[v,h]
+  plan_tiles(p, ncta, (int)ceil_div(H, 256));       // one n-tile per item
+  p.out = d_hidden; p.ld_out = H; p.out_fp32 = out_is_fp32 ? 1 : 0;
+  CUtensorMap tmA, tmB;
+  if ((rc = make_tmap_bf16(&tmA, dlogits, V, T, ld_dlogits, 128))) return rc;   // A = P, K-major (K = V)
+  if ((rc = make_tmap_bf16(&tmB, weight, H, V, H, 64))) return rc;              // B = W, MN-major (N = H contiguous)
+  cudaStream_t st = (cudaStream_t)stream;
+  return (ncta == 1) ? launch_gemm<false, true, 1, EPI_STORE>(tmA, tmB, p, st)
+                     : launch_gemm<false, true, 2, EPI_STORE>(tmA, tmB, p, st);
+}
+
+extern "C" int o3v_lmhead_bwd_dweight(const void* dlogits, int64_t ld_dlogits, const void* hidden,
+                                      int64_t T, int64_t V, int64_t H, float* d_weight, int32_t accumulate,
+                                      void* stream) {
+  if (!dlogits || !hidden || !d_weight || T <= 0 || V <= 0 || H <= 0) return O3V_ERR_INVALID_ARG;
+  if (H % 8 != 0 || ld_dlogits % 8 != 0 || ld_dlogits < V) return O3V_ERR_SHAPE;
+  if (T > 0x7fffffffLL - 512 || V > 0x7fffffffLL - 512) return O3V_ERR_SHAPE;
+  if (reinterpret_cast<uintptr_t>(d_weight) & 15u) return O3V_ERR_ALIGNMENT;
+  int rc = check_device();
+  if (rc) return rc;
+  const int ncta = g_cta_pair;
+  GemmParams p = {};
+  p.M = V; p.N = H; p.K = T;                       // dW[v,h] = sum_t P[t,v] hidden[t,h]
+  plan_tiles(p, ncta, (int)ceil_div(H, 256));
+  p.out = d_weight; p.ld_out = H; p.out_fp32 = 1; p.accumulate = accumulate ? 1 : 0;
+  CUtensorMap tmA, tmB;
+  if ((rc = make_tmap_bf16(&tmA, dlogits, V, T, ld_dlogits, 64))) return rc;    // A = P^T, MN-major (M = V contiguous)
+  if ((rc = make_tmap_bf16(&tmB, hidden, H, T, H, 64))) return rc;              // B = hidden, MN-major
+  cudaStream_t st = (cudaStream_t)stream;
+  return (ncta == 1) ? launch_gemm<true, true, 1, EPI_ACCUM>(tmA, tmB, p, st)
+                     : launch_gemm<true, true, 2, EPI_ACCUM>(tmA, tmB, p, st);
+}

@@ -1,0 +1,349 @@
+// Warp-specialised, persistent tcgen05 GEMM for the lm_head hot path (sm_100a).
+//
+//   D[M, N] = A[M, K] . B[N, K]^T      bf16 x bf16 -> fp32 accumulators in TMEM
+//
+// One kernel template serves the three contractions of the path; they differ in operand
+// majorness (chosen so that NO tensor is ever transposed in HBM) and in the epilogue:
+//
+//   K1  logits tile = hidden . W^T        A K-major,  B K-major   EPI_STATS
+//       online (max, sum-exp) + target-logit capture per token row, carried in registers
+//       across the n-tiles of a work item; optional bf16 store of the tile for the backward
+//   K2a dHidden = P . W                   A K-major,  B MN-major  EPI_STORE (bf16 / fp32)
+//   K2b dW (+)= P^T . hidden              A MN-major, B MN-major  EPI_ACCUM (fp32 RMW)
+//
+// Structure (256 threads, 1 CTA per SM, optionally a cta_group::2 pair per tile):
+//   warp 0 / lane 0   TMA producer: cp.async.bulk.tensor 2-D boxes, 128B swizzle, into a
+//                     kStages-deep smem ring guarded by full/empty mbarriers
+//   warp 1 / lane 0   MMA issuer: tcgen05.mma (M=128 or 256 with cta_group::2, N=256, K=16),
+//                     tcgen05.commit releases smem stages and publishes accumulators
+//   warp 2            TMEM allocator (512 columns = 2 accumulator stages of 256)
+//   warps 4..7        epilogue: tcgen05.ld 32x32b (one accumulator row per thread), overlaps
+//                     the next tile's MMAs through the double-buffered accumulator
+// Work items are statically strided over the persistent grid; an item is an (m-block,
+// n-group) pair, n-groups fastest so that concurrently running CTAs share A panels in L2.
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace o3v {
+
+enum : int { EPI_STATS = 0, EPI_STORE = 1, EPI_ACCUM = 2 };
+
+struct GemmParams {
+  int64_t M, N, K;
+  int32_t num_m_blocks;     // ceil(M / (128 * ncta))
+  int32_t num_n_tiles;      // ceil(N / 256)
+  int32_t tiles_per_group;  // consecutive n-tiles per work item (online softmax state lives across them)
+  int32_t num_n_groups;     // ceil(num_n_tiles / tiles_per_group)
+  // EPI_STATS
+  const int64_t* targets;   // [M] global vocab ids
+  int64_t v_offset;         // first vocab id of this slice
+  float* parts;             // [num_n_groups, 3, M]: max, sum exp(z - max), target logit
+  __nv_bfloat16* logits;    // optional [M, ld_logits]
+  int64_t ld_logits;
+  // EPI_STORE / EPI_ACCUM
+  void* out;                // [M, ld_out] bf16 or fp32
+  int64_t ld_out;
+  int32_t out_fp32;
+  int32_t accumulate;
+};
+
+template <int kNCta>
+struct GemmShape {
+  static constexpr int BM = 128;                  // accumulator rows per CTA (TMEM lanes)
+  static constexpr int UMMA_M = BM * kNCta;
+  static constexpr int BN = 256;                  // UMMA_N = accumulator columns per stage
+  static constexpr int BK = 64;                   // one 128-byte swizzle atom of bf16
+  static constexpr int UMMA_K = 16;
+  static constexpr int LOAD_BN = BN / kNCta;      // B rows fetched by each CTA of the pair
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = LOAD_BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (kNCta == 1) ? 4 : 6;
+  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // +1024: manual alignment
+  static constexpr int TMEM_COLS = 512;
+};
+
+constexpr int kGemmThreads = 256;
+constexpr float kLog2e = 1.4426950408889634f;
+
+template <bool kAMN, bool kBMN, int kNCta, int kEpi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const GemmParams p) {
+  using S = GemmShape<kNCta>;
+  constexpr int BM = S::BM, BN = S::BN, BK = S::BK, STAGES = S::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  // 128B-swizzled tiles need 1024-byte aligned bases (in the shared window, identical in both CTAs of a pair)
+  const uint32_t raw_u32 = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_u32 + 1023u) & ~1023u) - raw_u32);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * S::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = (kNCta == 2) ? ptx::cluster_ctarank() : 0u;
+
+  if (kNCta == 2) ptx::cluster_sync();
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      ptx::mbar_init(&full[i], kNCta);       // producer arrivals (leader's barrier collects both CTAs)
+      ptx::mbar_init(&empty[i], 1);          // one tcgen05.commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tfull[i], 1);          // one tcgen05.commit
+      ptx::mbar_init(&tempty[i], kNCta * 4); // one arrival per epilogue warp of each CTA
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<kNCta>(tmem_slot, S::TMEM_COLS);
+  ptx::tc_fence_before();
+  if (kNCta == 2) ptx::cluster_sync(); else __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  const int num_workers = gridDim.x / kNCta;
+  const int worker = blockIdx.x / kNCta;
+  const int num_items = p.num_m_blocks * p.num_n_groups;
+  const int num_k_blocks = (int)((p.K + BK - 1) / BK);
+
+  if (warp == 0 && lane == 0) {
+    // ================================ TMA producer ================================
+    int stage = 0; uint32_t phase = 0;
+    for (int item = worker; item < num_items; item += num_workers) {
+      const int n_grp = item % p.num_n_groups, m_blk = item / p.num_n_groups;
+      const int m0 = m_blk * S::UMMA_M + (int)rank * BM;
+      const int t_begin = n_grp * p.tiles_per_group;
+      const int t_end = min(t_begin + p.tiles_per_group, p.num_n_tiles);
+      for (int nt = t_begin; nt < t_end; ++nt) {
+        const int n0 = nt * BN + (int)rank * S::LOAD_BN;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1u);
+          const int k0 = kb * BK;
+          uint8_t* sa = smem_a + stage * S::A_BYTES;
+          uint8_t* sb = smem_b + stage * S::B_BYTES;
+          if constexpr (kNCta == 1) {
+            ptx::mbar_expect_tx(&full[stage], S::STAGE_BYTES);
+          } else {
+            if (rank == 0) ptx::mbar_expect_tx(&full[stage], 2 * S::STAGE_BYTES);
+            else ptx::mbar_arrive_cluster(&full[stage], 0);
+          }
+          auto load = [&](void* dst, const CUtensorMap* tm, int c0, int c1) {
+            if constexpr (kNCta == 1) ptx::tma_load_2d(dst, tm, &full[stage], c0, c1);
+            else ptx::tma_load_2d_2sm(dst, tm, &full[stage], c0, c1);
+          };
+          if constexpr (!kAMN) {
+            load(sa, &tmA, k0, m0);                                   // [128 rows][64 k] K-major
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i) load(sa + i * (BK * 128), &tmA, m0 + 64 * i, k0);   // [64 k][64 m] atoms
+          }
+          if constexpr (!kBMN) {
+            load(sb, &tmB, k0, n0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < S::LOAD_BN / 64; ++i) load(sb + i * (BK * 128), &tmB, n0 + 64 * i, k0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ================================ MMA issuer (leader CTA only) ================================
+    if (rank == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(S::UMMA_M, BN, kAMN, kBMN);
+      // K-major SW128: rows of 128 B, 8-row groups 1024 B apart (SBO), one atom along K (LBO unused)
+      // MN-major SW128: 64-element atoms along MN 8 KB apart (LBO), 8-k groups 1024 B apart (SBO)
+      constexpr uint32_t a_lbo = kAMN ? BK * 128 : 0, b_lbo = kBMN ? BK * 128 : 0;
+      constexpr uint32_t a_kstep = kAMN ? S::UMMA_K * 128 : S::UMMA_K * 2;
+      constexpr uint32_t b_kstep = kBMN ? S::UMMA_K * 128 : S::UMMA_K * 2;
+      int stage = 0; uint32_t phase = 0; uint32_t acc_iter = 0;
+      for (int item = worker; item < num_items; item += num_workers) {
+        const int n_grp = item % p.num_n_groups;
+        const int t_begin = n_grp * p.tiles_per_group;
+        const int t_end = min(t_begin + p.tiles_per_group, p.num_n_tiles);
+        for (int nt = t_begin; nt < t_end; ++nt, ++acc_iter) {
+          const uint32_t a = acc_iter & 1u, aphase = (acc_iter >> 1) & 1u;
+          ptx::mbar_wait(&tempty[a], aphase ^ 1u);           // epilogue has drained this accumulator
+          ptx::tc_fence_after();
+          const uint32_t tmem_d = tmem_base + a * BN;
+          for (int kb = 0; kb < num_k_blocks; ++kb) {
+            ptx::mbar_wait(&full[stage], phase);             // TMA bytes have landed (both CTAs)
+            ptx::tc_fence_after();
+            const uint32_t a_base = ptx::smem_u32(smem_a + stage * S::A_BYTES);
+            const uint32_t b_base = ptx::smem_u32(smem_b + stage * S::B_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / S::UMMA_K; ++k) {
+              const uint64_t da = ptx::make_smem_desc(a_base + k * a_kstep, a_lbo, 1024);
+              const uint64_t db = ptx::make_smem_desc(b_base + k * b_kstep, b_lbo, 1024);
+              ptx::umma_bf16<kNCta>(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            ptx::umma_commit<kNCta>(&empty[stage]);          // frees the smem stage when the MMAs retire
+            if (kb == num_k_blocks - 1) ptx::umma_commit<kNCta>(&tfull[a]);   // accumulator ready
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+      if (kNCta == 2 && acc_iter > 0) {
+        // the peer's last remote arrivals must land before this CTA may exit
+        const uint32_t last = acc_iter - 1;
+        ptx::mbar_wait(&tempty[last & 1u], (last >> 1) & 1u);
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue warps ================================
+    const int q = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int row_in_tile = q * 32 + lane;
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t acc_iter = 0;
+    for (int item = worker; item < num_items; item += num_workers) {
+      const int n_grp = item % p.num_n_groups, m_blk = item / p.num_n_groups;
+      const int64_t row = (int64_t)m_blk * S::UMMA_M + (int64_t)rank * BM + row_in_tile;
+      const bool row_ok = row < p.M;
+      const int t_begin = n_grp * p.tiles_per_group;
+      const int t_end = min(t_begin + p.tiles_per_group, p.num_n_tiles);
+
+      float run_max = -INFINITY, run_sum = 0.f, tgt_logit = 0.f;
+      int64_t tgt_col = -1;
+      if constexpr (kEpi == EPI_STATS) {
+        if (row_ok) tgt_col = p.targets[row] - p.v_offset;   // may fall outside this slice
+        if (tgt_col >= p.N) tgt_col = -1;                    // (never match a zero-filled column)
+      }
+
+      for (int nt = t_begin; nt < t_end; ++nt, ++acc_iter) {
+        const uint32_t a = acc_iter & 1u, aphase = (acc_iter >> 1) & 1u;
+        ptx::mbar_wait(&tfull[a], aphase);
+        ptx::tc_fence_after();
+        const int64_t n0 = (int64_t)nt * BN;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(tmem_row + a * BN + c * 32, v);
+          ptx::tmem_ld_wait();
+          const int64_t col0 = n0 + c * 32;
+          if constexpr (kEpi == EPI_STATS) {
+            if (p.logits != nullptr && row_ok) {
+              // bf16 copy of the tile for the chunked backward (vector granularity: 8 columns)
+              __nv_bfloat16* dst = p.logits + row * p.ld_logits + col0;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (col0 + j * 8 < p.N) {
+                  uint4 pk;
+                  __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]));
+                  __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
+                  __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5]));
+                  __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]));
+                  pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                  pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                  *reinterpret_cast<uint4*>(dst + j * 8) = pk;
+                }
+              }
+            }
+            if (col0 + 32 > p.N) {                 // ragged last tile: TMA zero-filled columns are not vocabulary
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j >= p.N) v[j] = __float_as_uint(-INFINITY);
+            }
+            if (tgt_col >= col0 && tgt_col < col0 + 32) {   // rare: once per row over the whole sweep
+              const int jj = (int)(tgt_col - col0);
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j == jj) tgt_logit = __uint_as_float(v[j]);
+            }
+            float cmax = __uint_as_float(v[0]);
+#pragma unroll
+            for (int j = 1; j < 32; ++j) cmax = fmaxf(cmax, __uint_as_float(v[j]));
+            const float new_max = fmaxf(run_max, cmax);
+            if (new_max != -INFINITY) {            // (an all-masked chunk before any valid column cannot occur)
+              const float neg = -new_max * kLog2e;
+              float acc = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc += exp2f(fmaf(__uint_as_float(v[j]), kLog2e, neg));
+              run_sum = run_sum * exp2f(fmaf(run_max, kLog2e, neg)) + acc;
+              run_max = new_max;
+            }
+          } else if constexpr (kEpi == EPI_STORE) {
+            if (row_ok) {
+              if (p.out_fp32) {
+                float* dst = reinterpret_cast<float*>(p.out) + row * p.ld_out + col0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (col0 + j * 4 < p.N)
+                    *reinterpret_cast<uint4*>(dst + j * 4) = make_uint4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+              } else {
+                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ld_out + col0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  if (col0 + j * 8 < p.N) {
+                    uint4 pk;
+                    __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]));
+                    __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
+                    __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5]));
+                    __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]));
+                    pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                    pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                    *reinterpret_cast<uint4*>(dst + j * 8) = pk;
+                  }
+                }
+              }
+            }
+          } else {  // EPI_ACCUM: fp32 read-modify-write
+            if (row_ok) {
+              float* dst = reinterpret_cast<float*>(p.out) + row * p.ld_out + col0;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (col0 + j * 4 < p.N) {
+                  float4 o = make_float4(__uint_as_float(v[j * 4]), __uint_as_float(v[j * 4 + 1]),
+                                         __uint_as_float(v[j * 4 + 2]), __uint_as_float(v[j * 4 + 3]));
+                  if (p.accumulate) {
+                    const float4 old = *reinterpret_cast<const float4*>(dst + j * 4);
+                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                  }
+                  *reinterpret_cast<float4*>(dst + j * 4) = o;
+                }
+              }
+            }
+          }
+        }
+        // all tcgen05.ld of this warp have completed (wait::ld above): hand the accumulator back
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (kNCta == 1) ptx::mbar_arrive(&tempty[a]);
+          else ptx::mbar_arrive_cluster(&tempty[a], 0);
+        }
+      }
+
+      if constexpr (kEpi == EPI_STATS) {
+        if (row_ok) {
+          float* part = p.parts + (int64_t)n_grp * 3 * p.M;
+          part[row] = run_max;
+          part[p.M + row] = run_sum;
+          part[2 * p.M + row] = tgt_logit;
+        }
+      }
+    }
+  }
+
+  // ================================ teardown ================================
+  ptx::tc_fence_before();
+  if (kNCta == 2) ptx::cluster_sync(); else __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<kNCta>(tmem_base, S::TMEM_COLS);
+  }
+}
+
+}  // namespace o3v

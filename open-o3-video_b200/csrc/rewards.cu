@@ -1,0 +1,243 @@
+// K4: grounded (spatio-temporal) rewards on parsed rollouts, fp64, struct of arrays.
+//
+// Replaces the numeric cores of the reference's reward_func.py (see include/o3v.h for the
+// line map).  HBM-bound: 16 lanes cooperate on one rollout (lane = prediction index, so a
+// rollout's [P]/[C] rows are read with coalesced 128-byte requests); ground truth is shared
+// by the G rollouts of a prompt and is served from L1/L2 after the first touch.
+// Arithmetic follows the reference's float64 operation order; explicit __d*_rn intrinsics
+// keep nvcc from contracting mul+add into FMA so that results are bit-identical to numpy's.
+#include "common.cuh"
+
+namespace o3v {
+
+constexpr int kLanes = 16;             // lanes per rollout
+constexpr int kRewardThreads = 256;    // 16 rollouts per CTA
+
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+
+// reward_func.py:356-386 with boxA = GT, boxB = pred (validity of boxB checked by caller).
+__device__ __forceinline__ double box_iou(const double a[4], const double b[4]) {
+  const double xA = fmax(a[0], b[0]), yA = fmax(a[1], b[1]);
+  const double xB = fmin(a[2], b[2]), yB = fmin(a[3], b[3]);
+  const double inter = dmul(fmax(0.0, dsub(xB, xA)), fmax(0.0, dsub(yB, yA)));
+  const double areaA = dmul(dsub(a[2], a[0]), dsub(a[3], a[1]));
+  const double areaB = dmul(dsub(b[2], b[0]), dsub(b[3], b[1]));
+  const double uni = dsub(dadd(areaA, areaB), inter);
+  return uni > 0.0 ? __ddiv_rn(inter, uni) : 0.0;
+}
+
+__device__ __forceinline__ void load4(const double* p, double o[4]) {
+  const double2 lo = *reinterpret_cast<const double2*>(p);
+  const double2 hi = *reinterpret_cast<const double2*>(p + 2);
+  o[0] = lo.x; o[1] = lo.y; o[2] = hi.x; o[3] = hi.y;
+}
+
+// sum v over the 16 lanes of a rollout IN INDEX ORDER (as the reference's Python loop does),
+// result valid in every lane.  `base` = first lane of the group within the warp.
+__device__ __forceinline__ double ordered_group_sum(double v, int count, int base, unsigned gmask, double acc) {
+  for (int i = 0; i < kLanes; ++i) {
+    const double x = __shfl_sync(gmask, v, base + i);
+    if (i < count) acc = dadd(acc, x);
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(kRewardThreads)
+rewards_kernel(const o3v_rewards_soa s, double* __restrict__ out) {
+  const int lane = threadIdx.x & (kLanes - 1);
+  const int64_t r = (int64_t)blockIdx.x * (kRewardThreads / kLanes) + (threadIdx.x / kLanes);
+  const int base = (threadIdx.x & 31) & ~(kLanes - 1);
+  const unsigned gmask = 0xffffu << base;
+  if (r >= s.R) return;   // whole 16-lane group leaves together
+  const int64_t q = r / s.G;
+
+  const int flags = s.flags[r];
+  const int task = s.task[q];
+  const bool has_think = flags & O3V_RF_HAS_THINK;
+  const bool has_answer = flags & O3V_RF_HAS_ANSWER;
+  const bool general = (task == O3V_TASK_GENERAL_MCQ || task == O3V_TASK_GENERAL_FREEFORM);
+  const bool temporal = (task == O3V_TASK_TEMPORAL_QA || task == O3V_TASK_TEMPORAL_QA_MCQ);
+
+  double r_tiou = 0.0, r_viou = 0.0, r_seg = 0.0, r_point = 0.0, r_spatial = 0.0;
+
+  // ---- ans_tiou_reward (reward_func.py:99-143)
+  if (temporal && (flags & O3V_RF_ANS_SEG)) {
+    const double s1 = s.ans_seg[r * 2], e1 = s.ans_seg[r * 2 + 1];
+    const double s2 = s.gt_seg[q * 2], e2 = s.gt_seg[q * 2 + 1];
+    if (!(e1 < s1)) {                                                   // :128
+      const double inter = fmax(0.0, dsub(fmin(e1, e2), fmax(s1, s2))); // :138-140
+      const double uni = dsub(fmax(e1, e2), fmin(s1, s2));              // :141
+      r_tiou = (uni != 0.0) ? __ddiv_rn(inter, uni) : 0.0;              // :142
+    }
+  }
+
+  // GT box of the visual-QA tasks, rescaled (convert_coord_format_gqa, :349-354)
+  double gvb[4] = {0, 0, 0, 0};
+  const bool has_gvb = (task == O3V_TASK_VISUAL_QA) && (s.gt_flags[q] & O3V_GF_VBOX);
+  if (has_gvb) {
+    double raw[4];
+    load4(s.gt_vbox + q * 4, raw);
+    const double W = s.image_size[q * 2], H = s.image_size[q * 2 + 1];
+    const double rw = s.image_refine[q * 2], rh = s.image_refine[q * 2 + 1];
+    gvb[0] = __ddiv_rn(dmul(raw[0], rw), W); gvb[1] = __ddiv_rn(dmul(raw[1], rh), H);
+    gvb[2] = __ddiv_rn(dmul(raw[2], rw), W); gvb[3] = __ddiv_rn(dmul(raw[3], rh), H);
+  }
+
+  // ---- ans_viou_reward (:196-226)
+  if (has_gvb && (flags & O3V_RF_ANS_BOX)) {
+    double pb[4];
+    load4(s.ans_box + r * 4, pb);
+    r_viou = box_iou(gvb, pb);
+  }
+
+  const int n_times = s.n_times[r];
+
+  // ---- thk_temporal_segment_reward (:396, :416-420)
+  if (has_think && !(task == O3V_TASK_VISUAL_QA || task == O3V_TASK_TS_FREEFORM || general)) {
+    const double g0 = s.gt_seg[q * 2], g1 = s.gt_seg[q * 2 + 1];
+    int hits = 0;
+    for (int p = lane; p < n_times; p += kLanes) {
+      const double t = s.think_times[r * s.P + p];
+      hits += (g0 <= t && t <= g1) ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = kLanes / 2; o > 0; o >>= 1) hits += __shfl_xor_sync(gmask, hits, o);
+    if (n_times > 0) r_seg = __ddiv_rn((double)hits, (double)n_times);   // exact small integers
+  }
+
+  const int nk = s.n_kf[q];
+  const double* kft = s.kf_time + q * s.K;
+
+  // ---- thk_temporal_point_reward: adaptive temporal proximity (:439, :452-467)
+  if (has_think && !(task == O3V_TASK_VISUAL_QA || temporal || general) && n_times > 0) {
+    const double sp = s.step_percent;
+    const double sigma = (sp < 0.75) ? dmul(4.0, dsub(1.0, sp)) : 1.0;  // :459-462
+    const double two_s2 = dmul(2.0, dmul(sigma, sigma));
+    double total = 0.0;
+    for (int p0 = 0; p0 < n_times; p0 += kLanes) {
+      const int p = p0 + lane;
+      double score = 0.0;
+      if (p < n_times) {
+        const double t = s.think_times[r * s.P + p];
+        double d = INFINITY;
+        for (int k = 0; k < nk; ++k) d = fmin(d, fabs(dsub(t, kft[k])));   // :457
+        score = exp(__ddiv_rn(-dmul(d, d), two_s2));                       // :463
+      }
+      total = ordered_group_sum(score, min(kLanes, n_times - p0), base, gmask, total);
+    }
+    r_point = __ddiv_rn(total, (double)n_times);                           // :467
+  }
+
+  // ---- thk_spatial_reward (:484-603)
+  if (has_think && has_answer) {
+    if (task == O3V_TASK_VISUAL_QA) {                                      // :490-525
+      const int nb = s.n_tboxes[r];
+      if (nb > 0 && has_gvb) {
+        const unsigned valid = s.tbox_valid[r];
+        double best = 0.0;
+        for (int b = lane; b < nb; b += kLanes) {
+          if ((valid >> b) & 1u) {
+            double pb[4];
+            load4(s.think_box + (r * s.Tb + b) * 4, pb);
+            best = fmax(best, box_iou(gvb, pb));
+          }
+        }
+#pragma unroll
+        for (int o = kLanes / 2; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(gmask, best, o));
+        r_spatial = best;
+      }
+    } else if (!(temporal || general)) {                                   // :528
+      const int nc = s.n_claims[r];
+      if (nc > 0) {
+        const double W = s.image_size[q * 2], H = s.image_size[q * 2 + 1];
+        double total = 0.0;
+        for (int c0 = 0; c0 < nc; c0 += kLanes) {
+          const int c = c0 + lane;
+          double score = 0.0;
+          if (c < nc) {
+            const double t = s.claim_t[r * s.C + c];
+            // temporal gating (:550-560): one-sided signed test, strict '<' keeps the first
+            int kbest = -1;
+            double dbest = INFINITY, tbest = -1.0;
+            for (int k = 0; k < nk; ++k) {
+              const double g = kft[k];
+              if (dsub(g, t) < 1.0) {
+                const double d = fabs(dsub(g, t));
+                if (d < dbest) { dbest = d; tbest = g; kbest = k; }
+              }
+            }
+            // :561 sentinel compare on the VALUE (a key frame at exactly -1 s is "none")
+            if (kbest >= 0 && tbest != -1.0) {
+              // :566-569 first key frame whose time equals the chosen one
+              int kf = kbest;
+              for (int k = 0; k < nk; ++k) if (kft[k] == tbest) { kf = k; break; }
+              const int nb = s.claim_nbox[r * s.C + c];
+              const unsigned valid = s.claim_valid[r * s.C + c];
+              const double* cb = s.claim_box + ((r * s.C + c) * (int64_t)s.Bc) * 4;
+              const int nobj = s.n_obj[q * s.K + kf];
+              double max_iou = 0.0;
+              for (int o = 0; o < nobj; ++o) {                              // :575
+                const int ng = s.n_gtbox[(q * s.K + kf) * s.O + o];
+                if (ng <= 0) continue;                                      // :596 empty list
+                double acc = 0.0;
+                for (int gi = 0; gi < ng; ++gi) {                           // :590
+                  double nb4[4], g4[4];
+                  load4(s.gt_box + ((((q * s.K + kf) * s.O + o) * (int64_t)s.Gb) + gi) * 4, nb4);
+                  g4[0] = dmul(nb4[0], W); g4[1] = dmul(nb4[1], H);         // :337-346
+                  g4[2] = dmul(nb4[2], W); g4[3] = dmul(nb4[3], H);
+                  double best = 0.0;
+                  bool first = true;
+                  for (int b = 0; b < nb; ++b) {                            // :592-593 max(list)
+                    double v = 0.0;
+                    if ((valid >> b) & 1u) { double pb[4]; load4(cb + b * 4, pb); v = box_iou(g4, pb); }
+                    best = first ? v : fmax(best, v);
+                    first = false;
+                  }
+                  acc = dadd(acc, best);                                    // :597 sum(...)
+                }
+                const double iou = __ddiv_rn(acc, (double)ng);
+                if (iou > max_iou) max_iou = iou;                           // :598-599
+              }
+              score = max_iou;
+            }
+          }
+          total = ordered_group_sum(score, min(kLanes, nc - c0), base, gmask, total);   // :601
+        }
+        r_spatial = __ddiv_rn(total, (double)nc);                           // :603
+      }
+    }
+  }
+
+  if (lane == 0) {
+    double* o = out + r * 5;
+    o[0] = r_tiou; o[1] = r_viou; o[2] = r_seg; o[3] = r_point; o[4] = r_spatial;
+  }
+}
+
+}  // namespace o3v
+
+extern "C" int o3v_grounded_rewards(const o3v_rewards_soa* soa, double* out, void* stream) {
+  if (!soa || !out) return O3V_ERR_INVALID_ARG;
+  const o3v_rewards_soa& s = *soa;
+  if (s.R < 0 || s.G <= 0 || (s.R % s.G) != 0) return O3V_ERR_INVALID_ARG;
+  if (s.P < 0 || s.C < 0 || s.Bc < 0 || s.Bc > 32 || s.Tb < 0 || s.Tb > 32 || s.K < 0 || s.O < 0 || s.Gb < 0)
+    return O3V_ERR_INVALID_ARG;
+  if (!s.flags || !s.ans_seg || !s.ans_box || !s.n_times || !s.think_times || !s.n_claims || !s.claim_t ||
+      !s.claim_nbox || !s.claim_valid || !s.claim_box || !s.n_tboxes || !s.tbox_valid || !s.think_box ||
+      !s.task || !s.gt_flags || !s.gt_seg || !s.gt_vbox || !s.image_size || !s.image_refine || !s.n_kf ||
+      !s.kf_time || !s.n_obj || !s.n_gtbox || !s.gt_box)
+    return O3V_ERR_INVALID_ARG;
+  const uintptr_t al = (uintptr_t)s.ans_box | (uintptr_t)s.claim_box | (uintptr_t)s.think_box |
+                       (uintptr_t)s.gt_vbox | (uintptr_t)s.gt_box;
+  if (al & 15u) return O3V_ERR_ALIGNMENT;
+  int rc = o3v::check_device();
+  if (rc) return rc;
+  if (s.R == 0) return O3V_OK;
+  const int per_cta = o3v::kRewardThreads / o3v::kLanes;
+  const unsigned grid = (unsigned)((s.R + per_cta - 1) / per_cta);
+  o3v::rewards_kernel<<<grid, o3v::kRewardThreads, 0, (cudaStream_t)stream>>>(s, out);
+  O3V_LAUNCH_CHECK();
+  return O3V_OK;
+}

@@ -1,0 +1,228 @@
+"""Fused lm_head -> log-softmax -> gather (K1) with its chunked fused backward (K2), and the
+whole-step `fused_logprob_gspo`.
+
+Replaces the reference's `_get_per_token_logps`
+(src/r1-v/src/open_r1/trainer/grpo_trainer.py:371-384, whose `model(...).logits` ends in
+transformers' lm_head = nn.Linear(H, V, bias=False)) and its autograd backward.  The
+[tokens x vocab] logits are never materialised in the forward; the backward materialises
+bf16 dlogits for one token chunk at a time ("backward").
+"""
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .gspo import _need_cuda, _p, _stream, gspo_raw
+
+# token chunk of the fused fwd+bwd: bounds the bf16 dlogits buffer (chunk x V x 2 bytes)
+DEFAULT_CHUNK_TOKENS = 32768
+# autograd path: keep bf16 logits for backward when they fit in this many bytes, else recompute
+SAVE_LOGITS_BYTES = 24 << 30
+
+
+def _check_head(hidden, weight, targets):
+    _need_cuda(hidden, weight, targets)
+    if hidden.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
+        raise TypeError("hidden and weight must be bf16 (got %s, %s)" % (hidden.dtype, weight.dtype))
+    if hidden.dim() != 2 or weight.dim() != 2 or hidden.shape[1] != weight.shape[1]:
+        raise ValueError("hidden [T, H], weight [V, H] expected")
+    if targets.shape != (hidden.shape[0],):
+        raise ValueError("targets must be [T]")
+
+
+def lmhead_stats(hidden, weight, targets, v_offset=0, logits_out=None):
+    """K1 on one vocab slice -> stats [3, T] fp32 (row max, sum exp(z - max), target logit).
+    `logits_out` ([T, ld] bf16, optional) also receives the bf16 logits."""
+    T, H = hidden.shape
+    V = weight.shape[0]
+    lib = _lib.load()
+    dev = hidden.device
+    stats = torch.empty(3, T, dtype=torch.float32, device=dev)
+    ws = torch.empty(int(lib.o3v_lmhead_fwd_workspace_bytes(T, V, H)), dtype=torch.uint8, device=dev)
+    ld = 0 if logits_out is None else logits_out.stride(0)
+    with torch.cuda.device(dev):
+        _lib.check(lib.o3v_lmhead_fwd(_p(hidden), _p(weight), _p(targets), T, V, H, int(v_offset), _p(stats),
+                                      _p(logits_out), ld, _p(ws), ws.numel(), _stream()), "o3v_lmhead_fwd")
+    return stats
+
+
+def merge_stats(parts):
+    """parts [P, 3, T] -> (logp [T], lse [T])."""
+    P, _, T = parts.shape
+    logp = torch.empty(T, dtype=torch.float32, device=parts.device)
+    lse = torch.empty(T, dtype=torch.float32, device=parts.device)
+    with torch.cuda.device(parts.device):
+        _lib.check(_lib.load().o3v_lmhead_merge_stats(_p(parts), P, T, _p(logp), _p(lse), _stream()),
+                   "o3v_lmhead_merge_stats")
+    return logp, lse
+
+
+def _gather_stats(stats, group):
+    """Vocab-parallel exchange: only the per-token (max, sum-exp, target-logit) triples cross
+    NVLink (12 bytes per token per rank)."""
+    if group is None:
+        return stats.unsqueeze(0)
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    out = torch.empty((world,) + tuple(stats.shape), dtype=stats.dtype, device=stats.device)
+    dist.all_gather_into_tensor(out, stats.contiguous(), group=group)
+    return out
+
+
+def dlogits_(logits, lse, grad_logp, targets, v_offset=0, V=None):
+    """In place: logits[t, v] <- g[t] * (onehot - softmax)."""
+    T = logits.shape[0]
+    V = logits.shape[1] if V is None else V
+    with torch.cuda.device(logits.device):
+        _lib.check(_lib.load().o3v_lmhead_dlogits(_p(logits), T, V, logits.stride(0), _p(lse), _p(grad_logp),
+                                                  _p(targets), int(v_offset), _stream()), "o3v_lmhead_dlogits")
+    return logits
+
+
+def bwd_dhidden(dlogits, weight, out=None, fp32=False):
+    T, V = dlogits.shape
+    H = weight.shape[1]
+    if out is None:
+        out = torch.empty(T, H, dtype=torch.float32 if fp32 else torch.bfloat16, device=dlogits.device)
+    with torch.cuda.device(dlogits.device):
+        _lib.check(_lib.load().o3v_lmhead_bwd_dhidden(_p(dlogits), dlogits.stride(0), _p(weight), T, V, H, _p(out),
+                                                      1 if out.dtype == torch.float32 else 0, _stream()),
+                   "o3v_lmhead_bwd_dhidden")
+    return out
+
+
+def bwd_dweight(dlogits, hidden, d_weight, accumulate):
+    T, V = dlogits.shape
+    H = hidden.shape[1]
+    with torch.cuda.device(dlogits.device):
+        _lib.check(_lib.load().o3v_lmhead_bwd_dweight(_p(dlogits), dlogits.stride(0), _p(hidden), T, V, H,
+                                                      _p(d_weight), 1 if accumulate else 0, _stream()),
+                   "o3v_lmhead_bwd_dweight")
+    return d_weight
+
+
+class _FusedLogprobFn(torch.autograd.Function):
+    """logp[t] = log_softmax(hidden[t] . W^T)[targets[t]] with a chunked fused backward."""
+
+    @staticmethod
+    def forward(ctx, hidden, weight, targets, v_offset, group, chunk_tokens):
+        T, H = hidden.shape
+        V = weight.shape[0]
+        need_grad = hidden.requires_grad or weight.requires_grad
+        keep = need_grad and (T * V * 2 <= SAVE_LOGITS_BYTES)
+        logits = torch.empty(T, V, dtype=torch.bfloat16, device=hidden.device) if keep else None
+        stats = lmhead_stats(hidden, weight, targets, v_offset, logits)
+        logp, lse = merge_stats(_gather_stats(stats, group))
+        ctx.save_for_backward(hidden, weight, targets, lse)
+        ctx.logits, ctx.v_offset, ctx.group, ctx.chunk_tokens = logits, v_offset, group, chunk_tokens
+        ctx.mark_non_differentiable(lse)
+        return logp, lse
+
+    @staticmethod
+    def backward(ctx, g_logp, _g_lse):
+        hidden, weight, targets, lse = ctx.saved_tensors
+        T, H = hidden.shape
+        V = weight.shape[0]
+        g = g_logp.to(torch.float32).contiguous()
+        d_hidden = torch.empty(T, H, dtype=torch.bfloat16, device=hidden.device)
+        d_weight = torch.empty(V, H, dtype=torch.float32, device=hidden.device)
+        chunk = min(T, ctx.chunk_tokens)
+        zbuf = None if ctx.logits is not None else torch.empty(chunk, V, dtype=torch.bfloat16, device=hidden.device)
+        first = True
+        for s in range(0, T, chunk):
+            e = min(T, s + chunk)
+            if ctx.logits is not None:
+                z = ctx.logits[s:e]
+            else:                                   # recompute this chunk's logits (forward kept nothing)
+                z = zbuf[: e - s]
+                lmhead_stats(hidden[s:e], weight, targets[s:e], ctx.v_offset, z)
+            dlogits_(z, lse[s:e], g[s:e], targets[s:e], ctx.v_offset)
+            bwd_dhidden(z, weight, out=d_hidden[s:e])
+            bwd_dweight(z, hidden[s:e], d_weight, accumulate=not first)
+            first = False
+        ctx.logits = None
+        if ctx.group is not None:                   # partial sums over vocab slices
+            import torch.distributed as dist
+            dist.all_reduce(d_hidden, group=ctx.group)
+        return d_hidden, d_weight.to(weight.dtype), None, None, None, None
+
+
+def fused_logprob(hidden: torch.Tensor, weight: torch.Tensor, targets: torch.Tensor, *, v_offset: int = 0,
+                  group=None, chunk_tokens: int = DEFAULT_CHUNK_TOKENS, return_lse: bool = False):
+    """hidden [T, H] bf16, weight [V, H] bf16 (rows v_offset.. of lm_head.weight when vocab
+    sharded over `group`), targets [T] int64 global ids -> logp [T] fp32 (autograd-enabled)."""
+    hidden = hidden.contiguous()
+    weight = weight.contiguous()
+    targets = targets.to(torch.int64).contiguous()
+    _check_head(hidden, weight, targets)
+    logp, lse = _FusedLogprobFn.apply(hidden, weight, targets, int(v_offset), group, int(chunk_tokens))
+    return (logp, lse) if return_lse else logp
+
+
+def per_token_logps(hidden: torch.Tensor, weight: torch.Tensor, input_ids: torch.Tensor, **kw) -> torch.Tensor:
+    """The reference's contract (grpo_trainer.py:371-384): hidden [B, L, H] (final hidden
+    states of `input_ids` [B, L]) -> [B, L-1]: log p(input_ids[:, t+1] | ..t)."""
+    B, L, H = hidden.shape
+    h = hidden[:, :-1, :].reshape(B * (L - 1), H)          # :376 drop the last position
+    tgt = input_ids[:, 1:].reshape(B * (L - 1))            # :377 drop the first id
+    return fused_logprob(h, weight, tgt, **kw).view(B, L - 1)
+
+
+def fused_logprob_gspo(hidden: torch.Tensor, weight: torch.Tensor, completion_ids: torch.Tensor,
+                       ref_per_token_logps: torch.Tensor, completion_mask: torch.Tensor,
+                       rewards_per_func: torch.Tensor, num_generations: int, beta: float,
+                       epsilon_low: float = 0.2, epsilon_high: float = 0.2, gspo: bool = True,
+                       old_per_token_logps: Optional[torch.Tensor] = None, *, v_offset: int = 0, group=None,
+                       chunk_tokens: int = DEFAULT_CHUNK_TOKENS, need_grad: bool = True,
+                       d_weight_out: Optional[torch.Tensor] = None):
+    """The whole policy-objective step in one call: per-token log-probs, KL, group advantages,
+    GSPO loss AND the gradients w.r.t. hidden and lm_head.weight (grpo_trainer.py:612-613,
+    635-636, 658-706 + their backward), chunked over whole sequences.
+
+    hidden [N, Tc, H] bf16: final hidden states at the positions that PREDICT each completion
+    token; completion_ids / ref / mask / old: [N, Tc]; rewards_per_func [N, F].
+    Returns dict(loss, per_token_logps, advantages, mean_kl, completion_length, reward_std,
+    d_hidden [N, Tc, H] bf16, d_weight [V, H] fp32).
+    """
+    N, Tc, H = hidden.shape
+    V = weight.shape[0]
+    dev = hidden.device
+    hidden2 = hidden.reshape(N * Tc, H).contiguous()
+    weight = weight.contiguous()
+    targets = completion_ids.to(torch.int64).reshape(N * Tc).contiguous()
+    _check_head(hidden2, weight, targets)
+    f32 = lambda t: None if t is None else t.detach().to(torch.float32).contiguous()
+    ref, old, rpf = f32(ref_per_token_logps), f32(old_per_token_logps), f32(rewards_per_func)
+    mask = completion_mask.to(torch.int32).contiguous()
+
+    seqs = max(1, min(N, chunk_tokens // Tc))
+    n_chunks = -(-N // seqs)
+    seqs = -(-N // n_chunks)                                  # even out the chunks
+    logp = torch.empty(N, Tc, dtype=torch.float32, device=dev)
+    zbuf = torch.empty(seqs * Tc, V, dtype=torch.bfloat16, device=dev) if need_grad else None
+    d_hidden = torch.empty(N * Tc, H, dtype=torch.bfloat16, device=dev) if need_grad else None
+    d_weight = None
+    if need_grad:
+        d_weight = d_weight_out if d_weight_out is not None else torch.empty(V, H, dtype=torch.float32, device=dev)
+    state = {}
+    for ci, n0 in enumerate(range(0, N, seqs)):
+        n1 = min(N, n0 + seqs)
+        s, e = n0 * Tc, n1 * Tc
+        z = zbuf[: e - s] if need_grad else None
+        stats = lmhead_stats(hidden2[s:e], weight, targets[s:e], v_offset, z)
+        lp, lse = merge_stats(_gather_stats(stats, group))
+        logp[n0:n1] = lp.view(n1 - n0, Tc)
+        state, g, _ = gspo_raw(logp[n0:n1], ref[n0:n1], mask[n0:n1], rpf, num_generations, beta, epsilon_low,
+                               epsilon_high, gspo, None if old is None else old[n0:n1], want_grad=need_grad,
+                               want_kl=False, N_total=N, seq_offset=n0, state=state)
+        if need_grad:
+            dlogits_(z, lse, g.view(-1), targets[s:e], v_offset)
+            bwd_dhidden(z, weight, out=d_hidden[s:e])
+            bwd_dweight(z, hidden2[s:e], d_weight, accumulate=(ci > 0) or (d_weight_out is not None))
+    if need_grad and group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(d_hidden, group=group)
+    return dict(loss=state["loss"].reshape(()), per_token_logps=logp, advantages=state["adv"],
+                mean_kl=state["mean_kl"].reshape(()), completion_length=state["clen"], reward_std=state["rstd"],
+                d_hidden=None if d_hidden is None else d_hidden.view(N, Tc, H), d_weight=d_weight)

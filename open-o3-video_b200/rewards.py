@@ -1,0 +1,258 @@
+"""Spatio-temporal rewards: text parsing in Python, numerics on the GPU (K4).
+
+Drop-in for the numeric reward callables of the reference
+(src/r1-v/src/open_r1/reward_func.py): same names, same `f(completions, **kwargs) ->
+list[float]` signature (grpo_trainer.py:655), same task gating.  The regex / json / ast
+extraction is string work and stays in Python exactly as the reference does it (cited per
+function); everything after parsing -- temporal IoU, in-segment ratio, adaptive temporal
+proximity, temporal gating + bbox IoU, visual-QA IoUs -- runs in one CUDA launch over a
+struct-of-arrays batch (include/o3v.h `o3v_rewards_soa`).  `ans_acc_reward` and
+`format_reward` are pure string rewards and are not part of this path.
+"""
+import ast
+import ctypes
+import json
+import re
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+TASK_IDS = {"visual QA": 0, "temporal QA": 1, "temporal QA (MCQ)": 2,
+            "temporal-spatial free-form QA": 3, "General video QA MCQ": 4, "General video QA Free-form": 5}
+REWARD_NAMES = ("ans_tiou_reward", "ans_viou_reward", "thk_temporal_segment_reward",
+                "thk_temporal_point_reward", "thk_spatial_reward")
+RF_HAS_THINK, RF_HAS_ANSWER, RF_ANS_SEG, RF_ANS_BOX, GF_VBOX = 1, 2, 4, 8, 1
+
+
+# ----------------------------------------------------------------------------- parsing
+def _box_ok(b) -> bool:
+    """What calculate_iou accepts as a prediction (reward_func.py:361-368): a list of 4 numbers."""
+    if not (isinstance(b, list) and len(b) == 4):
+        return False
+    try:
+        np.array(b, dtype=float)
+        return True
+    except (ValueError, TypeError):
+        return False
+
+
+def parse_claims(think_content: str):
+    """reward_func.py:308-335 (parse_temporal_spatial_reasoning_process) -> [(t, [box, ...])]."""
+    pattern = r"<obj>(.*?)</obj>((?:<box>\[.*?\]</box>)+)at<t>(.*?)</t>s"
+    claims = []
+    for match in re.finditer(pattern, think_content, re.DOTALL):
+        try:
+            timestamp = float(match.group(3).strip())
+            boxes = [json.loads(b) for b in re.findall(r"\[.*?\]", match.group(2))]
+            claims.append((timestamp, boxes))
+        except (json.JSONDecodeError, ValueError, IndexError):
+            continue
+    return claims
+
+
+def parse_rollout(content: str, task: str, answer: str, key_frames=None, key_items=None, image_size=None,
+                  image_size_refine=None, step_percent: float = 0.0) -> dict:
+    """One completion + its reward kwargs -> the parsed structure the kernels consume."""
+    think_match = re.search(r"<think>(.*?)</think>", content, re.DOTALL)            # :392
+    answer_match = re.search(r"<answer>(.*?)</answer>", content, re.DOTALL)         # :482
+    r = dict(task=task, has_think=bool(think_match), has_answer=bool(answer_match), ans_seg=None, ans_box=None,
+             think_times=[], think_boxes=[], claims=[], gt_seg=[0.0, 0.0], gt_vbox=None,
+             key_frames=key_frames or [], key_items=key_items or {}, image_size=image_size or (1, 1),
+             image_size_refine=image_size_refine or (1, 1), step_percent=step_percent)
+    m = re.search(r"<answer>\s*(.*?)\s*</answer>", content, re.DOTALL)              # :91 extract_answer
+    output_ans = m.group(1).strip() if m else ""
+    think = think_match.group(1) if think_match else ""
+    if task in ("temporal QA", "temporal QA (MCQ)"):
+        gt = answer.split("\n")[1] if task == "temporal QA (MCQ)" else answer       # :116, :146
+        r["gt_seg"] = [float(x) for x in ast.literal_eval(gt)]
+        mm = re.search(r"<t>(\d+\.?\d*)</t>s to <t>(\d+\.?\d*)</t>s", output_ans)   # :119
+        if mm:
+            r["ans_seg"] = [float(mm.group(1)), float(mm.group(2))]
+    if think_match:
+        try:
+            r["think_times"] = [float(x) for x in re.findall(r"<t>([\d.]+)</t>s", think)]   # :405, :447
+        except ValueError:
+            r["think_times"] = []
+    if task == "visual QA":
+        pat = r"<box>(\[.*?\])</box>"
+        mg = re.search(pat, "<answer>%s</answer>" % answer)                         # :204, :493
+        if mg:
+            try:
+                r["gt_vbox"] = json.loads(mg.group(1))
+            except Exception:
+                r["gt_vbox"] = None
+        mp = re.search(pat, output_ans)                                             # :212
+        if mp:
+            try:
+                r["ans_box"] = json.loads(mp.group(1))
+            except Exception:
+                r["ans_box"] = None
+        for b in re.findall(pat, think):                                            # :505-512
+            try:
+                r["think_boxes"].append(json.loads(b))
+            except Exception:
+                pass
+    elif think_match:
+        r["claims"] = parse_claims(think)                                           # :535 (used by the ungated tasks)
+    return r
+
+
+# ----------------------------------------------------------------------------- packing
+def pack_rollouts(rollouts: Sequence[dict], G: int = 1):
+    """Parsed rollouts (GT identical within each block of G) -> dict of numpy arrays in the
+    o3v_rewards_soa layout, plus the dims."""
+    R = len(rollouts)
+    assert R % G == 0
+    Q = R // G
+    P = max([len(r["think_times"]) for r in rollouts] + [1])
+    C = max([len(r["claims"]) for r in rollouts] + [1])
+    Bc = max([len(b) for r in rollouts for _, b in r["claims"]] + [1])
+    Tb = max([len(r["think_boxes"]) for r in rollouts] + [1])
+    if Bc > 32 or Tb > 32:
+        raise ValueError("more than 32 boxes per claim / think block")
+    gts = [rollouts[q * G] for q in range(Q)]
+    K = max([len(g["key_frames"]) for g in gts] + [1])
+    O = max([len(g["key_items"].get(str(f["idx"]), {})) for g in gts for f in g["key_frames"]] + [1])
+    Gb = max([len(bx) for g in gts for f in g["key_frames"]
+              for bx in g["key_items"].get(str(f["idx"]), {}).values()] + [1])
+    a = dict(
+        flags=np.zeros(R, np.int32), ans_seg=np.zeros((R, 2)), ans_box=np.zeros((R, 4)),
+        n_times=np.zeros(R, np.int32), think_times=np.zeros((R, P)), n_claims=np.zeros(R, np.int32),
+        claim_t=np.zeros((R, C)), claim_nbox=np.zeros((R, C), np.int32), claim_valid=np.zeros((R, C), np.uint32),
+        claim_box=np.zeros((R, C, Bc, 4)), n_tboxes=np.zeros(R, np.int32), tbox_valid=np.zeros(R, np.uint32),
+        think_box=np.zeros((R, Tb, 4)),
+        task=np.zeros(Q, np.int32), gt_flags=np.zeros(Q, np.int32), gt_seg=np.zeros((Q, 2)),
+        gt_vbox=np.zeros((Q, 4)), image_size=np.ones((Q, 2)), image_refine=np.ones((Q, 2)),
+        n_kf=np.zeros(Q, np.int32), kf_time=np.zeros((Q, K)), n_obj=np.zeros((Q, K), np.int32),
+        n_gtbox=np.zeros((Q, K, O), np.int32), gt_box=np.zeros((Q, K, O, Gb, 4)))
+    for i, r in enumerate(rollouts):
+        f = (RF_HAS_THINK if r["has_think"] else 0) | (RF_HAS_ANSWER if r["has_answer"] else 0)
+        if r["ans_seg"] is not None:
+            f |= RF_ANS_SEG
+            a["ans_seg"][i] = r["ans_seg"]
+        if r["ans_box"] is not None and _box_ok(r["ans_box"]):
+            f |= RF_ANS_BOX
+            a["ans_box"][i] = r["ans_box"]
+        a["flags"][i] = f
+        n = len(r["think_times"])
+        a["n_times"][i] = n
+        a["think_times"][i, :n] = r["think_times"]
+        a["n_claims"][i] = len(r["claims"])
+        for c, (t, boxes) in enumerate(r["claims"]):
+            a["claim_t"][i, c] = t
+            a["claim_nbox"][i, c] = len(boxes)
+            for b, box in enumerate(boxes):
+                if _box_ok(box):
+                    a["claim_valid"][i, c] |= np.uint32(1 << b)
+                    a["claim_box"][i, c, b] = box
+        a["n_tboxes"][i] = len(r["think_boxes"])
+        for b, box in enumerate(r["think_boxes"]):
+            if _box_ok(box):
+                a["tbox_valid"][i] |= np.uint32(1 << b)
+                a["think_box"][i, b] = box
+    for q, g in enumerate(gts):
+        if g["task"] not in TASK_IDS:
+            raise ValueError("Unknown task: %s" % g["task"])            # data_loader.py:33
+        a["task"][q] = TASK_IDS[g["task"]]
+        a["gt_seg"][q] = g["gt_seg"]
+        if g["gt_vbox"] is not None:
+            a["gt_flags"][q] = GF_VBOX
+            a["gt_vbox"][q] = g["gt_vbox"]
+        a["image_size"][q] = g["image_size"]
+        a["image_refine"][q] = g["image_size_refine"]
+        a["n_kf"][q] = len(g["key_frames"])
+        for k, fr in enumerate(g["key_frames"]):
+            a["kf_time"][q, k] = fr["time"]
+            objs = g["key_items"].get(str(fr["idx"]), {})
+            a["n_obj"][q, k] = len(objs)
+            for o, boxes in enumerate(objs.values()):
+                a["n_gtbox"][q, k, o] = len(boxes)
+                for gi, box in enumerate(boxes):
+                    a["gt_box"][q, k, o, gi] = box
+    dims = dict(R=R, G=G, P=P, C=C, Bc=Bc, Tb=Tb, K=K, O=O, Gb=Gb)
+    return a, dims
+
+
+def soa_bytes(arrays) -> int:
+    return int(sum(v.nbytes for v in arrays.values()))
+
+
+def to_device(arrays, device):
+    """Host SoA -> device tensors (one H2D copy per array from pinned memory)."""
+    out = {}
+    for k, v in arrays.items():
+        t = torch.from_numpy(np.ascontiguousarray(v).view(np.int32) if v.dtype == np.uint32 else np.ascontiguousarray(v))
+        out[k] = t.pin_memory().to(device, non_blocking=True)
+    return out
+
+
+def grounded_rewards_device(dev_arrays, dims, step_percent: float, out: Optional[torch.Tensor] = None):
+    """K4 launch on device-resident SoA -> [R, 5] float64 (device)."""
+    any_t = dev_arrays["flags"]
+    if not any_t.is_cuda:
+        raise RuntimeError("open-o3-video_b200 ops take CUDA tensors only (no CPU fallback)")
+    R = dims["R"]
+    if out is None:
+        out = torch.empty(R, 5, dtype=torch.float64, device=any_t.device)
+    soa = _lib.RewardsSoA()
+    soa.R, soa.G = R, dims["G"]
+    for k in ("P", "C", "Bc", "Tb", "K", "O", "Gb"):
+        setattr(soa, k, dims[k])
+    soa.step_percent = float(step_percent)
+    for name, _ in _lib.RewardsSoA._fields_[11:]:
+        setattr(soa, name, dev_arrays[name].data_ptr())
+    with torch.cuda.device(any_t.device):
+        _lib.check(_lib.load().o3v_grounded_rewards(ctypes.byref(soa), ctypes.c_void_p(out.data_ptr()),
+                                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                   "o3v_grounded_rewards")
+    return out
+
+
+def rewards_from_rollouts(rollouts: Sequence[dict], G: int = 1, device="cuda") -> torch.Tensor:
+    if len(rollouts) == 0:
+        return torch.empty(0, 5, dtype=torch.float64, device=device)
+    arrays, dims = pack_rollouts(rollouts, G)
+    return grounded_rewards_device(to_device(arrays, device), dims, rollouts[0]["step_percent"])
+
+
+# ----------------------------------------------------------------------------- reference-named callables
+_cache = {"key": None, "val": None}
+
+
+def grounded_rewards(completions, **kwargs) -> np.ndarray:
+    """All five numeric rewards for a batch: [len(completions), 5] float64 (host)."""
+    contents = [c[0]["content"] for c in completions]
+    task = kwargs["task"][0]                                   # the reference reads element 0 for the batch
+    step = kwargs["step_percent"][0] if "step_percent" in kwargs else 0.0
+    key = (tuple(contents), task, step, id(kwargs.get("answer")), id(kwargs.get("key_frames")))
+    if _cache["key"] == key:
+        return _cache["val"]
+    get = lambda name, i: (kwargs[name][i] if name in kwargs and kwargs[name] is not None else None)
+    rollouts = [parse_rollout(c, task, get("answer", i) or "", get("key_frames", i), get("key_items", i),
+                              get("image_size", i), get("image_size_refine", i), step)
+                for i, c in enumerate(contents)]
+    val = rewards_from_rollouts(rollouts, 1).cpu().numpy()
+    _cache["key"], _cache["val"] = key, val
+    return val
+
+
+def _column(j):
+    def f(completions, **kwargs) -> List[float]:
+        return [float(x) for x in grounded_rewards(completions, **kwargs)[:, j]]
+    return f
+
+
+ans_tiou_reward = _column(0)
+ans_viou_reward = _column(1)
+thk_temporal_segment_reward = _column(2)
+thk_temporal_point_reward = _column(3)
+thk_spatial_reward = _column(4)
+for _j, _n in enumerate(REWARD_NAMES):
+    globals()[_n].__name__ = _n          # `reward_func.__name__` names the metric (grpo_trainer.py:718)
+    globals()[_n].__doc__ = "B200 drop-in for reward_func.%s (numeric core on the GPU)." % _n
+
+# name -> callable, the numeric subset of grpo.py:58-66's reward_funcs_registry
+reward_funcs_registry = {n: globals()[n] for n in REWARD_NAMES}

@@ -1,0 +1,89 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds for sm_100a, loads, and
+exports every symbol include/o3v.h declares; argument validation works without a GPU; the
+product package never imports the oracle."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from open_o3_video_b200 import _build, _lib
+    _build.build()
+    return _lib.load()
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "o3v.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(o3v_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported_and_bound(lib):
+    from open_o3_video_b200 import _lib
+    declared = _declared_functions()
+    assert len(declared) >= 14
+    for name in declared:
+        assert hasattr(lib, name), "libo3v.so does not export %s" % name
+    assert sorted(_lib.SIGNATURES) == declared, "ctypes binding and include/o3v.h disagree"
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (o3v_[a-z0-9_]+)", out))
+    assert exported == set(declared), exported ^ set(declared)
+
+
+def test_version_and_strerror(lib):
+    assert lib.o3v_version() == 100
+    assert b"sm_100" in lib.o3v_strerror(-3)
+    assert lib.o3v_strerror(0) == b"ok"
+    assert b"invalid argument" in lib.o3v_strerror(-1)
+
+
+def test_argument_validation_without_gpu(lib):
+    """Bad arguments are rejected before any CUDA call: error codes, never a crash."""
+    null = ctypes.c_void_p(0)
+    one = ctypes.c_void_p(16)   # never dereferenced: validation fails first
+    assert lib.o3v_eos_mask(null, 1, 1, 0, null, null, null) == -1
+    assert lib.o3v_lmhead_fwd(null, null, null, 1, 1, 64, 0, null, null, 0, null, 0, null) == -1
+    assert lib.o3v_lmhead_fwd(one, one, one, 128, 256, 100, 0, one, null, 0, one, 1 << 30, null) == -6  # H % 64
+    assert lib.o3v_gspo_fwd_bwd(one, null, one, one, one, 6, 8, 1, 4, 0, 6, 0.04, 0.2, 0.2, 1,
+                                one, null, null, null, null, null, null, one, 1 << 20, null) == -1   # N % G
+    assert lib.o3v_gspo_fwd_bwd(one, null, one, one, one, 8, 8, 1, 4, 0, 8, 0.04, 0.2, 0.2, 1,
+                                one, null, null, null, null, null, null, one, 8, null) == -4         # workspace
+    assert lib.o3v_grounded_rewards(None, null, null) == -1
+    assert lib.o3v_set_tunable(b"nope", 1) == -1
+    assert lib.o3v_lmhead_fwd_workspace_bytes(128, 1024, 64) == 4 * 3 * 128 * 4
+    assert lib.o3v_gspo_workspace_bytes(8) == (2 * 8 + 4) * 4
+
+
+def test_sass_is_blackwell_native():
+    """tcgen05.mma / tcgen05.ld / TMA must be in the shipped binary (B200_PROFILING.md)."""
+    from open_o3_video_b200 import _lib
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG"):
+        assert mnemonic in sass, mnemonic
+    assert "HMMA.16" not in sass      # no legacy mma.sync path
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "open-o3-video_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+                assert "/root/reference" not in src, f
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+    from open_o3_video_b200 import gspo, logprob
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        gspo.eos_mask(torch.zeros(2, 4, dtype=torch.int64), 1)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        logprob.fused_logprob(torch.zeros(4, 64, dtype=torch.bfloat16), torch.zeros(8, 64, dtype=torch.bfloat16),
+                              torch.zeros(4, dtype=torch.int64))

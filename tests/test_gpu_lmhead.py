@@ -1,0 +1,169 @@
+"""GPU parity (through the C ABI) of the tcgen05 lm_head kernels.
+
+K1: fused GEMM + online log-softmax + gather against the oracle (the reference's torch path
+in fp32 on the same bf16-valued inputs): log-probs within 1e-3 relative (north_star, bf16);
+the gather index must be exact, so the captured target logit is compared too.
+K2: dlogits / dHidden / dW against torch fp32 autograd through the oracle.
+Every case runs for both tile modes: one CTA per tile and cta_group::2 pairs.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import logps as ologps
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(params=[1, 2], ids=["cta1", "cta2"])
+def cta_pair(request):
+    from open_o3_video_b200 import _lib
+    _lib.set_tunable("cta_pair", request.param)
+    yield request.param
+    _lib.set_tunable("cta_pair", 1)
+    _lib.set_tunable("fwd_groups", 0)
+
+
+def _rel(a, b):
+    return (np.abs(a - b) / np.maximum(np.abs(b), 1e-6)).max()
+
+
+# T, H, V, planted, fwd_groups
+FWD_CASES = [
+    (128, 64, 256, False, 0),          # one tile, one k-block
+    (256, 128, 1024, False, 0),
+    (300, 192, 1000, False, 1),        # ragged M, N (V % 8 == 0), odd k-block count, 1 group
+    (1000, 512, 5000, True, 3),        # planted +-60 logits, uneven groups
+    (515, 256, 151936 // 16, False, 5),
+    (2048, 3584, 152064 // 8, True, 0),
+]
+
+
+@pytest.mark.parametrize("T,H,V,planted,groups", FWD_CASES)
+def test_fwd_logp_matches_oracle(cta_pair, T, H, V, planted, groups):
+    from open_o3_video_b200 import _lib, logprob
+    _lib.set_tunable("fwd_groups", groups)
+    hidden, weight, targets = synth.head_inputs(T, H, V, seed=T + V, planted=planted)
+    ref_logp, ref_lse = ologps.token_logps(hidden, weight, targets)
+    logp, lse = logprob.fused_logprob(hidden.cuda().bfloat16(), weight.cuda().bfloat16(), targets.cuda(),
+                                      return_lse=True)
+    torch.cuda.synchronize()
+    assert _rel(lse.cpu().numpy(), ref_lse.numpy()) < 1e-4
+    assert _rel(logp.cpu().numpy(), ref_logp.numpy()) < 1e-3          # north_star tolerance
+    assert np.abs(logp.cpu().numpy() - ref_logp.numpy()).max() < 2e-3
+
+
+def test_fwd_gather_is_exact_and_logits_store(cta_pair):
+    """Target logit captured in the epilogue == the logit at exactly targets[t] (bit-exact index),
+    and the optional bf16 logits equal the fp32 accumulators rounded to bf16."""
+    from open_o3_video_b200 import logprob
+    T, H, V = 384, 256, 2048 + 8 * 13
+    hidden, weight, targets = synth.head_inputs(T, H, V, seed=3)
+    targets[:4] = torch.tensor([0, V - 1, 255, 256])                  # tile / chunk boundaries
+    h, w, t = hidden.cuda().bfloat16(), weight.cuda().bfloat16(), targets.cuda()
+    z = torch.full((T, V + 24), 7.0, dtype=torch.bfloat16, device="cuda")   # ld > V: padding untouched
+    stats = logprob.lmhead_stats(h, w, t, 0, z[:, :V])
+    torch.backends.cuda.matmul.allow_tf32 = False
+    z_ref = h.float() @ w.float().T
+    tgt_ref = z_ref.gather(1, t[:, None])[:, 0]
+    np.testing.assert_allclose(stats[2].cpu().numpy(), tgt_ref.cpu().numpy(), rtol=1e-5, atol=1e-5)
+    # a wrong column would be off by O(1), not 1e-5: also check against every other column's logit
+    assert (torch.abs(stats[2] - tgt_ref) < 1e-4).all()
+    np.testing.assert_allclose(stats[0].cpu().numpy(), z_ref.max(1).values.cpu().numpy(), rtol=1e-5, atol=1e-5)
+    diff = (z[:, :V].float() - z_ref).abs().max().item()
+    assert diff <= 2 ** -8 * z_ref.abs().max().item() + 1e-6
+    assert (z[:, V:] == 7.0).all()
+
+
+def test_fwd_vocab_slices_merge_to_full():
+    """Vocab-sharded use: per-slice statistics merged by o3v_lmhead_merge_stats == unsharded."""
+    from open_o3_video_b200 import logprob
+    T, H, V = 640, 128, 4096 + 512
+    hidden, weight, targets = synth.head_inputs(T, H, V, seed=9)
+    h, w, t = hidden.cuda().bfloat16(), weight.cuda().bfloat16(), targets.cuda()
+    full, lse_full = logprob.merge_stats(logprob.lmhead_stats(h, w, t).unsqueeze(0))
+    bounds = [0, 1024, 1024 + 256, 3072, V]                            # tile-granular, uneven
+    parts = torch.stack([logprob.lmhead_stats(h, w[a:b].contiguous(), t, a) for a, b in zip(bounds, bounds[1:])])
+    sh, lse_sh = logprob.merge_stats(parts)
+    np.testing.assert_allclose(sh.cpu().numpy(), full.cpu().numpy(), rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(lse_sh.cpu().numpy(), lse_full.cpu().numpy(), rtol=2e-6, atol=2e-6)
+
+
+def _torch_ref_grads(hidden, weight, targets, g):
+    h = hidden.clone().requires_grad_(True)
+    w = weight.clone().requires_grad_(True)
+    z = h @ w.T
+    lp = z.log_softmax(-1).gather(1, targets[:, None])[:, 0]
+    (lp * g).sum().backward()
+    return h.grad, w.grad, z.detach()
+
+
+BWD_CASES = [(128, 64, 256), (384, 128, 1024), (300, 192, 1000), (1100, 512, 5000), (777, 1024, 9496)]
+
+
+@pytest.mark.parametrize("T,H,V", BWD_CASES)
+def test_bwd_gemms_match_torch(cta_pair, T, H, V):
+    """dH = P.W (A K-major, B MN-major) and dW = P^T.hidden (both MN-major) on a given bf16 P."""
+    from open_o3_video_b200 import logprob
+    g = torch.Generator().manual_seed(T + H + V)
+    P = (torch.randn(T, V, generator=g) * 0.05).bfloat16()
+    W = (torch.randn(V, H, generator=g) * 0.02).bfloat16()
+    Hd = torch.randn(T, H, generator=g).bfloat16()
+    Pc, Wc, Hc = P.cuda(), W.cuda(), Hd.cuda()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dH_ref = Pc.float() @ Wc.float()
+    dW_ref = Pc.float().T @ Hc.float()
+    dH32 = logprob.bwd_dhidden(Pc, Wc, fp32=True)
+    np.testing.assert_allclose(dH32.cpu().numpy(), dH_ref.cpu().numpy(), rtol=1e-4, atol=1e-4 * dH_ref.abs().max().item())
+    dH16 = logprob.bwd_dhidden(Pc, Wc)
+    assert dH16.dtype == torch.bfloat16
+    assert (dH16.float() - dH_ref).abs().max().item() <= 2 ** -8 * dH_ref.abs().max().item() * 1.01 + 1e-6
+    dW = torch.full((V, H), float("nan"), device="cuda")
+    logprob.bwd_dweight(Pc, Hc, dW, accumulate=False)
+    np.testing.assert_allclose(dW.cpu().numpy(), dW_ref.cpu().numpy(), rtol=1e-4, atol=1e-4 * dW_ref.abs().max().item())
+    logprob.bwd_dweight(Pc, Hc, dW, accumulate=True)                  # fp32 read-modify-write
+    np.testing.assert_allclose(dW.cpu().numpy(), 2 * dW_ref.cpu().numpy(), rtol=1e-4,
+                               atol=2e-4 * dW_ref.abs().max().item())
+
+
+def test_dlogits_in_place():
+    from open_o3_video_b200 import logprob
+    T, V = 50, 1000
+    g0 = torch.Generator().manual_seed(1)
+    z = (torch.randn(T, V, generator=g0) * 2).bfloat16()
+    targets = torch.randint(0, V, (T,), generator=g0)
+    grad = torch.randn(T, generator=g0) * 0.01
+    grad[3] = 0.0
+    lse = torch.logsumexp(z.float(), -1)
+    ref = grad[:, None] * (torch.nn.functional.one_hot(targets, V).float() - torch.exp(z.float() - lse[:, None]))
+    buf = torch.zeros(T, V + 8, dtype=torch.bfloat16, device="cuda")
+    buf[:, :V] = z.cuda()
+    logprob.dlogits_(buf[:, :V], lse.cuda(), grad.cuda(), targets.cuda(), 0)
+    out = buf[:, :V].float().cpu()
+    assert (out - ref).abs().max().item() <= 2 ** -8 * ref.abs().max().item() + 1e-7
+    assert (out[3] == 0).all() and (buf[:, V:] == 0).all()
+    # vocab slice: the one-hot lands only in the owner slice
+    buf2 = z[:, 256:512].cuda().contiguous()
+    logprob.dlogits_(buf2, lse.cuda(), grad.cuda(), targets.cuda(), 256)
+    assert (buf2.float().cpu() - ref[:, 256:512]).abs().max().item() <= 2 ** -8 * ref.abs().max().item() + 1e-7
+
+
+@pytest.mark.parametrize("T,H,V", [(384, 128, 1024), (1000, 512, 5000)])
+def test_autograd_function_backward(cta_pair, T, H, V):
+    """fused_logprob as a torch.autograd.Function: gradients w.r.t. hidden and weight."""
+    from open_o3_video_b200 import logprob
+    hidden, weight, targets = synth.head_inputs(T, H, V, seed=T)
+    g = torch.randn(T, generator=torch.Generator().manual_seed(2)) * 0.01
+    dH_ref, dW_ref, _ = _torch_ref_grads(hidden, weight, targets, g)
+    for save_bytes in (1 << 40, 0):                                   # keep logits / recompute per chunk
+        logprob.SAVE_LOGITS_BYTES = save_bytes
+        h = hidden.cuda().bfloat16().requires_grad_(True)
+        w = weight.cuda().bfloat16().requires_grad_(True)
+        lp = logprob.fused_logprob(h, w, targets.cuda(), chunk_tokens=256)
+        (lp * g.cuda()).sum().backward()
+        for got, ref in ((h.grad, dH_ref), (w.grad, dW_ref)):
+            err = (got.float().cpu() - ref).norm() / ref.norm()
+            assert err < 1e-2, err
+            assert (got.float().cpu() - ref).abs().max() < 3e-2 * ref.abs().max()
+    logprob.SAVE_LOGITS_BYTES = 24 << 30

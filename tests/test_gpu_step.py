@@ -1,0 +1,91 @@
+"""GPU parity of the whole fused step (`fused_logprob_gspo`) against the oracle: loss and
+log-probs within the north_star tolerances, gradients against autograd through the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gspo as ogspo
+from oracle import logps as ologps
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_step(hidden, weight, ids, ref, mask, rpf, G, beta, old, gspo=True):
+    N, Tc, H = hidden.shape
+    h = hidden.clone().requires_grad_(True)
+    w = weight.clone().requires_grad_(True)
+    z = h.view(N * Tc, H) @ w.T
+    lp = z.log_softmax(-1).gather(1, ids.view(-1, 1))[:, 0].view(N, Tc)
+    out = ogspo.gspo_step(lp, ref, mask, rpf, G, beta, 0.2, 0.2, gspo, old)
+    out["loss"].backward()
+    return out, lp.detach(), h.grad, w.grad
+
+
+def _inputs(N, Tc, G, H, V, off_policy, seed=0):
+    hidden, weight, targets = synth.head_inputs(N * Tc, H, V, seed=seed + 17)
+    d = synth.gspo_inputs(N, Tc, G, off_policy=off_policy, vocab=V + 1000, eos_id=V - 1, seed=seed)
+    ids = d["ids"] % V
+    _, mask = ogspo.eos_mask(ids, V - 1)
+    lp_true, _ = ologps.token_logps(hidden, weight, ids.view(-1))
+    lp_true = lp_true.view(N, Tc)
+    ref = lp_true + (d["ref"] - d["logp"])
+    old = None if d["old"] is None else lp_true + (d["old"] - d["logp"])
+    return hidden.view(N, Tc, H), weight, ids, ref, mask, d["rewards_per_func"], old
+
+
+@pytest.mark.parametrize("cta", [1, 2])
+@pytest.mark.parametrize("off_policy", [False, True])
+@pytest.mark.parametrize("N,Tc,G,H,V,chunk", [(8, 64, 4, 128, 1024, 128), (8, 100, 4, 256, 5000, 300),
+                                              (4, 512, 4, 512, 152064 // 16, 1 << 20)])
+def test_fused_step_matches_oracle(N, Tc, G, H, V, chunk, off_policy, cta):
+    from open_o3_video_b200 import _lib, logprob
+    _lib.set_tunable("cta_pair", cta)
+    try:
+        hidden, weight, ids, ref, mask, rpf, old = _inputs(N, Tc, G, H, V, off_policy)
+        exp, lp_ref, dH_ref, dW_ref = _oracle_step(hidden, weight, ids, ref, mask, rpf, G, 0.04, old)
+        cu = lambda t: None if t is None else t.cuda()
+        out = logprob.fused_logprob_gspo(hidden.cuda().bfloat16(), weight.cuda().bfloat16(), ids.cuda(), cu(ref),
+                                         cu(mask), cu(rpf), G, 0.04, 0.2, 0.2, True, cu(old), chunk_tokens=chunk)
+        torch.cuda.synchronize()
+    finally:
+        _lib.set_tunable("cta_pair", 1)
+    lp = out["per_token_logps"].cpu()
+    assert ((lp - lp_ref).abs() / lp_ref.abs().clamp(min=1e-6)).max() < 1e-3
+    np.testing.assert_allclose(out["loss"].item(), exp["loss"].item(), rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose(out["mean_kl"].item(), exp["mean_kl"].item(), rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose(out["advantages"].cpu().numpy(), exp["advantages"].numpy(), rtol=2e-5, atol=2e-6)
+    assert torch.equal(out["completion_length"].cpu(), exp["completion_length"].to(torch.int32))
+    dH = out["d_hidden"].float().cpu().view_as(dH_ref)
+    dW = out["d_weight"].cpu()
+    # gradients flow through bf16 logits (as in the reference's bf16 path): 1% in norm
+    assert (dH - dH_ref).norm() / dH_ref.norm() < 1e-2
+    assert (dW - dW_ref).norm() / dW_ref.norm() < 1e-2
+    assert (dH - dH_ref).abs().max() < 3e-2 * dH_ref.abs().max()
+    assert (dW - dW_ref).abs().max() < 3e-2 * dW_ref.abs().max()
+    # masked-out tokens get exactly zero gradient
+    assert (dH.view(N, Tc, H)[mask == 0] == 0).all()
+
+
+def test_c1_shape_known_answer():
+    """BASELINE config 1 / SURVEY Appendix B: 7B head, 1 x 4 x 512 tokens, on-policy,
+    ref = logp + 0.1, rewards [0.5, 2.0, 1.25, 3.0], full mask -> loss = 0.000207."""
+    from open_o3_video_b200 import logprob
+    H, V, N, Tc = 3584, 152064, 4, 512
+    hidden, weight, targets = synth.head_inputs(N * Tc, H, V)
+    h, w, t = hidden.cuda().bfloat16(), weight.cuda().bfloat16(), targets.cuda()
+    del hidden, weight
+    lp = logprob.fused_logprob(h, w, t).view(N, Tc)
+    rpf = torch.tensor([[0.5], [2.0], [1.25], [3.0]], device="cuda")
+    mask = torch.ones(N, Tc, dtype=torch.int32, device="cuda")
+    out = logprob.fused_logprob_gspo(h.view(N, Tc, H), w, t.view(N, Tc), lp + 0.1, mask, rpf, 4, 0.04)
+    assert abs(out["loss"].item() - 0.000207) < 2e-6
+    assert torch.equal(out["per_token_logps"], lp)                     # deterministic across calls
+    # reference arithmetic on the same inputs, on the GPU in fp32 (too slow for CI on the host)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = torch.empty(N * Tc, device="cuda")
+    for s in range(0, N * Tc, 512):
+        z = h[s:s + 512].float() @ w.float().T
+        ref[s:s + 512] = z.log_softmax(-1).gather(1, t[s:s + 512, None])[:, 0]
+    assert ((lp.view(-1) - ref).abs() / ref.abs()).max().item() < 1e-3
+    assert out["d_hidden"].float().abs().max().item() > 0 and torch.isfinite(out["d_weight"]).all()
