@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- completion tokens/s of the fused logprob + GSPO fwd+bwd step (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c3|c5]
+
+A "step" is one pass of the hot path over one batch of synthetic rollouts: lm_head ->
+log-softmax -> gather -> KL / advantages / GSPO loss, and the backward to dHidden and
+dW_lm_head.  Default workload = BASELINE config 2 (Qwen2.5-VL-7B head, 8 prompts x G=8 x 2048
+completion tokens, bf16, 1 B200).  N > 1 (launched by torchrun, one rank per GPU): the
+vocabulary is sharded over the ranks (whole 256-column tiles), every rank sees all tokens,
+only (max, sum-exp, target-logit) triples are all-gathered in the forward and dHidden is
+all-reduced once per step -> strong scaling, T fixed.
+
+`value`   : device-resident inputs, CUDA events around the K timed steps, max over ranks.
+`e2e`     : same metric through the public API with HOST (pinned) inputs: H2D of hidden
+            states / ids / ref log-probs / mask / rewards and D2H of the loss inside the
+            timed region (lm_head.weight is model state and stays on the device).
+`roofline`: dominant kernel (the K1 tcgen05 GEMM with fused softmax-stats epilogue), timed
+            live with CUDA events around its launches inside the timed region.
+`cpu_baseline`: the oracle port of the reference's torch path (fp32) on the host cores, on
+            a bounded sample (config 1: 4 x 512 tokens of the same head).
+`--impl reference`: that CPU path alone, same JSON shape.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    "c2": dict(head="qwen2.5-vl-7b", H=3584, V=152064, prompts=8, G=8, Tc=2048),
+    "c3": dict(head="qwen3-vl-8b", H=4096, V=151936, prompts=16, G=8, Tc=4096),
+    "c5": dict(head="qwen3-vl-8b", H=4096, V=151936, prompts=1, G=16, Tc=16384),
+    "c1": dict(head="qwen2.5-vl-7b", H=3584, V=152064, prompts=1, G=4, Tc=512),
+    "tiny": dict(head="tiny", H=256, V=8192, prompts=2, G=4, Tc=128),
+}
+METRIC = "completion tokens/s, fused logprob+GSPO fwd+bwd; % bf16 tensor-pipe peak"
+BETA, EPS = 0.04, 0.2
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(burst=p["bf16_tflops"], sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    hbm=p["hbm_gbs"], source="measured")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        rows = [r for r in self.rows if len(r) >= 7 and r[0].isdigit()]
+        if not rows:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        sm = sorted(int(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(r[3 + j].lower().startswith("active") for r in rows)]
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=int(rows[0][1]), reasons=reasons, samples=len(rows),
+                    power_w_max=max(float(r[2]) for r in rows))
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def cpu_reference(steps, warmup, head_cfg):
+    """The reference's torch path on the host: oracle/logps.py (grpo_trainer.py:371-384 with the
+    lm_head) + oracle/gspo.py (the inline loss block) + loss.backward() to hidden and W, fp32,
+    all host threads.  Bounded sample: config 1's 4 x 512 tokens of the benchmarked head."""
+    from oracle import gspo as ogspo, logps as ologps, synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    H, V, N, Tc, G = head_cfg["H"], head_cfg["V"], 4, 512, 4
+    hidden, weight, _ = synth.head_inputs(N * Tc, H, V)
+    d = synth.gspo_inputs(N, Tc, G, vocab=V, eos_id=V - 1)
+    ids = d["ids"] % V
+    _, mask = ogspo.eos_mask(ids, V - 1)
+
+    def step():
+        h = hidden.view(N, Tc, H).clone().requires_grad_(True)
+        w = weight.clone().requires_grad_(True)
+        full_ids = torch.cat([ids[:, :1], ids], 1)          # [N, Tc+1]: logits[:, :-1] pair with ids[:, 1:]
+        hh = torch.cat([h, h[:, -1:]], 1)
+        lp = ologps.per_token_logps(hh, w, full_ids)
+        out = ogspo.gspo_step(lp, lp.detach() + 0.1, mask, d["rewards_per_func"], G, BETA, EPS, EPS)
+        out["loss"].backward()
+        return float(out["loss"])
+
+    for _ in range(warmup):
+        step()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    best = min(times)
+    return dict(value=N * Tc / best, unit="tokens/s", cores=cores, kind="port",
+                sample="%d steps of config 1 (1 prompt x G=4 x 512 tokens, %s head, fp32, fwd+bwd), best step %.2f s"
+                       % (steps, head_cfg["head"], best)), sum(times) / len(times)
+
+
+def run_reference(args):
+    cfg = CONFIGS[args.config]
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    base, mean_s = cpu_reference(steps, min(args.warmup, 1), cfg)
+    line = dict(metric=METRIC, value=base["value"], unit="tokens/s", n_gpus=args.gpus, steps=steps,
+                warmup=min(args.warmup, 1), ms_per_step=mean_s * 1e3, higher_is_better=True, scaling="strong",
+                vs_baseline=None, dtype="fp32", data="synthetic", impl="reference",
+                config=dict(workload="%s: %s head (H=%d, V=%d), bounded CPU sample of the same head" %
+                                     (args.config, cfg["head"], cfg["H"], cfg["V"]), sample=base["sample"]),
+                cpu_baseline=base,
+                e2e=dict(value=base["value"], unit="tokens/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch.distributed as dist
+    from open_o3_video_b200 import _lib, gspo, logprob, sharded
+    cfg = CONFIGS[args.config]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    _lib.check(_lib.load().o3v_check_device(), "o3v_check_device")
+    if args.cta_pair:
+        _lib.set_tunable("cta_pair", args.cta_pair)
+
+    H, V, G, Tc = cfg["H"], cfg["V"], cfg["G"], cfg["Tc"]
+    N = cfg["prompts"] * G
+    T = N * Tc
+    # synthetic rollouts (seeded, identical on every rank): hidden ~ N(0,1), W ~ N(0, 0.02^2)
+    g = torch.Generator(device=dev).manual_seed(20261018)
+    hidden = torch.randn(N, Tc, H, device=dev, generator=g, dtype=torch.float32).bfloat16()
+    w_full = (torch.randn(V, H, device=dev, generator=g, dtype=torch.float32) * 0.02).bfloat16()
+    ids = torch.randint(0, V - 1, (N, Tc), device=dev, generator=g)
+    lens = torch.randint(Tc // 4, Tc + 1, (N,), device=dev, generator=g)
+    eos_id = V - 1
+    ids[torch.arange(N, device=dev), lens - 1] = eos_id      # planted EOS drives the mask
+    _, mask = gspo.eos_mask(ids, eos_id)
+    weight, v_off = sharded.shard_weight(w_full, rank, world)
+    del w_full
+    # reference-model log-probs = policy log-probs + N(0, 0.1^2) (forward-only pass, untimed)
+    ref = logprob.fused_logprob(hidden.view(T, H), weight, ids.view(T), v_offset=v_off, group=group).view(N, Tc)
+    ref = ref + torch.randn(N, Tc, device=dev, generator=g) * 0.1
+    rpf = torch.rand(N, 3, device=dev, generator=g)
+    d_weight = torch.zeros(weight.shape[0], H, dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+
+    def step(h, i, r, m, rw):
+        return logprob.fused_logprob_gspo(h, weight, i, r, m, rw, G, BETA, EPS, EPS, True, None, v_offset=v_off,
+                                          group=group, chunk_tokens=args.chunk_tokens, d_weight_out=None)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        out = step(hidden, ids, ref, mask, rpf)
+    barrier()
+
+    # ---- timed region 1: device-resident inputs
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    trace = _lib.Trace(events=True)
+    _lib.trace = trace
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = step(hidden, ids, ref, mask, rpf)
+    e1.record()
+    barrier()
+    _lib.trace = None
+    clocks = sampler.stop() if rank == 0 else None
+    ms_dev = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    loss = float(out["loss"])
+    durs = trace.durations_ms()
+    launches = trace.launches
+
+    # ---- timed region 2: end to end from pinned host buffers
+    host = [t.cpu().pin_memory() for t in (hidden, ids, ref, mask, rpf)]
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        dev_in = [t.to(dev, non_blocking=True) for t in host]
+        o = step(*dev_in)
+        loss_host.copy_(o["loss"], non_blocking=True)
+        return o
+
+    for _ in range(min(args.warmup, 2)):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    flop_tok = 6.0 * H * V
+    value = T / (ms_dev * 1e-3)
+    # dominant kernel: K1 (tcgen05 GEMM + fused softmax statistics + bf16 logits store); the call
+    # also contains the tiny partial-merge kernel, timed with it
+    k1 = durs.get("o3v_lmhead_fwd+store", [])
+    n_chunks = max(1, len(k1) // args.steps)
+    tok_per_launch = T / n_chunks
+    k1_ms = sum(k1) / len(k1) if k1 else float("nan")
+    v_local = weight.shape[0]
+    ach = 2.0 * tok_per_launch * H * v_local / (k1_ms * 1e-3) / 1e12
+    shares = {k: sum(v) / args.steps for k, v in durs.items()}
+    line = dict(
+        metric=METRIC, value=value, unit="tokens/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+        ms_per_step=ms_dev, higher_is_better=True, scaling="strong", vs_baseline=None,
+        dtype="bf16", data="synthetic",
+        config=dict(workload="%s: %s head (H=%d, V=%d), %d prompts x G=%d x %d completion tokens = %d tokens/step, "
+                             "fused logprob+GSPO fwd+bwd" % (args.config, cfg["head"], H, V, cfg["prompts"], G, Tc, T),
+                    parallelism="vocab-sharded x%d (NCCL all-gather of softmax triples, all-reduce of dHidden)" % world
+                    if world > 1 else "single GPU", chunk_tokens=args.chunk_tokens,
+                    cache="inputs (%.1f GB) and per-chunk logits are far larger than the 126 MB L2; no flush needed"
+                          % ((hidden.numel() * 2 + weight.numel() * 2) / 1e9), loss=loss),
+        frac_of_bf16_peak=dict(burst=flop_tok * value / world / 1e12 / pk["burst"],
+                               sustained=flop_tok * value / world / 1e12 / pk["sustained"], source=pk["source"]),
+        roofline=dict(bound="tensor", kernel="lmhead_gemm_kernel<EPI_STATS> (K1 + logits store), per token chunk",
+                      achieved=ach, peak=pk["sustained"], unit="TFLOP/s", frac=ach / pk["sustained"],
+                      frac_of_burst=ach / pk["burst"], peak_source=pk["source"] + " (sustained: kernel timed inside a long step)",
+                      ms_per_launch=k1_ms, traffic=None),
+        kernel_ms_per_step=shares,
+        e2e=dict(value=T / (ms_e2e * 1e-3), unit="tokens/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
+                 ms_per_step=ms_e2e),
+        gpu_launches=launches, clocks=clocks)
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"], _ = cpu_reference(1, 0, cfg)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--chunk-tokens", type=int, default=32768)
+    ap.add_argument("--cta-pair", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

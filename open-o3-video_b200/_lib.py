@@ -84,3 +84,37 @@ def check(code: int, where: str) -> None:
 
 def set_tunable(name: str, value: int) -> None:
     check(load().o3v_set_tunable(name.encode(), int(value)), "o3v_set_tunable(%s)" % name)
+
+
+class Trace:
+    """Optional per-call instrumentation used by bench.py: counts the kernels this library
+    launches and (events=True) brackets every C-ABI call with CUDA events on the launching
+    stream, so per-kernel durations are measured live inside the timed region."""
+
+    def __init__(self, events: bool = False):
+        self.events = events
+        self.launches = 0
+        self.records = {}
+
+    def durations_ms(self):
+        """name -> list of elapsed ms (call after a device synchronize)."""
+        return {k: [a.elapsed_time(b) for a, b in v] for k, v in self.records.items()}
+
+
+trace = None   # set to a Trace() to instrument
+
+
+def call(name: str, n_kernels: int, fn, *args) -> None:
+    """Invoke one C-ABI entry point (which enqueues `n_kernels` kernels) and raise on error."""
+    t = trace
+    if t is not None and t.events:
+        import torch
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        check(fn(*args), name)
+        b.record()
+        t.records.setdefault(name, []).append((a, b))
+    else:
+        check(fn(*args), name)
+    if t is not None:
+        t.launches += n_kernels

@@ -271,7 +271,10 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               float acc = 0.f;
 #pragma unroll
               for (int j = 0; j < 32; ++j) acc += exp2f(fmaf(__uint_as_float(v[j]), kLog2e, neg));
-              run_sum = run_sum * exp2f(fmaf(run_max, kLog2e, neg)) + acc;
+              // rescale from the EXACT difference: an unchanged max must give a factor of exactly 1
+              // (via fmaf(run_max, log2e, neg) the rounding of max*log2e would compound over the
+              // ~4.7k chunks of a vocabulary sweep)
+              run_sum = run_sum * exp2f((run_max - new_max) * kLog2e) + acc;
               run_max = new_max;
             }
           } else if constexpr (kEpi == EPI_STORE) {

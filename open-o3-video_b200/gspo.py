@@ -34,8 +34,8 @@ def eos_mask(completion_ids: torch.Tensor, eos_token_id: int):
     eos_idx = torch.empty(N, dtype=torch.int64, device=ids.device)
     mask = torch.empty(N, Tc, dtype=torch.int32, device=ids.device)
     with torch.cuda.device(ids.device):
-        _lib.check(_lib.load().o3v_eos_mask(_p(ids), N, Tc, int(eos_token_id), _p(eos_idx), _p(mask), _stream()),
-                   "o3v_eos_mask")
+        _lib.call("o3v_eos_mask", 1, _lib.load().o3v_eos_mask, _p(ids), N, Tc, int(eos_token_id), _p(eos_idx),
+                  _p(mask), _stream())
     return eos_idx, mask
 
 
@@ -73,27 +73,27 @@ def gspo_raw(logp, ref, mask, rewards_per_func, num_generations, beta, epsilon_l
     rpf = rewards_per_func
     F = rpf.shape[1]
     with torch.cuda.device(dev):
-        _lib.check(lib.o3v_gspo_fwd_bwd(
-            _p(logp), _p(old), _p(ref), _p(mask), _p(rpf), N, Tc, F, int(num_generations),
-            int(seq_offset), n_seq, float(beta), float(epsilon_low), float(epsilon_high), 1 if gspo else 0,
-            _p(state["loss"]), _p(state["mean_kl"]), _p(state["adv"]), _p(state["rstd"]), _p(state["clen"]),
-            _p(grad), _p(kl), _p(state["ws"]), state["ws"].numel(), _stream()), "o3v_gspo_fwd_bwd")
+        _lib.call("o3v_gspo_fwd_bwd", 1, lib.o3v_gspo_fwd_bwd,
+                  _p(logp), _p(old), _p(ref), _p(mask), _p(rpf), N, Tc, F, int(num_generations),
+                  int(seq_offset), n_seq, float(beta), float(epsilon_low), float(epsilon_high), 1 if gspo else 0,
+                  _p(state["loss"]), _p(state["mean_kl"]), _p(state["adv"]), _p(state["rstd"]), _p(state["clen"]),
+                  _p(grad), _p(kl), _p(state["ws"]), state["ws"].numel(), _stream())
     return state, grad, kl
 
 
-class _GspoLossFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, logp, ref, mask, rpf, old, G, beta, eps_lo, eps_hi, gspo):
-        state, grad, kl = gspo_raw(logp, ref, mask, rpf, G, beta, eps_lo, eps_hi, gspo, old,
-                                   want_grad=True, want_kl=True)
-        ctx.save_for_backward(grad)
-        ctx.mark_non_differentiable(state["adv"], state["mean_kl"], state["clen"], state["rstd"], kl)
-        return state["loss"].reshape(()), state["adv"], state["mean_kl"].reshape(()), state["clen"], state["rstd"], kl
+class _AttachGrad(torch.autograd.Function):
+    """loss value and d loss / d logp were both produced by the same K3 launch; this only
+    wires them into autograd."""
 
     @staticmethod
-    def backward(ctx, g_loss, *unused):
+    def forward(ctx, logp, loss, grad):
+        ctx.save_for_backward(grad)
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, g_loss):
         (grad,) = ctx.saved_tensors
-        return (grad * g_loss,) + (None,) * 9
+        return grad * g_loss, None, None
 
 
 def gspo_loss(per_token_logps: torch.Tensor, ref_per_token_logps: torch.Tensor,
@@ -108,7 +108,11 @@ def gspo_loss(per_token_logps: torch.Tensor, ref_per_token_logps: torch.Tensor,
     """
     f32 = lambda t: None if t is None else t.detach().to(torch.float32).contiguous()
     logp = per_token_logps.to(torch.float32).contiguous()
-    out = _GspoLossFn.apply(logp, f32(ref_per_token_logps), completion_mask.to(torch.int32).contiguous(),
-                            f32(rewards_per_func), f32(old_per_token_logps), int(num_generations),
-                            float(beta), float(epsilon_low), float(epsilon_high), bool(gspo))
-    return GspoOutput(*out)
+    want_grad = torch.is_grad_enabled() and logp.requires_grad
+    state, grad, kl = gspo_raw(logp.detach(), f32(ref_per_token_logps), completion_mask.to(torch.int32).contiguous(),
+                               f32(rewards_per_func), int(num_generations), float(beta), float(epsilon_low),
+                               float(epsilon_high), bool(gspo), f32(old_per_token_logps), want_grad=want_grad)
+    loss = state["loss"].reshape(())
+    if want_grad:
+        loss = _AttachGrad.apply(logp, loss, grad)
+    return GspoOutput(loss, state["adv"], state["mean_kl"].reshape(()), state["clen"], state["rstd"], kl)

@@ -42,8 +42,9 @@ def lmhead_stats(hidden, weight, targets, v_offset=0, logits_out=None):
     ws = torch.empty(int(lib.o3v_lmhead_fwd_workspace_bytes(T, V, H)), dtype=torch.uint8, device=dev)
     ld = 0 if logits_out is None else logits_out.stride(0)
     with torch.cuda.device(dev):
-        _lib.check(lib.o3v_lmhead_fwd(_p(hidden), _p(weight), _p(targets), T, V, H, int(v_offset), _p(stats),
-                                      _p(logits_out), ld, _p(ws), ws.numel(), _stream()), "o3v_lmhead_fwd")
+        _lib.call("o3v_lmhead_fwd" if logits_out is None else "o3v_lmhead_fwd+store", 2, lib.o3v_lmhead_fwd,
+                  _p(hidden), _p(weight), _p(targets), T, V, H, int(v_offset), _p(stats),
+                  _p(logits_out), ld, _p(ws), ws.numel(), _stream())
     return stats
 
 
@@ -53,8 +54,8 @@ def merge_stats(parts):
     logp = torch.empty(T, dtype=torch.float32, device=parts.device)
     lse = torch.empty(T, dtype=torch.float32, device=parts.device)
     with torch.cuda.device(parts.device):
-        _lib.check(_lib.load().o3v_lmhead_merge_stats(_p(parts), P, T, _p(logp), _p(lse), _stream()),
-                   "o3v_lmhead_merge_stats")
+        _lib.call("o3v_lmhead_merge_stats", 1, _lib.load().o3v_lmhead_merge_stats, _p(parts), P, T, _p(logp),
+                  _p(lse), _stream())
     return logp, lse
 
 
@@ -75,8 +76,8 @@ def dlogits_(logits, lse, grad_logp, targets, v_offset=0, V=None):
     T = logits.shape[0]
     V = logits.shape[1] if V is None else V
     with torch.cuda.device(logits.device):
-        _lib.check(_lib.load().o3v_lmhead_dlogits(_p(logits), T, V, logits.stride(0), _p(lse), _p(grad_logp),
-                                                  _p(targets), int(v_offset), _stream()), "o3v_lmhead_dlogits")
+        _lib.call("o3v_lmhead_dlogits", 1, _lib.load().o3v_lmhead_dlogits, _p(logits), T, V, logits.stride(0),
+                  _p(lse), _p(grad_logp), _p(targets), int(v_offset), _stream())
     return logits
 
 
@@ -86,9 +87,8 @@ def bwd_dhidden(dlogits, weight, out=None, fp32=False):
     if out is None:
         out = torch.empty(T, H, dtype=torch.float32 if fp32 else torch.bfloat16, device=dlogits.device)
     with torch.cuda.device(dlogits.device):
-        _lib.check(_lib.load().o3v_lmhead_bwd_dhidden(_p(dlogits), dlogits.stride(0), _p(weight), T, V, H, _p(out),
-                                                      1 if out.dtype == torch.float32 else 0, _stream()),
-                   "o3v_lmhead_bwd_dhidden")
+        _lib.call("o3v_lmhead_bwd_dhidden", 1, _lib.load().o3v_lmhead_bwd_dhidden, _p(dlogits), dlogits.stride(0),
+                  _p(weight), T, V, H, _p(out), 1 if out.dtype == torch.float32 else 0, _stream())
     return out
 
 
@@ -96,9 +96,8 @@ def bwd_dweight(dlogits, hidden, d_weight, accumulate):
     T, V = dlogits.shape
     H = hidden.shape[1]
     with torch.cuda.device(dlogits.device):
-        _lib.check(_lib.load().o3v_lmhead_bwd_dweight(_p(dlogits), dlogits.stride(0), _p(hidden), T, V, H,
-                                                      _p(d_weight), 1 if accumulate else 0, _stream()),
-                   "o3v_lmhead_bwd_dweight")
+        _lib.call("o3v_lmhead_bwd_dweight", 1, _lib.load().o3v_lmhead_bwd_dweight, _p(dlogits), dlogits.stride(0),
+                  _p(hidden), T, V, H, _p(d_weight), 1 if accumulate else 0, _stream())
     return d_weight
 
 

@@ -205,9 +205,8 @@ def grounded_rewards_device(dev_arrays, dims, step_percent: float, out: Optional
     for name, _ in _lib.RewardsSoA._fields_[11:]:
         setattr(soa, name, dev_arrays[name].data_ptr())
     with torch.cuda.device(any_t.device):
-        _lib.check(_lib.load().o3v_grounded_rewards(ctypes.byref(soa), ctypes.c_void_p(out.data_ptr()),
-                                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
-                   "o3v_grounded_rewards")
+        _lib.call("o3v_grounded_rewards", 1, _lib.load().o3v_grounded_rewards, ctypes.byref(soa),
+                  ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     return out
 
 

@@ -41,11 +41,11 @@ def test_gspo_loss_and_grad(N, Tc, G, use_gspo, off_policy):
     out.loss.backward()
     tol = dict(rtol=1e-5, atol=1e-6)     # north_star: 1e-5 relative in fp32
     np.testing.assert_allclose(out.loss.item(), ref["loss"].item(), **tol)
-    np.testing.assert_allclose(out.advantages.cpu().numpy(), ref["advantages"].numpy(), rtol=2e-5, atol=2e-6)
-    np.testing.assert_allclose(out.per_token_kl.cpu().numpy(), ref["per_token_kl"].numpy(), **tol)
+    np.testing.assert_allclose(out.advantages.cpu().numpy(), ref["advantages"].detach().numpy(), rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(out.per_token_kl.cpu().numpy(), ref["per_token_kl"].detach().numpy(), **tol)
     assert torch.equal(out.completion_length.cpu(), ref["completion_length"].to(torch.int32))
     np.testing.assert_allclose(out.mean_kl.item(), ref["mean_kl"].item(), equal_nan=True, **tol)
-    np.testing.assert_allclose(out.reward_std.cpu().numpy(), ref["reward_std"].numpy(), rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(out.reward_std.cpu().numpy(), ref["reward_std"].detach().numpy(), rtol=2e-5, atol=2e-6)
     g_ref = lp.grad.numpy()
     np.testing.assert_allclose(lp_g.grad.cpu().numpy(), g_ref, rtol=2e-5, atol=1e-6 * np.abs(g_ref).max())
 
