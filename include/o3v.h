@@ -171,7 +171,6 @@ typedef struct o3v_rewards_soa {
   int32_t O;  /* max objects per key frame */
   int32_t Gb; /* max GT boxes per object */
   int32_t pad_;
-  double step_percent; /* kwargs['step_percent'][0] (reward_func.py:431) */
   /* per rollout */
   const int32_t* flags;       /* [R] O3V_RF_* */
   const double* ans_seg;      /* [R, 2] */
@@ -188,6 +187,7 @@ typedef struct o3v_rewards_soa {
   const double* think_box;    /* [R, Tb, 4] pixels */
   /* per prompt */
   const int32_t* task;        /* [Q] O3V_TASK_* */
+  const double* step_percent; /* [Q] kwargs['step_percent'][0] of the prompt's batch (reward_func.py:431) */
   const int32_t* gt_flags;    /* [Q] O3V_GF_* */
   const double* gt_seg;       /* [Q, 2] */
   const double* gt_vbox;      /* [Q, 4] */

@@ -16,11 +16,10 @@ class RewardsSoA(ctypes.Structure):
     """struct o3v_rewards_soa (include/o3v.h)."""
     _fields_ = [("R", c_int64), ("G", c_int64),
                 ("P", c_int32), ("C", c_int32), ("Bc", c_int32), ("Tb", c_int32),
-                ("K", c_int32), ("O", c_int32), ("Gb", c_int32), ("pad_", c_int32),
-                ("step_percent", c_double)] + [(n, c_void_p) for n in (
+                ("K", c_int32), ("O", c_int32), ("Gb", c_int32), ("pad_", c_int32)] + [(n, c_void_p) for n in (
                     "flags", "ans_seg", "ans_box", "n_times", "think_times", "n_claims", "claim_t",
                     "claim_nbox", "claim_valid", "claim_box", "n_tboxes", "tbox_valid", "think_box",
-                    "task", "gt_flags", "gt_seg", "gt_vbox", "image_size", "image_refine", "n_kf",
+                    "task", "step_percent", "gt_flags", "gt_seg", "gt_vbox", "image_size", "image_refine", "n_kf",
                     "kf_time", "n_obj", "n_gtbox", "gt_box")]
 
 

@@ -38,13 +38,13 @@ static EncodeTiledFn get_encode_fn() {
 // 2-D bf16 row-major tensor [outer, inner] with row pitch `ld` elements; box = [box_outer, 64]
 // with the 128-byte swizzle; out-of-bounds elements read as zero.
 static int make_tmap_bf16(CUtensorMap* tm, const void* base, int64_t inner, int64_t outer, int64_t ld,
-                          int box_outer) {
+                          int box_outer, int box_inner = 64) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return O3V_ERR_DRIVER;
   if ((reinterpret_cast<uintptr_t>(base) & 15u) || ((ld * 2) & 15)) return O3V_ERR_ALIGNMENT;
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64u, (cuuint32_t)box_outer};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -56,8 +56,9 @@ static int make_tmap_bf16(CUtensorMap* tm, const void* base, int64_t inner, int6
 // launch
 // ------------------------------------------------------------------------------------
 template <bool kAMN, bool kBMN, int kNCta, int kEpi>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
-  using S = GemmShape<kNCta>;
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
+                       cudaStream_t st) {
+  using S = GemmShape<kNCta, kEpi == EPI_STATS>;
   auto kern = lmhead_gemm_kernel<kAMN, kBMN, kNCta, kEpi>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
@@ -82,7 +83,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  O3V_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  O3V_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, p));
   return O3V_OK;
 }
 
@@ -217,12 +218,13 @@ extern "C" int o3v_lmhead_fwd(const void* hidden, const void* weight, const int6
   if (workspace_bytes < (size_t)p.num_n_groups * 3 * T * sizeof(float)) return O3V_ERR_WORKSPACE;
   p.targets = targets; p.v_offset = v_offset; p.parts = reinterpret_cast<float*>(workspace);
   p.logits = reinterpret_cast<__nv_bfloat16*>(logits); p.ld_logits = ld_logits;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC = {};
   if ((rc = make_tmap_bf16(&tmA, hidden, H, T, H, 128))) return rc;
   if ((rc = make_tmap_bf16(&tmB, weight, H, V, H, 256 / ncta))) return rc;
+  if (logits && (rc = make_tmap_bf16(&tmC, logits, V, T, ld_logits, 32))) return rc;   // store box: 32 rows x 64 cols
   cudaStream_t st = (cudaStream_t)stream;
-  rc = (ncta == 1) ? launch_gemm<false, false, 1, EPI_STATS>(tmA, tmB, p, st)
-                   : launch_gemm<false, false, 2, EPI_STATS>(tmA, tmB, p, st);
+  rc = (ncta == 1) ? launch_gemm<false, false, 1, EPI_STATS>(tmA, tmB, tmC, p, st)
+                   : launch_gemm<false, false, 2, EPI_STATS>(tmA, tmB, tmC, p, st);
   if (rc) return rc;
   merge_stats_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, st>>>(p.parts, p.num_n_groups, T, stats, nullptr, nullptr);
   O3V_LAUNCH_CHECK();
@@ -273,8 +275,8 @@ extern "C" int o3v_lmhead_bwd_dhidden(const void* dlogits, int64_t ld_dlogits, c
   if ((rc = make_tmap_bf16(&tmA, dlogits, V, T, ld_dlogits, 128))) return rc;   // A = P, K-major (K = V)
   if ((rc = make_tmap_bf16(&tmB, weight, H, V, H, 64))) return rc;              // B = W, MN-major (N = H contiguous)
   cudaStream_t st = (cudaStream_t)stream;
-  return (ncta == 1) ? launch_gemm<false, true, 1, EPI_STORE>(tmA, tmB, p, st)
-                     : launch_gemm<false, true, 2, EPI_STORE>(tmA, tmB, p, st);
+  return (ncta == 1) ? launch_gemm<false, true, 1, EPI_STORE>(tmA, tmB, tmA, p, st)
+                     : launch_gemm<false, true, 2, EPI_STORE>(tmA, tmB, tmA, p, st);
 }
 
 extern "C" int o3v_lmhead_bwd_dweight(const void* dlogits, int64_t ld_dlogits, const void* hidden,
@@ -295,6 +297,6 @@ extern "C" int o3v_lmhead_bwd_dweight(const void* dlogits, int64_t ld_dlogits, c
   if ((rc = make_tmap_bf16(&tmA, dlogits, V, T, ld_dlogits, 64))) return rc;    // A = P^T, MN-major (M = V contiguous)
   if ((rc = make_tmap_bf16(&tmB, hidden, H, T, H, 64))) return rc;              // B = hidden, MN-major
   cudaStream_t st = (cudaStream_t)stream;
-  return (ncta == 1) ? launch_gemm<true, true, 1, EPI_ACCUM>(tmA, tmB, p, st)
-                     : launch_gemm<true, true, 2, EPI_ACCUM>(tmA, tmB, p, st);
+  return (ncta == 1) ? launch_gemm<true, true, 1, EPI_ACCUM>(tmA, tmB, tmA, p, st)
+                     : launch_gemm<true, true, 2, EPI_ACCUM>(tmA, tmB, tmA, p, st);
 }

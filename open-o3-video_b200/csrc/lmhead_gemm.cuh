@@ -48,7 +48,7 @@ struct GemmParams {
   int32_t accumulate;
 };
 
-template <int kNCta>
+template <int kNCta, bool kStaging>
 struct GemmShape {
   static constexpr int BM = 128;                  // accumulator rows per CTA (TMEM lanes)
   static constexpr int UMMA_M = BM * kNCta;
@@ -60,8 +60,10 @@ struct GemmShape {
   static constexpr int B_BYTES = LOAD_BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (kNCta == 1) ? 4 : 6;
+  // K1 only: per epilogue warp 2 x [32 rows x 128 B] swizzled staging buffers for the TMA store of bf16 logits
+  static constexpr int STAGING_BYTES = kStaging ? 4 * 2 * 4096 : 0;
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // +1024: manual alignment
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;   // +1024: manual alignment
   static constexpr int TMEM_COLS = 512;
 };
 
@@ -71,8 +73,8 @@ constexpr float kLog2e = 1.4426950408889634f;
 template <bool kAMN, bool kBMN, int kNCta, int kEpi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const GemmParams p) {
-  using S = GemmShape<kNCta>;
+                   const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+  using S = GemmShape<kNCta, kEpi == EPI_STATS>;
   constexpr int BM = S::BM, BN = S::BN, BK = S::BK, STAGES = S::STAGES;
 
   extern __shared__ uint8_t smem_raw[];
@@ -81,7 +83,8 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint8_t* smem = smem_raw + (((raw_u32 + 1023u) & ~1023u) - raw_u32);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * S::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  uint8_t* staging = smem + STAGES * S::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES + S::STAGING_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
@@ -96,6 +99,7 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
+    if (kEpi == EPI_STATS && p.logits != nullptr) ptx::prefetch_tmap(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -208,6 +212,8 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int row_in_tile = q * 32 + lane;
     const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t acc_iter = 0;
+    const uint32_t stg_warp = ptx::smem_u32(staging) + (uint32_t)(warp - 4) * 8192u;   // this warp's 2 buffers
+    uint32_t sbuf = 0;
     for (int item = worker; item < num_items; item += num_workers) {
       const int n_grp = item % p.num_n_groups, m_blk = item / p.num_n_groups;
       const int64_t row = (int64_t)m_blk * S::UMMA_M + (int64_t)rank * BM + row_in_tile;
@@ -234,21 +240,36 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           ptx::tmem_ld_wait();
           const int64_t col0 = n0 + c * 32;
           if constexpr (kEpi == EPI_STATS) {
-            if (p.logits != nullptr && row_ok) {
-              // bf16 copy of the tile for the chunked backward (vector granularity: 8 columns)
-              __nv_bfloat16* dst = p.logits + row * p.ld_logits + col0;
+            if (p.logits != nullptr) {
+              // bf16 copy of the tile for the chunked backward: [32 rows x 64 cols] per warp staged in
+              // 128B-swizzled smem (conflict-free 16-byte stores), then ONE coalesced TMA store; the
+              // box is clipped against [T, V] by the TMA unit, so ragged edges need no guards.
+              const int half = c & 1;
+              if (half == 0) {
+                if (lane == 0) ptx::bulk_wait_read<1>();   // the store that last read this buffer is done
+                __syncwarp();
+              }
+              const uint32_t rowbase = stg_warp + sbuf * 4096u + (uint32_t)lane * 128u;
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                if (col0 + j * 8 < p.N) {
-                  uint4 pk;
-                  __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]));
-                  __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
-                  __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5]));
-                  __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]));
-                  pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                  pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                  *reinterpret_cast<uint4*>(dst + j * 8) = pk;
+                __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]));
+                __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
+                __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5]));
+                __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]));
+                const uint32_t chunk16 = (uint32_t)(half * 4 + j) ^ ((uint32_t)lane & 7u);   // 128B swizzle
+                ptx::st_shared_v4(rowbase + (chunk16 << 4), *reinterpret_cast<uint32_t*>(&t0),
+                                  *reinterpret_cast<uint32_t*>(&t1), *reinterpret_cast<uint32_t*>(&t2),
+                                  *reinterpret_cast<uint32_t*>(&t3));
+              }
+              if (half == 1) {
+                ptx::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  const int32_t r0 = (int32_t)((int64_t)m_blk * S::UMMA_M + (int64_t)rank * BM + q * 32);
+                  ptx::tma_store_2d(&tmC, stg_warp + sbuf * 4096u, (int32_t)(col0 - 32), r0);
+                  ptx::bulk_commit();
                 }
+                sbuf ^= 1u;
               }
             }
             if (col0 + 32 > p.N) {                 // ragged last tile: TMA zero-filled columns are not vocabulary
@@ -339,6 +360,8 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     }
   }
+
+  if (kEpi == EPI_STATS && warp >= 4 && lane == 0 && p.logits != nullptr) ptx::bulk_wait<0>();   // smem must outlive the stores
 
   // ================================ teardown ================================
   ptx::tc_fence_before();

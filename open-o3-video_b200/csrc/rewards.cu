@@ -112,7 +112,7 @@ rewards_kernel(const o3v_rewards_soa s, double* __restrict__ out) {
 
   // ---- thk_temporal_point_reward: adaptive temporal proximity (:439, :452-467)
   if (has_think && !(task == O3V_TASK_VISUAL_QA || temporal || general) && n_times > 0) {
-    const double sp = s.step_percent;
+    const double sp = s.step_percent[q];
     const double sigma = (sp < 0.75) ? dmul(4.0, dsub(1.0, sp)) : 1.0;  // :459-462
     const double two_s2 = dmul(2.0, dmul(sigma, sigma));
     double total = 0.0;
@@ -226,7 +226,7 @@ extern "C" int o3v_grounded_rewards(const o3v_rewards_soa* soa, double* out, voi
     return O3V_ERR_INVALID_ARG;
   if (!s.flags || !s.ans_seg || !s.ans_box || !s.n_times || !s.think_times || !s.n_claims || !s.claim_t ||
       !s.claim_nbox || !s.claim_valid || !s.claim_box || !s.n_tboxes || !s.tbox_valid || !s.think_box ||
-      !s.task || !s.gt_flags || !s.gt_seg || !s.gt_vbox || !s.image_size || !s.image_refine || !s.n_kf ||
+      !s.task || !s.step_percent || !s.gt_flags || !s.gt_seg || !s.gt_vbox || !s.image_size || !s.image_refine || !s.n_kf ||
       !s.kf_time || !s.n_obj || !s.n_gtbox || !s.gt_box)
     return O3V_ERR_INVALID_ARG;
   const uintptr_t al = (uintptr_t)s.ans_box | (uintptr_t)s.claim_box | (uintptr_t)s.think_box |

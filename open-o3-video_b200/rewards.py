@@ -124,7 +124,7 @@ def pack_rollouts(rollouts: Sequence[dict], G: int = 1):
         claim_t=np.zeros((R, C)), claim_nbox=np.zeros((R, C), np.int32), claim_valid=np.zeros((R, C), np.uint32),
         claim_box=np.zeros((R, C, Bc, 4)), n_tboxes=np.zeros(R, np.int32), tbox_valid=np.zeros(R, np.uint32),
         think_box=np.zeros((R, Tb, 4)),
-        task=np.zeros(Q, np.int32), gt_flags=np.zeros(Q, np.int32), gt_seg=np.zeros((Q, 2)),
+        task=np.zeros(Q, np.int32), step_percent=np.zeros(Q), gt_flags=np.zeros(Q, np.int32), gt_seg=np.zeros((Q, 2)),
         gt_vbox=np.zeros((Q, 4)), image_size=np.ones((Q, 2)), image_refine=np.ones((Q, 2)),
         n_kf=np.zeros(Q, np.int32), kf_time=np.zeros((Q, K)), n_obj=np.zeros((Q, K), np.int32),
         n_gtbox=np.zeros((Q, K, O), np.int32), gt_box=np.zeros((Q, K, O, Gb, 4)))
@@ -157,6 +157,7 @@ def pack_rollouts(rollouts: Sequence[dict], G: int = 1):
         if g["task"] not in TASK_IDS:
             raise ValueError("Unknown task: %s" % g["task"])            # data_loader.py:33
         a["task"][q] = TASK_IDS[g["task"]]
+        a["step_percent"][q] = g["step_percent"]
         a["gt_seg"][q] = g["gt_seg"]
         if g["gt_vbox"] is not None:
             a["gt_flags"][q] = GF_VBOX
@@ -189,7 +190,7 @@ def to_device(arrays, device):
     return out
 
 
-def grounded_rewards_device(dev_arrays, dims, step_percent: float, out: Optional[torch.Tensor] = None):
+def grounded_rewards_device(dev_arrays, dims, out: Optional[torch.Tensor] = None):
     """K4 launch on device-resident SoA -> [R, 5] float64 (device)."""
     any_t = dev_arrays["flags"]
     if not any_t.is_cuda:
@@ -201,8 +202,7 @@ def grounded_rewards_device(dev_arrays, dims, step_percent: float, out: Optional
     soa.R, soa.G = R, dims["G"]
     for k in ("P", "C", "Bc", "Tb", "K", "O", "Gb"):
         setattr(soa, k, dims[k])
-    soa.step_percent = float(step_percent)
-    for name, _ in _lib.RewardsSoA._fields_[11:]:
+    for name, _ in _lib.RewardsSoA._fields_[10:]:
         setattr(soa, name, dev_arrays[name].data_ptr())
     with torch.cuda.device(any_t.device):
         _lib.call("o3v_grounded_rewards", 1, _lib.load().o3v_grounded_rewards, ctypes.byref(soa),
@@ -214,7 +214,7 @@ def rewards_from_rollouts(rollouts: Sequence[dict], G: int = 1, device="cuda") -
     if len(rollouts) == 0:
         return torch.empty(0, 5, dtype=torch.float64, device=device)
     arrays, dims = pack_rollouts(rollouts, G)
-    return grounded_rewards_device(to_device(arrays, device), dims, rollouts[0]["step_percent"])
+    return grounded_rewards_device(to_device(arrays, device), dims)
 
 
 # ----------------------------------------------------------------------------- reference-named callables

@@ -25,8 +25,10 @@ def cta_pair(request):
     _lib.set_tunable("fwd_groups", 0)
 
 
-def _rel(a, b):
-    return (np.abs(a - b) / np.maximum(np.abs(b), 1e-6)).max()
+def _rel(a, b, floor=2e-5):
+    # relative error with an absolute floor: planted rows have reference log-probs of exactly 0
+    # (and logits of +-60 whose fp32 spacing is 4e-6), where a pure ratio is meaningless
+    return (np.abs(a - b) / np.maximum(np.abs(b), floor / 1e-3)).max()
 
 
 # T, H, V, planted, fwd_groups
