@@ -1,8 +1,9 @@
-"""Kernel-level timing sweep on a B200 (CUDA events, L2 flushed between iterations).
-Usage: python tools/sweep.py [T] [head]   -> one line per (kernel, tile mode, knob)."""
+"""Kernel-level timing sweep on a B200 (CUDA events).
+Usage: python tools/sweep.py [T] [head] [sustain_iters]
+Each kernel is timed back to back `sustain_iters` times (default 8) after a warm-up so that the
+power cap / clock droop of a long step is part of the number; min and mean are printed."""
 import os
 import sys
-import time
 
 import torch
 
@@ -10,22 +11,23 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from open_o3_video_b200 import _lib, logprob  # noqa: E402
 
 
-def timeit(fn, iters=3, warmup=1):
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    for _ in range(warmup):
+def timeit(fn, iters):
+    for _ in range(2):
         fn()
-    ts = []
-    for _ in range(iters):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); fn(); b.record(); torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b))
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    evs[0].record()
+    for i in range(iters):
+        fn()
+        evs[i + 1].record()
+    torch.cuda.synchronize()
+    ts = [evs[i].elapsed_time(evs[i + 1]) for i in range(iters)]
     return min(ts), sum(ts) / len(ts)
 
 
 def main():
     T = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
     head = sys.argv[2] if len(sys.argv) > 2 else "7b"
+    iters = int(sys.argv[3]) if len(sys.argv) > 3 else 8
     H, V = (3584, 152064) if head == "7b" else (4096, 151936)
     dev = "cuda"
     g = torch.Generator(device=dev).manual_seed(0)
@@ -35,29 +37,35 @@ def main():
     z = torch.empty(T, V, dtype=torch.bfloat16, device=dev)
     dW = torch.zeros(V, H, device=dev)
     flops = 2.0 * T * H * V
-    print("T=%d H=%d V=%d  (2THV = %.3e flop)" % (T, H, V, flops), flush=True)
+    print("T=%d H=%d V=%d  (2THV = %.3e flop), %d back-to-back iterations" % (T, H, V, flops, iters), flush=True)
 
     def report(name, fn):
         try:
-            best, mean = timeit(fn)
-            print("%-34s best %8.3f ms  mean %8.3f ms  %7.1f TFLOP/s" % (name, best, mean, flops / best / 1e9), flush=True)
+            best, mean = timeit(fn, iters)
+            print("%-36s best %8.3f ms %7.1f TF | mean %8.3f ms %7.1f TF" %
+                  (name, best, flops / best / 1e9, mean, flops / mean / 1e9), flush=True)
         except Exception as e:  # keep sweeping
-            print("%-34s FAILED: %s" % (name, e), flush=True)
+            print("%-36s FAILED: %s" % (name, e), flush=True)
 
     # library reference point (not on the product path): cuBLAS bf16 GEMM of the same shape
     report("cublas hidden@W^T -> bf16", lambda: torch.matmul(hidden, weight.T, out=z))
+    lse = torch.zeros(T, device=dev)
+    gl = torch.full((T,), 1e-3, device=dev)
     for cta in (1, 2):
         _lib.set_tunable("cta_pair", cta)
-        for groups in (0, 1, 2, 4, 8, 16):
+        for groups in (2, 4, 8, 16, 32):
             _lib.set_tunable("fwd_groups", groups)
-            report("K1 fwd stats      cta%d groups=%d" % (cta, groups), lambda: logprob.lmhead_stats(hidden, weight, targets))
+            report("K1 fwd stats       cta%d groups=%d" % (cta, groups), lambda: logprob.lmhead_stats(hidden, weight, targets))
+        for groups in (4, 8, 16):
+            _lib.set_tunable("fwd_groups", groups)
+            report("K1 fwd stats+store cta%d groups=%d" % (cta, groups), lambda: logprob.lmhead_stats(hidden, weight, targets, 0, z))
         _lib.set_tunable("fwd_groups", 0)
-        report("K1 fwd stats+store cta%d" % cta, lambda: logprob.lmhead_stats(hidden, weight, targets, 0, z))
-        lse = torch.zeros(T, device=dev); gl = torch.full((T,), 1e-3, device=dev)
+        z.normal_(0, 1.0)
         report("dlogits (elementwise)", lambda: logprob.dlogits_(z, lse, gl, targets))
         z.normal_(0, 0.01)
         report("K2a dH = P.W        cta%d" % cta, lambda: logprob.bwd_dhidden(z, weight))
         report("K2b dW += P^T.h     cta%d" % cta, lambda: logprob.bwd_dweight(z, hidden, dW, True))
+    report("cublas hidden@W^T -> bf16 (again)", lambda: torch.matmul(hidden, weight.T, out=z))
     _lib.set_tunable("cta_pair", 1)
 
 
