@@ -117,13 +117,19 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (kNCta == 2) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  if (tmem_base != 0u) __trap();   // 512 columns = the whole TMEM of this SM (1 CTA/SM): base is lane 0, column 0
 
   const int num_workers = gridDim.x / kNCta;
   const int worker = blockIdx.x / kNCta;
   const int num_items = p.num_m_blocks * p.num_n_groups;
   const int num_k_blocks = (int)((p.K + BK - 1) / BK);
 
-  if (warp == 0 && lane == 0) {
+  // The two single-instruction-stream roles run with the WHOLE warp converged and only the
+  // TMA / tcgen05 instructions predicated on one elected lane: every operand is then provably
+  // warp-uniform and lives in uniform registers (a lane-0-only branch makes ptxas wrap each
+  // tcgen05.mma in an ELECT + R2UR.BROADCAST loop, ~130 instructions per k-block, which starved
+  // the tensor pipe: see profiles/r1_notes.md).
+  if (warp == 0) {
     // ================================ TMA producer ================================
     int stage = 0; uint32_t phase = 0;
     for (int item = worker; item < num_items; item += num_workers) {
@@ -135,36 +141,39 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int n0 = nt * BN + (int)rank * S::LOAD_BN;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           ptx::mbar_wait(&empty[stage], phase ^ 1u);
-          const int k0 = kb * BK;
-          uint8_t* sa = smem_a + stage * S::A_BYTES;
-          uint8_t* sb = smem_b + stage * S::B_BYTES;
-          if constexpr (kNCta == 1) {
-            ptx::mbar_expect_tx(&full[stage], S::STAGE_BYTES);
-          } else {
-            if (rank == 0) ptx::mbar_expect_tx(&full[stage], 2 * S::STAGE_BYTES);
-            else ptx::mbar_arrive_cluster(&full[stage], 0);
-          }
-          auto load = [&](void* dst, const CUtensorMap* tm, int c0, int c1) {
-            if constexpr (kNCta == 1) ptx::tma_load_2d(dst, tm, &full[stage], c0, c1);
-            else ptx::tma_load_2d_2sm(dst, tm, &full[stage], c0, c1);
-          };
-          if constexpr (!kAMN) {
-            load(sa, &tmA, k0, m0);                                   // [128 rows][64 k] K-major
-          } else {
+          if (ptx::elect_one()) {
+            const int k0 = kb * BK;
+            uint8_t* sa = smem_a + stage * S::A_BYTES;
+            uint8_t* sb = smem_b + stage * S::B_BYTES;
+            if constexpr (kNCta == 1) {
+              ptx::mbar_expect_tx(&full[stage], S::STAGE_BYTES);
+            } else {
+              if (rank == 0) ptx::mbar_expect_tx(&full[stage], 2 * S::STAGE_BYTES);
+              else ptx::mbar_arrive_cluster(&full[stage], 0);
+            }
+            auto load = [&](void* dst, const CUtensorMap* tm, int c0, int c1) {
+              if constexpr (kNCta == 1) ptx::tma_load_2d(dst, tm, &full[stage], c0, c1);
+              else ptx::tma_load_2d_2sm(dst, tm, &full[stage], c0, c1);
+            };
+            if constexpr (!kAMN) {
+              load(sa, &tmA, k0, m0);                                   // [128 rows][64 k] K-major
+            } else {
 #pragma unroll
-            for (int i = 0; i < BM / 64; ++i) load(sa + i * (BK * 128), &tmA, m0 + 64 * i, k0);   // [64 k][64 m] atoms
-          }
-          if constexpr (!kBMN) {
-            load(sb, &tmB, k0, n0);
-          } else {
+              for (int i = 0; i < BM / 64; ++i) load(sa + i * (BK * 128), &tmA, m0 + 64 * i, k0);   // [64 k][64 m] atoms
+            }
+            if constexpr (!kBMN) {
+              load(sb, &tmB, k0, n0);
+            } else {
 #pragma unroll
-            for (int i = 0; i < S::LOAD_BN / 64; ++i) load(sb + i * (BK * 128), &tmB, n0 + 64 * i, k0);
+              for (int i = 0; i < S::LOAD_BN / 64; ++i) load(sb + i * (BK * 128), &tmB, n0 + 64 * i, k0);
+            }
           }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ================================ MMA issuer (leader CTA only) ================================
     if (rank == 0) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(S::UMMA_M, BN, kAMN, kBMN);
@@ -173,6 +182,9 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       constexpr uint32_t a_lbo = kAMN ? BK * 128 : 0, b_lbo = kBMN ? BK * 128 : 0;
       constexpr uint32_t a_kstep = kAMN ? S::UMMA_K * 128 : S::UMMA_K * 2;
       constexpr uint32_t b_kstep = kBMN ? S::UMMA_K * 128 : S::UMMA_K * 2;
+      // descriptors of stage 0 / k 0; later ones differ only in the 14-bit start-address field
+      const uint64_t da0 = ptx::make_smem_desc(ptx::smem_u32(smem_a), a_lbo, 1024);
+      const uint64_t db0 = ptx::make_smem_desc(ptx::smem_u32(smem_b), b_lbo, 1024);
       int stage = 0; uint32_t phase = 0; uint32_t acc_iter = 0;
       for (int item = worker; item < num_items; item += num_workers) {
         const int n_grp = item % p.num_n_groups;
@@ -182,20 +194,21 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const uint32_t a = acc_iter & 1u, aphase = (acc_iter >> 1) & 1u;
           ptx::mbar_wait(&tempty[a], aphase ^ 1u);           // epilogue has drained this accumulator
           ptx::tc_fence_after();
-          const uint32_t tmem_d = tmem_base + a * BN;
+          const uint32_t tmem_d = a * BN;                    // TMEM base is 0: this CTA owns all 512 columns
           for (int kb = 0; kb < num_k_blocks; ++kb) {
             ptx::mbar_wait(&full[stage], phase);             // TMA bytes have landed (both CTAs)
             ptx::tc_fence_after();
-            const uint32_t a_base = ptx::smem_u32(smem_a + stage * S::A_BYTES);
-            const uint32_t b_base = ptx::smem_u32(smem_b + stage * S::B_BYTES);
+            if (ptx::elect_one()) {
+              const uint64_t da = da0 + (uint64_t)((uint32_t)(stage * S::A_BYTES) >> 4);
+              const uint64_t db = db0 + (uint64_t)((uint32_t)(stage * S::B_BYTES) >> 4);
 #pragma unroll
-            for (int k = 0; k < BK / S::UMMA_K; ++k) {
-              const uint64_t da = ptx::make_smem_desc(a_base + k * a_kstep, a_lbo, 1024);
-              const uint64_t db = ptx::make_smem_desc(b_base + k * b_kstep, b_lbo, 1024);
-              ptx::umma_bf16<kNCta>(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < BK / S::UMMA_K; ++k)
+                ptx::umma_bf16<kNCta>(tmem_d, da + (uint64_t)((k * a_kstep) >> 4), db + (uint64_t)((k * b_kstep) >> 4),
+                                      idesc, (kb | k) != 0 ? 1u : 0u);
+              ptx::umma_commit<kNCta>(&empty[stage]);        // frees the smem stage when the MMAs retire
+              if (kb == num_k_blocks - 1) ptx::umma_commit<kNCta>(&tfull[a]);   // accumulator ready
             }
-            ptx::umma_commit<kNCta>(&empty[stage]);          // frees the smem stage when the MMAs retire
-            if (kb == num_k_blocks - 1) ptx::umma_commit<kNCta>(&tfull[a]);   // accumulator ready
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -210,7 +223,7 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     // ================================ epilogue warps ================================
     const int q = warp & 3;                       // TMEM lane quadrant this warp may access
     const int row_in_tile = q * 32 + lane;
-    const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t tmem_row = ((uint32_t)(q * 32) << 16);
     uint32_t acc_iter = 0;
     const uint32_t stg_warp = ptx::smem_u32(staging) + (uint32_t)(warp - 4) * 8192u;   // this warp's 2 buffers
     uint32_t sbuf = 0;
