@@ -50,6 +50,12 @@ int o3v_check_device(void);
  *   "fwd_groups" vocab splits per token block in K1 (0 = auto)
  *   "max_ctas"   cap on the persistent grid (0 = all SMs) */
 int o3v_set_tunable(const char* name, int value);
+/* Diagnostic: the tcgen05 GEMM template on an arbitrary problem, D[M,N] (+)= A . B^T with
+ * bf16 operands.  a_mn / b_mn = 0: operand stored [rows, K] (K contiguous, "K-major");
+ * = 1: stored [K, rows] (rows contiguous, "MN-major").  out: bf16 or fp32 [M, ld_out]. */
+int o3v_debug_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                   int32_t a_mn, int32_t b_mn, void* out, int64_t ld_out, int32_t out_fp32,
+                   int32_t accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * K3a  first-EOS mask.   Replaces trainer/grpo_trainer.py:590-596.

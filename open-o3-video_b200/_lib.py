@@ -29,6 +29,8 @@ SIGNATURES = {
     "o3v_strerror": (c_char_p, [c_int]),
     "o3v_check_device": (c_int, []),
     "o3v_set_tunable": (c_int, [c_char_p, c_int]),
+    "o3v_debug_gemm": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_int32,
+                               c_void_p, c_int64, c_int32, c_int32, c_void_p]),
     "o3v_eos_mask": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "o3v_lmhead_fwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "o3v_lmhead_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,

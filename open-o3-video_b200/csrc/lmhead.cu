@@ -300,3 +300,34 @@ extern "C" int o3v_lmhead_bwd_dweight(const void* dlogits, int64_t ld_dlogits, c
   return (ncta == 1) ? launch_gemm<true, true, 1, EPI_ACCUM>(tmA, tmB, tmA, p, st)
                      : launch_gemm<true, true, 2, EPI_ACCUM>(tmA, tmB, tmA, p, st);
 }
+
+extern "C" int o3v_debug_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N,
+                              int64_t K, int32_t a_mn, int32_t b_mn, void* out, int64_t ld_out,
+                              int32_t out_fp32, int32_t accumulate, void* stream) {
+  if (!A || !B || !out || M <= 0 || N <= 0 || K <= 0) return O3V_ERR_INVALID_ARG;
+  int rc = check_device();
+  if (rc) return rc;
+  const int ncta = g_cta_pair;
+  GemmParams p = {};
+  p.M = M; p.N = N; p.K = K;
+  plan_tiles(p, ncta, (int)ceil_div(N, 256));
+  p.out = out; p.ld_out = ld_out; p.out_fp32 = (out_fp32 || accumulate) ? 1 : 0; p.accumulate = accumulate ? 1 : 0;
+  CUtensorMap tmA, tmB;
+  if (a_mn) { if ((rc = make_tmap_bf16(&tmA, A, M, K, lda, 64))) return rc; }
+  else      { if ((rc = make_tmap_bf16(&tmA, A, K, M, lda, 128))) return rc; }
+  if (b_mn) { if ((rc = make_tmap_bf16(&tmB, B, N, K, ldb, 64))) return rc; }
+  else      { if ((rc = make_tmap_bf16(&tmB, B, K, N, ldb, 256 / ncta))) return rc; }
+  cudaStream_t st = (cudaStream_t)stream;
+#define O3V_DISPATCH(AM, BM_, EPI)                                                    \
+  return (ncta == 1) ? launch_gemm<AM, BM_, 1, EPI>(tmA, tmB, tmA, p, st)             \
+                     : launch_gemm<AM, BM_, 2, EPI>(tmA, tmB, tmA, p, st)
+  if (accumulate) {
+    if (a_mn && b_mn) { O3V_DISPATCH(true, true, EPI_ACCUM); }
+    if (!a_mn && !b_mn) { O3V_DISPATCH(false, false, EPI_ACCUM); }
+    return O3V_ERR_INVALID_ARG;
+  }
+  if (!a_mn && b_mn) { O3V_DISPATCH(false, true, EPI_STORE); }
+  if (!a_mn && !b_mn) { O3V_DISPATCH(false, false, EPI_STORE); }
+  return O3V_ERR_INVALID_ARG;
+#undef O3V_DISPATCH
+}

@@ -53,10 +53,10 @@ def main():
     gl = torch.full((T,), 1e-3, device=dev)
     for cta in (1, 2):
         _lib.set_tunable("cta_pair", cta)
-        for groups in (2, 4, 8, 16, 32):
+        for groups in (4, 6):
             _lib.set_tunable("fwd_groups", groups)
             report("K1 fwd stats       cta%d groups=%d" % (cta, groups), lambda: logprob.lmhead_stats(hidden, weight, targets))
-        for groups in (4, 8, 16):
+        for groups in (4,):
             _lib.set_tunable("fwd_groups", groups)
             report("K1 fwd stats+store cta%d groups=%d" % (cta, groups), lambda: logprob.lmhead_stats(hidden, weight, targets, 0, z))
         _lib.set_tunable("fwd_groups", 0)
@@ -65,6 +65,25 @@ def main():
         z.normal_(0, 0.01)
         report("K2a dH = P.W        cta%d" % cta, lambda: logprob.bwd_dhidden(z, weight))
         report("K2b dW += P^T.h     cta%d" % cta, lambda: logprob.bwd_dweight(z, hidden, dW, True))
+    # experiment: the same dH / dW problems with pre-transposed (K-major) operands
+    import ctypes
+    lib = _lib.load()
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    Wt = weight.T.contiguous()            # [H, V]
+    dH = torch.empty(T, H, dtype=torch.bfloat16, device=dev)
+    def gemm(A, lda, B, ldb, M, N, K, amn, bmn, out, ldo, f32, acc):
+        _lib.check(lib.o3v_debug_gemm(P(A), lda, P(B), ldb, M, N, K, amn, bmn, P(out), ldo, f32, acc, st()), "debug_gemm")
+    for cta in (1, 2):
+        _lib.set_tunable("cta_pair", cta)
+        report("dH  A=P K-maj, B=W  MN-maj cta%d" % cta, lambda: gemm(z, V, weight, H, T, H, V, 0, 1, dH, H, 0, 0))
+        report("dH  A=P K-maj, B=Wt K-maj  cta%d" % cta, lambda: gemm(z, V, Wt, V, T, H, V, 0, 0, dH, H, 0, 0))
+    zt = z.T.contiguous()                 # [V, T]
+    ht = hidden.T.contiguous()            # [H, T]
+    for cta in (1, 2):
+        _lib.set_tunable("cta_pair", cta)
+        report("dW  A=P^T MN, B=h MN        cta%d" % cta, lambda: gemm(z, V, hidden, H, V, H, T, 1, 1, dW, H, 1, 1))
+        report("dW  A=Pt K-maj, B=ht K-maj  cta%d" % cta, lambda: gemm(zt, T, ht, T, V, H, T, 0, 0, dW, H, 1, 1))
     report("cublas hidden@W^T -> bf16 (again)", lambda: torch.matmul(hidden, weight.T, out=z))
     _lib.set_tunable("cta_pair", 1)
 
