@@ -161,6 +161,8 @@ def run_ours(args):
     _lib.check(_lib.load().o3v_check_device(), "o3v_check_device")
     if args.cta_pair:
         _lib.set_tunable("cta_pair", args.cta_pair)
+    if args.fwd_groups:
+        _lib.set_tunable("fwd_groups", args.fwd_groups)
 
     H, V, G, Tc = cfg["H"], cfg["V"], cfg["G"], cfg["Tc"]
     N = cfg["prompts"] * G
@@ -296,6 +298,7 @@ def main():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--chunk-tokens", type=int, default=32768)
     ap.add_argument("--cta-pair", type=int, default=0)
+    ap.add_argument("--fwd-groups", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -46,7 +46,8 @@ const char* o3v_strerror(int code);
 /* 0 if the CURRENT device is sm_100, else O3V_ERR_UNSUPPORTED_ARCH. */
 int o3v_check_device(void);
 /* Diagnostic knobs for bench sweeps (defaults are the shipped configuration):
- *   "cta_pair"   1 = one CTA per 128-row tile, 2 = cta_group::2 pairs (256-row tiles)
+ *   "cta_pair"   1 = one CTA per 128-row tile, 2 = cta_group::2 pairs (256-row tiles), all GEMMs;
+ *                "cta_pair_fwd" / "cta_pair_bwd" set it for K1 / K2 only (defaults 1 / 2)
  *   "fwd_groups" vocab splits per token block in K1 (0 = auto)
  *   "max_ctas"   cap on the persistent grid (0 = all SMs) */
 int o3v_set_tunable(const char* name, int value);

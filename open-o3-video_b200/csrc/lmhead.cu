@@ -11,7 +11,9 @@ namespace o3v {
 // ------------------------------------------------------------------------------------
 // Tunables (diagnostics / bench sweeps; defaults are what the product uses)
 // ------------------------------------------------------------------------------------
-static int g_cta_pair = 1;      // 1: one CTA per tile (UMMA M=128); 2: cta_group::2 pairs (M=256)
+// tile mode per kernel: 1 = one CTA per 128-row tile (UMMA M=128), 2 = cta_group::2 pair per 256-row tile
+static int g_cta_fwd = 1;       // K1 (measured: the 4-stage 1-CTA pipeline is ahead for the K-major sweep)
+static int g_cta_bwd = 2;       // K2a / K2b (measured: pairs are ahead once an operand is MN-major)
 static int g_fwd_groups = 0;    // n-groups (vocab splits) per m-block in K1; 0 = auto
 static int g_max_ctas = 0;      // cap on the persistent grid; 0 = all SMs
 
@@ -182,7 +184,9 @@ using namespace o3v;
 extern "C" int o3v_set_tunable(const char* name, int value) {
   if (!name) return O3V_ERR_INVALID_ARG;
   std::string n(name);
-  if (n == "cta_pair") { if (value != 1 && value != 2) return O3V_ERR_INVALID_ARG; g_cta_pair = value; }
+  if (n == "cta_pair") { if (value != 1 && value != 2) return O3V_ERR_INVALID_ARG; g_cta_fwd = g_cta_bwd = value; }
+  else if (n == "cta_pair_fwd") { if (value != 1 && value != 2) return O3V_ERR_INVALID_ARG; g_cta_fwd = value; }
+  else if (n == "cta_pair_bwd") { if (value != 1 && value != 2) return O3V_ERR_INVALID_ARG; g_cta_bwd = value; }
   else if (n == "fwd_groups") g_fwd_groups = value;
   else if (n == "max_ctas") g_max_ctas = value;
   else return O3V_ERR_INVALID_ARG;
@@ -211,7 +215,7 @@ extern "C" int o3v_lmhead_fwd(const void* hidden, const void* weight, const int6
   }
   int rc = check_device();
   if (rc) return rc;
-  const int ncta = g_cta_pair;
+  const int ncta = g_cta_fwd;
   GemmParams p = {};
   p.M = T; p.N = V; p.K = H;
   plan_tiles(p, ncta, fwd_groups(T, V, ncta));
@@ -266,7 +270,7 @@ extern "C" int o3v_lmhead_bwd_dhidden(const void* dlogits, int64_t ld_dlogits, c
   if (reinterpret_cast<uintptr_t>(d_hidden) & 15u) return O3V_ERR_ALIGNMENT;
   int rc = check_device();
   if (rc) return rc;
-  const int ncta = g_cta_pair;
+  const int ncta = g_cta_bwd;
   GemmParams p = {};
   p.M = T; p.N = H; p.K = V;                       // dH[t,h] = sum_v P[t,v] W[v,h]
   plan_tiles(p, ncta, (int)ceil_div(H, 256));       // one n-tile per item
@@ -288,7 +292,7 @@ extern "C" int o3v_lmhead_bwd_dweight(const void* dlogits, int64_t ld_dlogits, c
   if (reinterpret_cast<uintptr_t>(d_weight) & 15u) return O3V_ERR_ALIGNMENT;
   int rc = check_device();
   if (rc) return rc;
-  const int ncta = g_cta_pair;
+  const int ncta = g_cta_bwd;
   GemmParams p = {};
   p.M = V; p.N = H; p.K = T;                       // dW[v,h] = sum_t P[t,v] hidden[t,h]
   plan_tiles(p, ncta, (int)ceil_div(H, 256));
@@ -307,7 +311,7 @@ extern "C" int o3v_debug_gemm(const void* A, int64_t lda, const void* B, int64_t
   if (!A || !B || !out || M <= 0 || N <= 0 || K <= 0) return O3V_ERR_INVALID_ARG;
   int rc = check_device();
   if (rc) return rc;
-  const int ncta = g_cta_pair;
+  const int ncta = g_cta_bwd;
   GemmParams p = {};
   p.M = M; p.N = N; p.K = K;
   plan_tiles(p, ncta, (int)ceil_div(N, 256));

@@ -66,9 +66,9 @@ def _gather_stats(stats, group):
         return stats.unsqueeze(0)
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    out = torch.empty((world,) + tuple(stats.shape), dtype=stats.dtype, device=stats.device)
-    dist.all_gather_into_tensor(out, stats.contiguous(), group=group)
-    return out
+    out = torch.empty((world * stats.shape[0],) + tuple(stats.shape[1:]), dtype=stats.dtype, device=stats.device)
+    dist.all_gather_into_tensor(out, stats.contiguous(), group=group)     # rank-major concatenation along dim 0
+    return out.view((world,) + tuple(stats.shape))
 
 
 def dlogits_(logits, lse, grad_logp, targets, v_offset=0, V=None):

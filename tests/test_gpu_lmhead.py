@@ -21,7 +21,8 @@ def cta_pair(request):
     from open_o3_video_b200 import _lib
     _lib.set_tunable("cta_pair", request.param)
     yield request.param
-    _lib.set_tunable("cta_pair", 1)
+    _lib.set_tunable("cta_pair_fwd", 1)
+    _lib.set_tunable("cta_pair_bwd", 2)
     _lib.set_tunable("fwd_groups", 0)
 
 

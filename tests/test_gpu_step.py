@@ -49,7 +49,8 @@ def test_fused_step_matches_oracle(N, Tc, G, H, V, chunk, off_policy, cta):
                                          cu(mask), cu(rpf), G, 0.04, 0.2, 0.2, True, cu(old), chunk_tokens=chunk)
         torch.cuda.synchronize()
     finally:
-        _lib.set_tunable("cta_pair", 1)
+        _lib.set_tunable("cta_pair_fwd", 1)
+        _lib.set_tunable("cta_pair_bwd", 2)
     lp = out["per_token_logps"].cpu()
     assert ((lp - lp_ref).abs() / lp_ref.abs().clamp(min=1e-6)).max() < 1e-3
     np.testing.assert_allclose(out["loss"].item(), exp["loss"].item(), rtol=1e-3, atol=1e-6)
