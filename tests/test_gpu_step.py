@@ -90,3 +90,47 @@ def test_c1_shape_known_answer():
         ref[s:s + 512] = z.log_softmax(-1).gather(1, t[s:s + 512, None])[:, 0]
     assert ((lp.view(-1) - ref).abs() / ref.abs()).max().item() < 1e-3
     assert out["d_hidden"].float().abs().max().item() > 0 and torch.isfinite(out["d_weight"]).all()
+
+
+def test_trainer_mixin_keeps_reference_contract():
+    """`_get_per_token_logps(self, model, input_ids, **kwargs) -> [B, L-1]` (grpo_trainer.py:371) on a
+    fake model whose backbone returns fixed hidden states, against the oracle; plus the
+    prompt-skipping variant and the loss/metrics block."""
+    import types
+    from open_o3_video_b200.trainer import O3VB200TrainerMixin
+    B, L, H, V, G = 4, 40, 128, 3000, 4
+    hidden, weight, _ = synth.head_inputs(B * L, H, V, seed=31)
+    ids = torch.randint(0, V, (B, L), generator=torch.Generator().manual_seed(32))
+    exp = ologps.per_token_logps(hidden.view(B, L, H), weight, ids)
+
+    class Backbone(torch.nn.Module):
+        def forward(self, input_ids=None, **kw):
+            return types.SimpleNamespace(last_hidden_state=hidden.view(B, L, H).cuda().bfloat16())
+
+    class Model(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.model = Backbone()
+            self.lm_head = torch.nn.Linear(H, V, bias=False).cuda().bfloat16()
+            self.lm_head.weight.data.copy_(weight)
+
+    class T(O3VB200TrainerMixin):
+        num_generations, beta, epsilon_low, epsilon_high, gspo = G, 0.04, 0.2, 0.2, True
+        reward_funcs = []
+
+    t, model = T(), torch.nn.parallel.DataParallel(Model()) if False else Model()
+    lp = t._get_per_token_logps(model, ids.cuda())
+    assert lp.shape == (B, L - 1)
+    assert ((lp.cpu() - exp).abs() / exp.abs().clamp(min=1e-2)).max() < 1e-3
+    t.o3v_prompt_length = 25
+    lp2 = t._get_per_token_logps(model, ids.cuda())
+    assert lp2.shape == (B, L - 1) and torch.equal(lp2[:, 24:], lp[:, 24:]) and (lp2[:, :24] == 0).all()
+    # loss + metrics keys of grpo_trainer.py:711-738
+    comp = lp[:, 24:]
+    mask = torch.ones_like(comp, dtype=torch.int32)
+    rpf = torch.rand(B, 2, device="cuda")
+    loss = t.compute_policy_loss(comp.detach().requires_grad_(True), comp.detach() + 0.1, mask, rpf)
+    ref = ogspo.gspo_step(comp.cpu(), comp.cpu() + 0.1, mask.cpu(), rpf.cpu(), G, 0.04)
+    assert abs(loss.item() - ref["loss"].item()) < 1e-6
+    assert set(t._metrics) >= {"completion_length", "all_wrong", "all_correct", "reward", "reward_std", "kl"}
+    assert abs(t._metrics["kl"][0] - ref["mean_kl"].item()) < 1e-6
