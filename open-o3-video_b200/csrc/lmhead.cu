@@ -13,7 +13,8 @@ namespace o3v {
 // ------------------------------------------------------------------------------------
 // tile mode per kernel: 1 = one CTA per 128-row tile (UMMA M=128), 2 = cta_group::2 pair per 256-row tile
 static int g_cta_fwd = 1;       // K1 (measured: the 4-stage 1-CTA pipeline is ahead for the K-major sweep)
-static int g_cta_bwd = 2;       // K2a / K2b (measured: pairs are ahead once an operand is MN-major)
+static int g_cta_bwd = 2;       // K2a / K2b
+static int g_bwd_wide = 1;      // K2a / K2b on pairs: 256x512 tiles (both TMEM accumulators per tile)
 static int g_fwd_groups = 0;    // n-groups (vocab splits) per m-block in K1; 0 = auto
 static int g_max_ctas = 0;      // cap on the persistent grid; 0 = all SMs
 
@@ -57,11 +58,11 @@ static int make_tmap_bf16(CUtensorMap* tm, const void* base, int64_t inner, int6
 // ------------------------------------------------------------------------------------
 // launch
 // ------------------------------------------------------------------------------------
-template <bool kAMN, bool kBMN, int kNCta, int kEpi>
+template <bool kAMN, bool kBMN, int kNCta, int kEpi, int kAcc = 1>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
                        cudaStream_t st) {
-  using S = GemmShape<kNCta, kEpi == EPI_STATS>;
-  auto kern = lmhead_gemm_kernel<kAMN, kBMN, kNCta, kEpi>;
+  using S = GemmShape<kNCta, kEpi == EPI_STATS, kAcc>;
+  auto kern = lmhead_gemm_kernel<kAMN, kBMN, kNCta, kEpi, kAcc>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
@@ -89,9 +90,9 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   return O3V_OK;
 }
 
-static void plan_tiles(GemmParams& p, int ncta, int n_groups_hint) {
+static void plan_tiles(GemmParams& p, int ncta, int n_groups_hint, int acc = 1) {
   p.num_m_blocks = (int32_t)ceil_div(p.M, 128 * ncta);
-  p.num_n_tiles = (int32_t)ceil_div(p.N, 256);
+  p.num_n_tiles = (int32_t)ceil_div(p.N, 256 * acc);
   int groups = n_groups_hint < 1 ? 1 : n_groups_hint;
   if (groups > p.num_n_tiles) groups = p.num_n_tiles;
   p.tiles_per_group = (int32_t)ceil_div(p.num_n_tiles, groups);
@@ -187,6 +188,7 @@ extern "C" int o3v_set_tunable(const char* name, int value) {
   if (n == "cta_pair") { if (value != 1 && value != 2) return O3V_ERR_INVALID_ARG; g_cta_fwd = g_cta_bwd = value; }
   else if (n == "cta_pair_fwd") { if (value != 1 && value != 2) return O3V_ERR_INVALID_ARG; g_cta_fwd = value; }
   else if (n == "cta_pair_bwd") { if (value != 1 && value != 2) return O3V_ERR_INVALID_ARG; g_cta_bwd = value; }
+  else if (n == "bwd_wide") g_bwd_wide = value ? 1 : 0;
   else if (n == "fwd_groups") g_fwd_groups = value;
   else if (n == "max_ctas") g_max_ctas = value;
   else return O3V_ERR_INVALID_ARG;
@@ -273,12 +275,14 @@ extern "C" int o3v_lmhead_bwd_dhidden(const void* dlogits, int64_t ld_dlogits, c
   const int ncta = g_cta_bwd;
   GemmParams p = {};
   p.M = T; p.N = H; p.K = V;                       // dH[t,h] = sum_v P[t,v] W[v,h]
-  plan_tiles(p, ncta, (int)ceil_div(H, 256));       // one n-tile per item
+  const bool wide = (ncta == 2 && g_bwd_wide);
+  plan_tiles(p, ncta, 1 << 20, wide ? 2 : 1);       // one n-tile per item
   p.out = d_hidden; p.ld_out = H; p.out_fp32 = out_is_fp32 ? 1 : 0;
   CUtensorMap tmA, tmB;
   if ((rc = make_tmap_bf16(&tmA, dlogits, V, T, ld_dlogits, 128))) return rc;   // A = P, K-major (K = V)
   if ((rc = make_tmap_bf16(&tmB, weight, H, V, H, 64))) return rc;              // B = W, MN-major (N = H contiguous)
   cudaStream_t st = (cudaStream_t)stream;
+  if (wide) return launch_gemm<false, true, 2, EPI_STORE, 2>(tmA, tmB, tmA, p, st);
   return (ncta == 1) ? launch_gemm<false, true, 1, EPI_STORE>(tmA, tmB, tmA, p, st)
                      : launch_gemm<false, true, 2, EPI_STORE>(tmA, tmB, tmA, p, st);
 }
@@ -295,12 +299,14 @@ extern "C" int o3v_lmhead_bwd_dweight(const void* dlogits, int64_t ld_dlogits, c
   const int ncta = g_cta_bwd;
   GemmParams p = {};
   p.M = V; p.N = H; p.K = T;                       // dW[v,h] = sum_t P[t,v] hidden[t,h]
-  plan_tiles(p, ncta, (int)ceil_div(H, 256));
+  const bool wide = (ncta == 2 && g_bwd_wide);
+  plan_tiles(p, ncta, 1 << 20, wide ? 2 : 1);
   p.out = d_weight; p.ld_out = H; p.out_fp32 = 1; p.accumulate = accumulate ? 1 : 0;
   CUtensorMap tmA, tmB;
   if ((rc = make_tmap_bf16(&tmA, dlogits, V, T, ld_dlogits, 64))) return rc;    // A = P^T, MN-major (M = V contiguous)
   if ((rc = make_tmap_bf16(&tmB, hidden, H, T, H, 64))) return rc;              // B = hidden, MN-major
   cudaStream_t st = (cudaStream_t)stream;
+  if (wide) return launch_gemm<true, true, 2, EPI_ACCUM, 2>(tmA, tmB, tmA, p, st);
   return (ncta == 1) ? launch_gemm<true, true, 1, EPI_ACCUM>(tmA, tmB, tmA, p, st)
                      : launch_gemm<true, true, 2, EPI_ACCUM>(tmA, tmB, tmA, p, st);
 }

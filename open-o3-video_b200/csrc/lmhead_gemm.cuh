@@ -48,18 +48,26 @@ struct GemmParams {
   int32_t accumulate;
 };
 
-template <int kNCta, bool kStaging>
+// kAcc = 1: 256-column tiles, the two TMEM accumulator stages double-buffer the epilogue.
+// kAcc = 2: 512-column tiles (pairs only): both accumulators belong to ONE tile, every A smem tile
+//           feeds twice the MMAs (L2->SM bytes per flop -25 %, half as many sweeps over the other
+//           operand); the epilogue is not overlapped, fine when the K loop is hundreds of blocks.
+template <int kNCta, bool kStaging, int kAcc = 1>
 struct GemmShape {
+  static_assert(kAcc == 1 || (kAcc == 2 && kNCta == 2 && !kStaging), "512-column tiles need a CTA pair");
   static constexpr int BM = 128;                  // accumulator rows per CTA (TMEM lanes)
   static constexpr int UMMA_M = BM * kNCta;
-  static constexpr int BN = 256;                  // UMMA_N = accumulator columns per stage
+  static constexpr int BN = 256;                  // UMMA_N = columns per accumulator
+  static constexpr int TILE_N = BN * kAcc;        // output columns per work tile
+  static constexpr int ACC_STAGES = (kAcc == 1) ? 2 : 1;
   static constexpr int BK = 64;                   // one 128-byte swizzle atom of bf16
   static constexpr int UMMA_K = 16;
-  static constexpr int LOAD_BN = BN / kNCta;      // B rows fetched by each CTA of the pair
+  static constexpr int LOAD_BN = BN / kNCta;      // B rows per accumulator fetched by each CTA of the pair
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = LOAD_BN * BK * 2;
+  static constexpr int B1_BYTES = LOAD_BN * BK * 2;   // one accumulator's share of B
+  static constexpr int B_BYTES = kAcc * B1_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (kNCta == 1) ? 4 : 6;
+  static constexpr int STAGES = (kNCta == 1) ? 4 : (kAcc == 1 ? 6 : 4);
   // K1 only: per epilogue warp 2 x [32 rows x 128 B] swizzled staging buffers for the TMA store of bf16 logits
   static constexpr int STAGING_BYTES = kStaging ? 4 * 2 * 4096 : 0;
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
@@ -70,11 +78,11 @@ struct GemmShape {
 constexpr int kGemmThreads = 256;
 constexpr float kLog2e = 1.4426950408889634f;
 
-template <bool kAMN, bool kBMN, int kNCta, int kEpi>
+template <bool kAMN, bool kBMN, int kNCta, int kEpi, int kAcc = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
-  using S = GemmShape<kNCta, kEpi == EPI_STATS>;
+  using S = GemmShape<kNCta, kEpi == EPI_STATS, kAcc>;
   constexpr int BM = S::BM, BN = S::BN, BK = S::BK, STAGES = S::STAGES;
 
   extern __shared__ uint8_t smem_raw[];
@@ -138,7 +146,7 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int t_begin = n_grp * p.tiles_per_group;
       const int t_end = min(t_begin + p.tiles_per_group, p.num_n_tiles);
       for (int nt = t_begin; nt < t_end; ++nt) {
-        const int n0 = nt * BN + (int)rank * S::LOAD_BN;
+        const int n0 = nt * S::TILE_N + (int)rank * S::LOAD_BN;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           ptx::mbar_wait(&empty[stage], phase ^ 1u);
           if (ptx::elect_one()) {
@@ -161,11 +169,15 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
               for (int i = 0; i < BM / 64; ++i) load(sa + i * (BK * 128), &tmA, m0 + 64 * i, k0);   // [64 k][64 m] atoms
             }
-            if constexpr (!kBMN) {
-              load(sb, &tmB, k0, n0);
-            } else {
 #pragma unroll
-              for (int i = 0; i < S::LOAD_BN / 64; ++i) load(sb + i * (BK * 128), &tmB, n0 + 64 * i, k0);
+            for (int j = 0; j < kAcc; ++j) {                 // one B slab per accumulator
+              uint8_t* sbj = sb + j * S::B1_BYTES;
+              if constexpr (!kBMN) {
+                load(sbj, &tmB, k0, n0 + j * BN);
+              } else {
+#pragma unroll
+                for (int i = 0; i < S::LOAD_BN / 64; ++i) load(sbj + i * (BK * 128), &tmB, n0 + j * BN + 64 * i, k0);
+              }
             }
           }
           __syncwarp();
@@ -191,10 +203,10 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int t_begin = n_grp * p.tiles_per_group;
         const int t_end = min(t_begin + p.tiles_per_group, p.num_n_tiles);
         for (int nt = t_begin; nt < t_end; ++nt, ++acc_iter) {
-          const uint32_t a = acc_iter & 1u, aphase = (acc_iter >> 1) & 1u;
+          const uint32_t a = acc_iter % S::ACC_STAGES, aphase = (acc_iter / S::ACC_STAGES) & 1u;
           ptx::mbar_wait(&tempty[a], aphase ^ 1u);           // epilogue has drained this accumulator
           ptx::tc_fence_after();
-          const uint32_t tmem_d = a * BN;                    // TMEM base is 0: this CTA owns all 512 columns
+          const uint32_t tmem_d = a * S::TILE_N;             // TMEM base is 0: this CTA owns all 512 columns
           for (int kb = 0; kb < num_k_blocks; ++kb) {
             ptx::mbar_wait(&full[stage], phase);             // TMA bytes have landed (both CTAs)
             ptx::tc_fence_after();
@@ -202,9 +214,12 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               const uint64_t da = da0 + (uint64_t)((uint32_t)(stage * S::A_BYTES) >> 4);
               const uint64_t db = db0 + (uint64_t)((uint32_t)(stage * S::B_BYTES) >> 4);
 #pragma unroll
-              for (int k = 0; k < BK / S::UMMA_K; ++k)
-                ptx::umma_bf16<kNCta>(tmem_d, da + (uint64_t)((k * a_kstep) >> 4), db + (uint64_t)((k * b_kstep) >> 4),
-                                      idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int j = 0; j < kAcc; ++j)
+#pragma unroll
+                for (int k = 0; k < BK / S::UMMA_K; ++k)
+                  ptx::umma_bf16<kNCta>(tmem_d + j * BN, da + (uint64_t)((k * a_kstep) >> 4),
+                                        db + (uint64_t)((j * S::B1_BYTES + k * b_kstep) >> 4), idesc,
+                                        (kb | k) != 0 ? 1u : 0u);
               ptx::umma_commit<kNCta>(&empty[stage]);        // frees the smem stage when the MMAs retire
               if (kb == num_k_blocks - 1) ptx::umma_commit<kNCta>(&tfull[a]);   // accumulator ready
             }
@@ -216,7 +231,7 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       if (kNCta == 2 && acc_iter > 0) {
         // the peer's last remote arrivals must land before this CTA may exit
         const uint32_t last = acc_iter - 1;
-        ptx::mbar_wait(&tempty[last & 1u], (last >> 1) & 1u);
+        ptx::mbar_wait(&tempty[last % S::ACC_STAGES], (last / S::ACC_STAGES) & 1u);
       }
     }
   } else if (warp >= 4) {
@@ -242,14 +257,14 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
 
       for (int nt = t_begin; nt < t_end; ++nt, ++acc_iter) {
-        const uint32_t a = acc_iter & 1u, aphase = (acc_iter >> 1) & 1u;
+        const uint32_t a = acc_iter % S::ACC_STAGES, aphase = (acc_iter / S::ACC_STAGES) & 1u;
         ptx::mbar_wait(&tfull[a], aphase);
         ptx::tc_fence_after();
-        const int64_t n0 = (int64_t)nt * BN;
+        const int64_t n0 = (int64_t)nt * S::TILE_N;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = 0; c < S::TILE_N / 32; ++c) {
           uint32_t v[32];
-          ptx::tmem_ld_32x32b_x32(tmem_row + a * BN + c * 32, v);
+          ptx::tmem_ld_32x32b_x32(tmem_row + a * S::TILE_N + c * 32, v);
           ptx::tmem_ld_wait();
           const int64_t col0 = n0 + c * 32;
           if constexpr (kEpi == EPI_STATS) {

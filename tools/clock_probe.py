@@ -59,10 +59,11 @@ run("cublas", lambda: torch.matmul(hidden, weight.T, out=z))
 run("K1 stats cta1", lambda: logprob.lmhead_stats(hidden, weight, targets))
 run("K1 stats+store cta1", lambda: logprob.lmhead_stats(hidden, weight, targets, 0, z))
 z.normal_(0, 0.01)
-for cta in (1, 2):
+for cta, wide in ((1, 0), (2, 0), (2, 1)):
     _lib.set_tunable("cta_pair_bwd", cta)
-    run("K2a dH cta%d" % cta, lambda: logprob.bwd_dhidden(z, weight))
-    run("K2b dW cta%d" % cta, lambda: logprob.bwd_dweight(z, hidden, dW, True))
+    _lib.set_tunable("bwd_wide", wide)
+    run("K2a dH cta%d wide%d" % (cta, wide), lambda: logprob.bwd_dhidden(z, weight))
+    run("K2b dW cta%d wide%d" % (cta, wide), lambda: logprob.bwd_dweight(z, hidden, dW, True))
 z.zero_()
-run("K2a dH cta2 (P = 0)", lambda: logprob.bwd_dhidden(z, weight))
+run("K2a dH cta2 wide (P = 0)", lambda: logprob.bwd_dhidden(z, weight))
 run("cublas again", lambda: torch.matmul(hidden, weight.T, out=z))
