@@ -15,6 +15,8 @@ namespace o3v {
 static int g_cta_fwd = 1;       // K1 (measured: the 4-stage 1-CTA pipeline is ahead for the K-major sweep)
 static int g_cta_bwd = 2;       // K2a / K2b
 static int g_bwd_wide = 1;      // K2a / K2b on pairs: 256x512 tiles (both TMEM accumulators per tile)
+static int g_dh_mfast = 0;      // K2a item order (0 = n fastest)
+static int g_dw_mfast = 0;      // K2b item order
 static int g_fwd_groups = 0;    // n-groups (vocab splits) per m-block in K1; 0 = auto
 static int g_max_ctas = 0;      // cap on the persistent grid; 0 = all SMs
 
@@ -189,6 +191,8 @@ extern "C" int o3v_set_tunable(const char* name, int value) {
   else if (n == "cta_pair_fwd") { if (value != 1 && value != 2) return O3V_ERR_INVALID_ARG; g_cta_fwd = value; }
   else if (n == "cta_pair_bwd") { if (value != 1 && value != 2) return O3V_ERR_INVALID_ARG; g_cta_bwd = value; }
   else if (n == "bwd_wide") g_bwd_wide = value ? 1 : 0;
+  else if (n == "dh_mfast") g_dh_mfast = value ? 1 : 0;
+  else if (n == "dw_mfast") g_dw_mfast = value ? 1 : 0;
   else if (n == "fwd_groups") g_fwd_groups = value;
   else if (n == "max_ctas") g_max_ctas = value;
   else return O3V_ERR_INVALID_ARG;
@@ -277,7 +281,7 @@ extern "C" int o3v_lmhead_bwd_dhidden(const void* dlogits, int64_t ld_dlogits, c
   p.M = T; p.N = H; p.K = V;                       // dH[t,h] = sum_v P[t,v] W[v,h]
   const bool wide = (ncta == 2 && g_bwd_wide);
   plan_tiles(p, ncta, 1 << 20, wide ? 2 : 1);       // one n-tile per item
-  p.out = d_hidden; p.ld_out = H; p.out_fp32 = out_is_fp32 ? 1 : 0;
+  p.out = d_hidden; p.ld_out = H; p.out_fp32 = out_is_fp32 ? 1 : 0; p.m_fast = g_dh_mfast;
   CUtensorMap tmA, tmB;
   if ((rc = make_tmap_bf16(&tmA, dlogits, V, T, ld_dlogits, 128))) return rc;   // A = P, K-major (K = V)
   if ((rc = make_tmap_bf16(&tmB, weight, H, V, H, 64))) return rc;              // B = W, MN-major (N = H contiguous)
@@ -301,7 +305,7 @@ extern "C" int o3v_lmhead_bwd_dweight(const void* dlogits, int64_t ld_dlogits, c
   p.M = V; p.N = H; p.K = T;                       // dW[v,h] = sum_t P[t,v] hidden[t,h]
   const bool wide = (ncta == 2 && g_bwd_wide);
   plan_tiles(p, ncta, 1 << 20, wide ? 2 : 1);
-  p.out = d_weight; p.ld_out = H; p.out_fp32 = 1; p.accumulate = accumulate ? 1 : 0;
+  p.out = d_weight; p.ld_out = H; p.out_fp32 = 1; p.accumulate = accumulate ? 1 : 0; p.m_fast = g_dw_mfast;
   CUtensorMap tmA, tmB;
   if ((rc = make_tmap_bf16(&tmA, dlogits, V, T, ld_dlogits, 64))) return rc;    // A = P^T, MN-major (M = V contiguous)
   if ((rc = make_tmap_bf16(&tmB, hidden, H, T, H, 64))) return rc;              // B = hidden, MN-major

@@ -35,6 +35,8 @@ struct GemmParams {
   int32_t num_n_tiles;      // ceil(N / 256)
   int32_t tiles_per_group;  // consecutive n-tiles per work item (online softmax state lives across them)
   int32_t num_n_groups;     // ceil(num_n_tiles / tiles_per_group)
+  int32_t m_fast;           // item order: 0 = n-groups fastest (CTAs running together share A panels),
+                            //             1 = m-blocks fastest (they share B panels)
   // EPI_STATS
   const int64_t* targets;   // [M] global vocab ids
   int64_t v_offset;         // first vocab id of this slice
@@ -52,6 +54,13 @@ struct GemmParams {
 // kAcc = 2: 512-column tiles (pairs only): both accumulators belong to ONE tile, every A smem tile
 //           feeds twice the MMAs (L2->SM bytes per flop -25 %, half as many sweeps over the other
 //           operand); the epilogue is not overlapped, fine when the K loop is hundreds of blocks.
+__device__ __forceinline__ int item_n(const GemmParams& p, int item) {
+  return p.m_fast ? item / p.num_m_blocks : item % p.num_n_groups;
+}
+__device__ __forceinline__ int item_m(const GemmParams& p, int item) {
+  return p.m_fast ? item % p.num_m_blocks : item / p.num_n_groups;
+}
+
 template <int kNCta, bool kStaging, int kAcc = 1>
 struct GemmShape {
   static_assert(kAcc == 1 || (kAcc == 2 && kNCta == 2 && !kStaging), "512-column tiles need a CTA pair");
@@ -141,7 +150,7 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     // ================================ TMA producer ================================
     int stage = 0; uint32_t phase = 0;
     for (int item = worker; item < num_items; item += num_workers) {
-      const int n_grp = item % p.num_n_groups, m_blk = item / p.num_n_groups;
+      const int n_grp = item_n(p, item), m_blk = item_m(p, item);
       const int m0 = m_blk * S::UMMA_M + (int)rank * BM;
       const int t_begin = n_grp * p.tiles_per_group;
       const int t_end = min(t_begin + p.tiles_per_group, p.num_n_tiles);
@@ -199,7 +208,7 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const uint64_t db0 = ptx::make_smem_desc(ptx::smem_u32(smem_b), b_lbo, 1024);
       int stage = 0; uint32_t phase = 0; uint32_t acc_iter = 0;
       for (int item = worker; item < num_items; item += num_workers) {
-        const int n_grp = item % p.num_n_groups;
+        const int n_grp = item_n(p, item);
         const int t_begin = n_grp * p.tiles_per_group;
         const int t_end = min(t_begin + p.tiles_per_group, p.num_n_tiles);
         for (int nt = t_begin; nt < t_end; ++nt, ++acc_iter) {
@@ -243,7 +252,7 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const uint32_t stg_warp = ptx::smem_u32(staging) + (uint32_t)(warp - 4) * 8192u;   // this warp's 2 buffers
     uint32_t sbuf = 0;
     for (int item = worker; item < num_items; item += num_workers) {
-      const int n_grp = item % p.num_n_groups, m_blk = item / p.num_n_groups;
+      const int n_grp = item_n(p, item), m_blk = item_m(p, item);
       const int64_t row = (int64_t)m_blk * S::UMMA_M + (int64_t)rank * BM + row_in_tile;
       const bool row_ok = row < p.M;
       const int t_begin = n_grp * p.tiles_per_group;
