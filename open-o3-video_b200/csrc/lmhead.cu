@@ -1,6 +1,7 @@
 // Host side of K1 / K2 (C ABI in include/o3v.h) + the small elementwise kernels around the
 // tcgen05 GEMMs: partial-statistics merge and the in-place softmax backward (dlogits).
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <string>
 
@@ -15,6 +16,7 @@ namespace o3v {
 static int g_cta_fwd = 1;       // K1 (measured: the 4-stage 1-CTA pipeline is ahead for the K-major sweep)
 static int g_cta_bwd = 2;       // K2a / K2b
 static int g_bwd_wide = 1;      // K2a / K2b on pairs: 256x512 tiles (both TMEM accumulators per tile)
+static int g_bwd_sync = 1;      // K2a / K2b: wave-boundary rendezvous of the TMA producers
 static int g_dh_mfast = 0;      // K2a item order (0 = n fastest)
 static int g_dw_mfast = 0;      // K2b item order
 static int g_fwd_groups = 0;    // n-groups (vocab splits) per m-block in K1; 0 = auto
@@ -55,6 +57,24 @@ static int make_tmap_bf16(CUtensorMap* tm, const void* base, int64_t inner, int6
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? O3V_OK : O3V_ERR_DRIVER;
+}
+
+// ------------------------------------------------------------------------------------
+// wave-sync counters: static device memory (the library allocates nothing at run time).  A
+// launch takes the next slot round-robin and zeroes it on its stream, so GEMMs that overlap on
+// different streams do not share a counter.
+// ------------------------------------------------------------------------------------
+constexpr int kSyncSlots = 64;
+__device__ unsigned int g_wave_sync[kSyncSlots];
+
+static int acquire_wave_sync(unsigned int** out, cudaStream_t st) {
+  static std::atomic<unsigned int> next{0};
+  unsigned int* base = nullptr;
+  O3V_CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_wave_sync));
+  unsigned int* slot = base + (next.fetch_add(1) % kSyncSlots);
+  O3V_CUDA_TRY(cudaMemsetAsync(slot, 0, sizeof(unsigned int), st));
+  *out = slot;
+  return O3V_OK;
 }
 
 // ------------------------------------------------------------------------------------
@@ -191,6 +211,7 @@ extern "C" int o3v_set_tunable(const char* name, int value) {
   else if (n == "cta_pair_fwd") { if (value != 1 && value != 2) return O3V_ERR_INVALID_ARG; g_cta_fwd = value; }
   else if (n == "cta_pair_bwd") { if (value != 1 && value != 2) return O3V_ERR_INVALID_ARG; g_cta_bwd = value; }
   else if (n == "bwd_wide") g_bwd_wide = value ? 1 : 0;
+  else if (n == "bwd_sync") g_bwd_sync = value ? 1 : 0;
   else if (n == "dh_mfast") g_dh_mfast = value ? 1 : 0;
   else if (n == "dw_mfast") g_dw_mfast = value ? 1 : 0;
   else if (n == "fwd_groups") g_fwd_groups = value;
@@ -286,6 +307,7 @@ extern "C" int o3v_lmhead_bwd_dhidden(const void* dlogits, int64_t ld_dlogits, c
   if ((rc = make_tmap_bf16(&tmA, dlogits, V, T, ld_dlogits, 128))) return rc;   // A = P, K-major (K = V)
   if ((rc = make_tmap_bf16(&tmB, weight, H, V, H, 64))) return rc;              // B = W, MN-major (N = H contiguous)
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_bwd_sync && (rc = acquire_wave_sync(&p.wave_sync, st))) return rc;
   if (wide) return launch_gemm<false, true, 2, EPI_STORE, 2>(tmA, tmB, tmA, p, st);
   return (ncta == 1) ? launch_gemm<false, true, 1, EPI_STORE>(tmA, tmB, tmA, p, st)
                      : launch_gemm<false, true, 2, EPI_STORE>(tmA, tmB, tmA, p, st);
@@ -310,6 +332,7 @@ extern "C" int o3v_lmhead_bwd_dweight(const void* dlogits, int64_t ld_dlogits, c
   if ((rc = make_tmap_bf16(&tmA, dlogits, V, T, ld_dlogits, 64))) return rc;    // A = P^T, MN-major (M = V contiguous)
   if ((rc = make_tmap_bf16(&tmB, hidden, H, T, H, 64))) return rc;              // B = hidden, MN-major
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_bwd_sync && (rc = acquire_wave_sync(&p.wave_sync, st))) return rc;
   if (wide) return launch_gemm<true, true, 2, EPI_ACCUM, 2>(tmA, tmB, tmA, p, st);
   return (ncta == 1) ? launch_gemm<true, true, 1, EPI_ACCUM>(tmA, tmB, tmA, p, st)
                      : launch_gemm<true, true, 2, EPI_ACCUM>(tmA, tmB, tmA, p, st);

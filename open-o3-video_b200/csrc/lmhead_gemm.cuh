@@ -37,6 +37,9 @@ struct GemmParams {
   int32_t num_n_groups;     // ceil(num_n_tiles / tiles_per_group)
   int32_t m_fast;           // item order: 0 = n-groups fastest (CTAs running together share A panels),
                             //             1 = m-blocks fastest (they share B panels)
+  unsigned int* wave_sync;  // optional global counter (zeroed before launch): the TMA producers of all CTAs
+                            // rendezvous at every wave boundary of the static schedule, so that CTAs which
+                            // stream the same operand panels stay inside each other's L2 window
   // EPI_STATS
   const int64_t* targets;   // [M] global vocab ids
   int64_t v_offset;         // first vocab id of this slice
@@ -149,7 +152,22 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 0) {
     // ================================ TMA producer ================================
     int stage = 0; uint32_t phase = 0;
+    unsigned int sync_target = 0;
     for (int item = worker; item < num_items; item += num_workers) {
+      if (p.wave_sync != nullptr) {
+        if (item != worker) {          // every CTA active in the previous wave has issued all of its loads
+          if (ptx::elect_one()) {
+            const long long t0 = clock64();
+            while (ptx::ld_acquire_gpu(p.wave_sync) < sync_target) {
+              __nanosleep(200);
+              if (clock64() - t0 > 10000000000LL) ptx::mbar_timeout_trap(0xffffffffu, sync_target);
+            }
+          }
+          __syncwarp();
+        }
+        const int wave_first = item - worker;                                  // first item of this wave
+        sync_target += (unsigned int)(min(num_workers, num_items - wave_first) * kNCta);
+      }
       const int n_grp = item_n(p, item), m_blk = item_m(p, item);
       const int m0 = m_blk * S::UMMA_M + (int)rank * BM;
       const int t_begin = n_grp * p.tiles_per_group;
@@ -192,6 +210,10 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
+      }
+      if (p.wave_sync != nullptr) {
+        if (ptx::elect_one()) ptx::red_release_gpu_add(p.wave_sync, 1u);
+        __syncwarp();
       }
     }
   } else if (warp == 1) {

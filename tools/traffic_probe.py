@@ -13,17 +13,16 @@ H, V = 3584, 152064
 dev = "cuda"
 g = torch.Generator(device=dev).manual_seed(0)
 weight = (torch.randn(V, H, device=dev, generator=g) * 0.02).bfloat16()
-for T in (2560, 32768):                     # 10 m-blocks of 256 rows = one wave of 70 pair tiles; bench chunk
+for T in (32768,):                     # 10 m-blocks of 256 rows = one wave of 70 pair tiles; bench chunk
     hidden = torch.randn(T, H, device=dev, generator=g).bfloat16()
     z = (torch.randn(T, V, device=dev, generator=g, dtype=torch.bfloat16) * 0.01)
     dW = torch.zeros(V, H, device=dev)
     for wide in (1, 0):
         _lib.set_tunable("bwd_wide", wide)
-        for mfast in (0, 1):
-            _lib.set_tunable("dh_mfast", mfast)
-            _lib.set_tunable("dw_mfast", mfast)
+        for sync in (1, 0):
+            _lib.set_tunable("bwd_sync", sync)
             logprob.bwd_dhidden(z, weight)
             logprob.bwd_dweight(z, hidden, dW, True)
             torch.cuda.synchronize()
-            print("T=%d wide=%d mfast=%d: dH, dW launched" % (T, wide, mfast), flush=True)
+            print("T=%d wide=%d sync=%d: dH, dW launched" % (T, wide, sync), flush=True)
     del hidden, z, dW
