@@ -177,6 +177,9 @@ def run_ours(args):
     ids[torch.arange(N, device=dev), lens - 1] = eos_id      # planted EOS drives the mask
     _, mask = gspo.eos_mask(ids, eos_id)
     weight, v_off = sharded.shard_weight(w_full, rank, world)
+    if not args.chunk_tokens:
+        per_seq = max(1, min(N, logprob.auto_chunk_tokens(weight.shape[0]) // Tc))
+        args.chunk_tokens = -(-N // (-(-N // per_seq))) * Tc      # evened out over whole sequences
     del w_full
     # reference-model log-probs = policy log-probs + N(0, 0.1^2) (forward-only pass, untimed)
     ref = logprob.fused_logprob(hidden.view(T, H), weight, ids.view(T), v_offset=v_off, group=group).view(N, Tc)
@@ -324,7 +327,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
-    ap.add_argument("--chunk-tokens", type=int, default=32768)
+    ap.add_argument("--chunk-tokens", type=int, default=0, help="0 = size the chunk from a 10 GB logits buffer")
     ap.add_argument("--cta-pair", type=int, default=0)
     ap.add_argument("--fwd-groups", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

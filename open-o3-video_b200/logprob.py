@@ -15,8 +15,15 @@ import torch
 from . import _lib
 from .gspo import _need_cuda, _p, _stream, gspo_raw
 
-# token chunk of the fused fwd+bwd: bounds the bf16 dlogits buffer (chunk x V x 2 bytes)
+# token chunk of the fused fwd+bwd: bounds the bf16 dlogits buffer (chunk x V_local x 2 bytes)
 DEFAULT_CHUNK_TOKENS = 32768
+# chunk_tokens=0 sizes the chunk from this buffer budget instead (10 GB = 32768 tokens of a 152k
+# vocabulary on one GPU; a vocab-sharded rank with V/8 columns takes the whole batch in one chunk)
+CHUNK_BUFFER_BYTES = 10 << 30
+
+
+def auto_chunk_tokens(v_local: int) -> int:
+    return max(128, int(CHUNK_BUFFER_BYTES // (2 * v_local)))
 # autograd path: keep bf16 logits for backward when they fit in this many bytes, else recompute
 SAVE_LOGITS_BYTES = 24 << 30
 
@@ -195,6 +202,8 @@ def fused_logprob_gspo(hidden: torch.Tensor, weight: torch.Tensor, completion_id
     ref, old, rpf = f32(ref_per_token_logps), f32(old_per_token_logps), f32(rewards_per_func)
     mask = completion_mask.to(torch.int32).contiguous()
 
+    if not chunk_tokens:
+        chunk_tokens = auto_chunk_tokens(V)
     seqs = max(1, min(N, chunk_tokens // Tc))
     n_chunks = -(-N // seqs)
     seqs = -(-N // n_chunks)                                  # even out the chunks
