@@ -292,12 +292,14 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         ptx::mbar_wait(&tfull[a], aphase);
         ptx::tc_fence_after();
         const int64_t n0 = (int64_t)nt * S::TILE_N;
-#pragma unroll 1
-        for (int c = 0; c < S::TILE_N / 32; ++c) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32b_x32(tmem_row + a * S::TILE_N + c * 32, v);
-          ptx::tmem_ld_wait();
-          const int64_t col0 = n0 + c * 32;
+        const int64_t n_left = p.N - n0;
+        const int n_valid = n_left < (int64_t)S::TILE_N ? (int)n_left : S::TILE_N;          // columns of this tile inside N
+        const int tgt_in_tile = (tgt_col >= n0 && tgt_col < n0 + S::TILE_N) ? (int)(tgt_col - n0) : -1;
+        const uint32_t tmem_tile = tmem_row + a * S::TILE_N;
+
+        // one 32-column chunk of this thread's accumulator row
+        auto process = [&](uint32_t (&v)[32], const int c) {
+          const int cbase = c * 32;                       // first column of the chunk within the tile
           if constexpr (kEpi == EPI_STATS) {
             if (p.logits != nullptr) {
               // bf16 copy of the tile for the chunked backward: [32 rows x 64 cols] per warp staged in
@@ -325,19 +327,19 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 __syncwarp();
                 if (lane == 0) {
                   const int32_t r0 = (int32_t)((int64_t)m_blk * S::UMMA_M + (int64_t)rank * BM + q * 32);
-                  ptx::tma_store_2d(&tmC, stg_warp + sbuf * 4096u, (int32_t)(col0 - 32), r0);
+                  ptx::tma_store_2d(&tmC, stg_warp + sbuf * 4096u, (int32_t)(n0 + cbase - 32), r0);
                   ptx::bulk_commit();
                 }
                 sbuf ^= 1u;
               }
             }
-            if (col0 + 32 > p.N) {                 // ragged last tile: TMA zero-filled columns are not vocabulary
+            if (cbase + 32 > n_valid) {            // ragged last tile: TMA zero-filled columns are not vocabulary
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (col0 + j >= p.N) v[j] = __float_as_uint(-INFINITY);
+                if (cbase + j >= n_valid) v[j] = __float_as_uint(-INFINITY);
             }
-            if (tgt_col >= col0 && tgt_col < col0 + 32) {   // rare: once per row over the whole sweep
-              const int jj = (int)(tgt_col - col0);
+            if ((tgt_in_tile >> 5) == c) {          // rare: once per row over the whole sweep (-1 >> 5 == -1)
+              const int jj = tgt_in_tile & 31;
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (j == jj) tgt_logit = __uint_as_float(v[j]);
@@ -348,28 +350,33 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const float new_max = fmaxf(run_max, cmax);
             if (new_max != -INFINITY) {            // (an all-masked chunk before any valid column cannot occur)
               const float neg = -new_max * kLog2e;
-              float acc = 0.f;
+              float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;      // 4 chains: the adds do not serialise
 #pragma unroll
-              for (int j = 0; j < 32; ++j) acc += exp2f(fmaf(__uint_as_float(v[j]), kLog2e, neg));
+              for (int j = 0; j < 32; j += 4) {
+                acc0 += ptx::ex2_approx(fmaf(__uint_as_float(v[j + 0]), kLog2e, neg));
+                acc1 += ptx::ex2_approx(fmaf(__uint_as_float(v[j + 1]), kLog2e, neg));
+                acc2 += ptx::ex2_approx(fmaf(__uint_as_float(v[j + 2]), kLog2e, neg));
+                acc3 += ptx::ex2_approx(fmaf(__uint_as_float(v[j + 3]), kLog2e, neg));
+              }
               // rescale from the EXACT difference: an unchanged max must give a factor of exactly 1
               // (via fmaf(run_max, log2e, neg) the rounding of max*log2e would compound over the
               // ~4.7k chunks of a vocabulary sweep)
-              run_sum = run_sum * exp2f((run_max - new_max) * kLog2e) + acc;
+              run_sum = run_sum * ptx::ex2_approx((run_max - new_max) * kLog2e) + ((acc0 + acc1) + (acc2 + acc3));
               run_max = new_max;
             }
           } else if constexpr (kEpi == EPI_STORE) {
             if (row_ok) {
               if (p.out_fp32) {
-                float* dst = reinterpret_cast<float*>(p.out) + row * p.ld_out + col0;
+                float* dst = reinterpret_cast<float*>(p.out) + row * p.ld_out + n0 + cbase;
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                  if (col0 + j * 4 < p.N)
+                  if (cbase + j * 4 < n_valid)
                     *reinterpret_cast<uint4*>(dst + j * 4) = make_uint4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
               } else {
-                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ld_out + col0;
+                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ld_out + n0 + cbase;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  if (col0 + j * 8 < p.N) {
+                  if (cbase + j * 8 < n_valid) {
                     uint4 pk;
                     __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]));
                     __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
@@ -382,23 +389,36 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 }
               }
             }
-          } else {  // EPI_ACCUM: fp32 read-modify-write
+          } else {  // EPI_ACCUM: fp32 store, or fire-and-forget 16-byte reductions (one writer per element
+                    // per launch, so the result is still deterministic; no read latency in the epilogue)
             if (row_ok) {
-              float* dst = reinterpret_cast<float*>(p.out) + row * p.ld_out + col0;
+              float* dst = reinterpret_cast<float*>(p.out) + row * p.ld_out + n0 + cbase;
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                if (col0 + j * 4 < p.N) {
-                  float4 o = make_float4(__uint_as_float(v[j * 4]), __uint_as_float(v[j * 4 + 1]),
-                                         __uint_as_float(v[j * 4 + 2]), __uint_as_float(v[j * 4 + 3]));
-                  if (p.accumulate) {
-                    const float4 old = *reinterpret_cast<const float4*>(dst + j * 4);
-                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                  }
-                  *reinterpret_cast<float4*>(dst + j * 4) = o;
+                if (cbase + j * 4 < n_valid) {
+                  if (p.accumulate)
+                    ptx::red_add_v4_f32(dst + j * 4, __uint_as_float(v[j * 4]), __uint_as_float(v[j * 4 + 1]),
+                                        __uint_as_float(v[j * 4 + 2]), __uint_as_float(v[j * 4 + 3]));
+                  else
+                    *reinterpret_cast<uint4*>(dst + j * 4) = make_uint4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
                 }
               }
             }
           }
+        };
+
+        // software pipeline: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
+        constexpr int kChunks = S::TILE_N / 32;
+        uint32_t va[32], vb[32];
+        ptx::tmem_ld_32x32b_x32(tmem_tile, va);
+#pragma unroll 1
+        for (int c = 0; c < kChunks; c += 2) {
+          ptx::tmem_ld_wait();
+          ptx::tmem_ld_32x32b_x32(tmem_tile + (c + 1) * 32, vb);
+          process(va, c);
+          ptx::tmem_ld_wait();
+          if (c + 2 < kChunks) ptx::tmem_ld_32x32b_x32(tmem_tile + (c + 2) * 32, va);
+          process(vb, c + 1);
         }
         // all tcgen05.ld of this warp have completed (wait::ld above): hand the accumulator back
         ptx::tc_fence_before();
