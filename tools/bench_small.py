@@ -1,0 +1,66 @@
+"""Roofline of the HBM-bound kernels (K3 GSPO, K3a EOS mask, K4 rewards, dlogits, merge):
+achieved GB/s of algorithmic bytes against the measured copy bandwidth (MEASURED_PEAKS.json)."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from open_o3_video_b200 import gspo, logprob, rewards  # noqa: E402
+from oracle import synth  # noqa: E402
+
+dev = "cuda"
+peak = 6532.2
+p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+if os.path.isfile(p):
+    peak = json.load(open(p))["hbm_gbs"]
+flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn, iters=10):
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()                               # inputs here are smaller than the 126 MB L2: flush between iterations
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return min(ts), sum(ts) / len(ts)
+
+
+def line(name, nbytes, fn):
+    best, mean = timeit(fn)
+    print(json.dumps(dict(kernel=name, algorithmic_bytes=nbytes, best_us=best * 1e3, mean_us=mean * 1e3,
+                          achieved_gbs=nbytes / best / 1e6, peak_gbs=peak, frac=nbytes / best / 1e6 / peak)), flush=True)
+
+
+g = torch.Generator(device=dev).manual_seed(0)
+for name, N, Tc, G in (("c2", 64, 2048, 8), ("c3", 128, 4096, 8), ("c5", 16, 16384, 16)):
+    lp = -torch.rand(N, Tc, device=dev, generator=g) * 5
+    ref = lp + 0.1
+    old = lp + 0.01
+    ids = torch.randint(0, 1000, (N, Tc), device=dev, generator=g)
+    rpf = torch.rand(N, 3, device=dev, generator=g)
+    _, mask = gspo.eos_mask(ids, 7)
+    line("K3a eos_mask %s" % name, N * Tc * 12, lambda: gspo.eos_mask(ids, 7))
+    # logp, ref, mask read twice (two passes) + old + grad written: count each tensor once = 20 B/token
+    line("K3 gspo fwd+bwd %s" % name, N * Tc * 20, lambda: gspo.gspo_raw(lp, ref, mask, rpf, G, 0.04, 0.2, 0.2, True, old, want_kl=False))
+# K4 at BASELINE config 4: 65536 rollouts x 16 predictions
+ro = synth.rollouts(8192, 8, seed=4)
+arrays, dims = rewards.pack_rollouts(ro, 8)
+dev_arrays = rewards.to_device(arrays, dev)
+out = torch.empty(dims["R"], 5, dtype=torch.float64, device=dev)
+nbytes = rewards.soa_bytes(arrays) + out.numel() * 8
+line("K4 grounded rewards c4 (65536 x 16, %.0f B/rollout)" % (nbytes / dims["R"]), nbytes,
+     lambda: rewards.grounded_rewards_device(dev_arrays, dims, out))
+# dlogits / merge at the bench chunk
+T, V = 8192, 152064
+z = torch.randn(T, V, device=dev, generator=g, dtype=torch.bfloat16)
+lse = torch.full((T,), 12.0, device=dev); gl = torch.full((T,), 1e-3, device=dev)
+tg = torch.randint(0, V, (T,), device=dev, generator=g)
+line("dlogits (T=8192, V=152064)", T * V * 4, lambda: logprob.dlogits_(z, lse, gl, tg))
+parts = torch.randn(8, 3, 131072, device=dev, generator=g)
+line("merge_stats (P=8, T=131072)", 8 * 3 * 131072 * 4 + 2 * 131072 * 4, lambda: logprob.merge_stats(parts))
