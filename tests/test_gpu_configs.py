@@ -1,0 +1,146 @@
+"""GPU tests at the BASELINE.json configuration shapes through size-independent properties,
+schedule / tile-mode variants of the backward GEMMs, and error behaviour at the boundary."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gspo as ogspo
+from oracle import logps as ologps
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def reset_tunables():
+    from open_o3_video_b200 import _lib
+    yield _lib
+    for k, v in (("cta_pair_fwd", 1), ("cta_pair_bwd", 2), ("bwd_wide", 1), ("bwd_sync", 1), ("fwd_groups", 0),
+                 ("dh_mfast", 0), ("dw_mfast", 0), ("max_ctas", 0)):
+        _lib.set_tunable(k, v)
+
+
+@pytest.mark.parametrize("cta,wide,sync,mfast", [(2, 1, 1, 0), (2, 1, 0, 0), (2, 0, 1, 0), (2, 0, 0, 1), (1, 0, 1, 0),
+                                                 (1, 0, 0, 1), (2, 1, 1, 1)])
+def test_backward_gemm_variants_agree(reset_tunables, cta, wide, sync, mfast):
+    """Every schedule / tile variant of K2a / K2b gives the same result on a multi-wave problem
+    (more tiles than CTAs, ragged M / N / K)."""
+    lib = reset_tunables
+    from open_o3_video_b200 import logprob
+    T, H, V = 2900, 1792, 9496                      # dH: 12 x 7 = 84 wide tiles > 74 pairs; dW: 38 x 7 = 266
+    g = torch.Generator().manual_seed(5)
+    P = (torch.randn(T, V, generator=g) * 0.05).bfloat16().cuda()
+    W = (torch.randn(V, H, generator=g) * 0.02).bfloat16().cuda()
+    Hd = torch.randn(T, H, generator=g).bfloat16().cuda()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dH_ref = P.float() @ W.float()
+    dW_ref = P.float().T @ Hd.float()
+    lib.set_tunable("cta_pair_bwd", cta); lib.set_tunable("bwd_wide", wide); lib.set_tunable("bwd_sync", sync)
+    lib.set_tunable("dh_mfast", mfast); lib.set_tunable("dw_mfast", mfast)
+    dH = logprob.bwd_dhidden(P, W, fp32=True)
+    dW = torch.zeros(V, H, device="cuda")
+    logprob.bwd_dweight(P, Hd, dW, accumulate=False)
+    logprob.bwd_dweight(P, Hd, dW, accumulate=True)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(dH.cpu().numpy(), dH_ref.cpu().numpy(), rtol=1e-4, atol=1e-4 * dH_ref.abs().max().item())
+    np.testing.assert_allclose(dW.cpu().numpy(), 2 * dW_ref.cpu().numpy(), rtol=1e-4, atol=2e-4 * dW_ref.abs().max().item())
+
+
+def test_small_grid_and_capped_grid(reset_tunables):
+    """Fewer work items than SMs, and a persistent grid capped below the SM count."""
+    lib = reset_tunables
+    from open_o3_video_b200 import logprob
+    hidden, weight, targets = synth.head_inputs(700, 256, 3000, seed=8)
+    ref, _ = ologps.token_logps(hidden, weight, targets)
+    h, w, t = hidden.cuda().bfloat16(), weight.cuda().bfloat16(), targets.cuda()
+    for cap in (0, 6, 1):
+        lib.set_tunable("max_ctas", cap)
+        lp = logprob.fused_logprob(h, w, t)
+        assert (lp.cpu() - ref).abs().max() < 2e-4
+        g = torch.full((700,), 1e-3)
+        z = torch.empty(700, 3000, dtype=torch.bfloat16, device="cuda")
+        st = logprob.lmhead_stats(h, w, t, 0, z)
+        _, lse = logprob.merge_stats(st.unsqueeze(0))
+        logprob.dlogits_(z, lse, g.cuda(), t)
+        dH = logprob.bwd_dhidden(z, w, fp32=True)
+        assert torch.isfinite(dH).all()
+
+
+def test_c3_head_ragged_vocab_properties():
+    """Config 3 head (H=4096, V=151936 = 593.5 tiles): probabilities of ALL targets of a row sum to 1
+    is too expensive, so check (a) lse against torch on a row subset, (b) sharding invariance over
+    8 tile-granular slices, (c) exp(logp) <= 1 and finite everywhere."""
+    from open_o3_video_b200 import logprob, sharded
+    H, V, T = 4096, 151936, 1024
+    g = torch.Generator(device="cuda").manual_seed(3)
+    h = torch.randn(T, H, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(V, H, device="cuda", generator=g) * 0.02).bfloat16()
+    t = torch.randint(0, V, (T,), device="cuda", generator=g)
+    t[:3] = torch.tensor([V - 1, V - 128, 151808], device="cuda")              # inside the ragged last tile
+    lp, lse = logprob.fused_logprob(h, w, t, return_lse=True)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    z = h[:64].float() @ w.float().T
+    ref = z.log_softmax(-1).gather(1, t[:64, None])[:, 0]
+    assert ((lp[:64] - ref).abs() / ref.abs()).max().item() < 1e-3
+    assert ((lse[:64] - torch.logsumexp(z, -1)).abs()).max().item() < 1e-4
+    assert torch.isfinite(lp).all() and (lp <= 1e-6).all()
+    parts = torch.stack([logprob.lmhead_stats(h, w[a:b].contiguous(), t, a) for a, b in sharded.vocab_slices(V, 8)])
+    lp8, _ = logprob.merge_stats(parts)
+    assert (lp8 - lp).abs().max().item() < 5e-6
+
+
+def test_c5_long_horizon_chunked_step_is_chunk_invariant():
+    """Config 5 geometry scaled down in H, V only (G = 16 sequences of 16384 tokens): the loss and
+    gradients must not depend on how the step is chunked."""
+    from open_o3_video_b200 import logprob
+    N, Tc, G, H, V = 16, 16384, 16, 128, 1024
+    g = torch.Generator(device="cuda").manual_seed(9)
+    h = torch.randn(N, Tc, H, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(V, H, device="cuda", generator=g) * 0.05).bfloat16()
+    ids = torch.randint(0, V - 1, (N, Tc), device="cuda", generator=g)
+    lens = torch.randint(Tc // 4, Tc + 1, (N,), device="cuda", generator=g)
+    ids[torch.arange(N, device="cuda"), lens - 1] = V - 1
+    from open_o3_video_b200 import gspo
+    eos_idx, mask = gspo.eos_mask(ids, V - 1)
+    assert torch.equal(eos_idx, lens - 1) and torch.equal(mask.sum(1), lens.to(torch.int32).to(mask.sum(1).dtype))
+    ref = torch.full((N, Tc), -7.0, device="cuda")
+    rpf = torch.rand(N, 2, device="cuda", generator=g)
+    a = logprob.fused_logprob_gspo(h, w, ids, ref, mask, rpf, G, 0.04, chunk_tokens=N * Tc)
+    b = logprob.fused_logprob_gspo(h, w, ids, ref, mask, rpf, G, 0.04, chunk_tokens=2 * Tc)
+    assert torch.equal(a["per_token_logps"], b["per_token_logps"])
+    assert abs(a["loss"].item() - b["loss"].item()) <= 1e-6 * abs(a["loss"].item()) + 1e-9
+    assert torch.equal(a["d_hidden"], b["d_hidden"])                      # per-token rows are independent of chunking
+    rel = (a["d_weight"] - b["d_weight"]).norm() / a["d_weight"].norm()   # fp32 accumulation order differs
+    assert rel.item() < 1e-5
+    assert (a["d_hidden"][mask == 0] == 0).all()
+
+
+def test_errors_are_python_exceptions_not_crashes():
+    from open_o3_video_b200 import _lib, gspo, logprob
+    h = torch.zeros(128, 100, dtype=torch.bfloat16, device="cuda")          # H % 64 != 0
+    w = torch.zeros(256, 100, dtype=torch.bfloat16, device="cuda")
+    t = torch.zeros(128, dtype=torch.int64, device="cuda")
+    with pytest.raises(_lib.O3VError, match="unsupported shape"):
+        logprob.fused_logprob(h, w, t)
+    with pytest.raises(TypeError):
+        logprob.fused_logprob(h.float(), w.float(), t)
+    lp = torch.zeros(6, 8, device="cuda")
+    with pytest.raises(_lib.O3VError, match="invalid argument"):           # N % G != 0
+        gspo.gspo_loss(lp, lp, torch.ones(6, 8, dtype=torch.int32, device="cuda"), torch.zeros(6, 1, device="cuda"), 4, 0.04)
+    # the device is still healthy afterwards
+    assert gspo.eos_mask(torch.zeros(2, 4, dtype=torch.int64, device="cuda"), 1)[0].tolist() == [4, 4]
+
+
+def test_determinism_run_to_run():
+    from open_o3_video_b200 import logprob
+    N, Tc, G, H, V = 8, 256, 4, 256, 5000
+    hidden, weight, _ = synth.head_inputs(N * Tc, H, V, seed=2)
+    d = synth.gspo_inputs(N, Tc, G, vocab=V + 1000, eos_id=V - 1)
+    ids = (d["ids"] % V).cuda()
+    _, mask = ogspo.eos_mask(ids.cpu(), V - 1)
+    args = (hidden.cuda().bfloat16().view(N, Tc, H), weight.cuda().bfloat16(), ids, d["ref"].cuda() - 6, mask.cuda(),
+            d["rewards_per_func"].cuda(), G, 0.04)
+    a = logprob.fused_logprob_gspo(*args, chunk_tokens=512)
+    b = logprob.fused_logprob_gspo(*args, chunk_tokens=512)
+    for k in ("loss", "per_token_logps", "d_hidden", "d_weight", "advantages", "mean_kl"):
+        assert torch.equal(a[k], b[k]), k
