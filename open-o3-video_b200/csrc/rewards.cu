@@ -6,6 +6,8 @@
 // by the G rollouts of a prompt and is served from L1/L2 after the first touch.
 // Arithmetic follows the reference's float64 operation order; explicit __d*_rn intrinsics
 // keep nvcc from contracting mul+add into FMA so that results are bit-identical to numpy's.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace o3v {
@@ -44,14 +46,63 @@ __device__ __forceinline__ double ordered_group_sum(double v, int count, int bas
   return acc;
 }
 
-__global__ void __launch_bounds__(kRewardThreads)
+// Ground truth of the prompts a CTA touches is staged in shared memory (coalesced copy, one
+// barrier): the gating / IoU loops then chase smem (30 cycles) instead of L2 (300 cycles).
+// Per prompt: kf_time[K] f64 | gt_box[K*O*Gb*4] f64 | n_obj[K] i32 | n_gtbox[K*O] i32.
+// (kf_time is padded to an even count and the record to 16 bytes so that the 16-byte box loads stay aligned)
+__host__ __device__ inline int gt_kpad(const o3v_rewards_soa& s) { return (s.K + 1) & ~1; }
+__host__ __device__ inline int gt_doubles(const o3v_rewards_soa& s) { return gt_kpad(s) + s.K * s.O * s.Gb * 4; }
+__host__ __device__ inline int gt_ints(const o3v_rewards_soa& s) { return s.K + s.K * s.O; }
+__host__ __device__ inline size_t gt_bytes_per_prompt(const o3v_rewards_soa& s) {
+  return (size_t)gt_doubles(s) * 8 + (((size_t)gt_ints(s) * 4 + 15) & ~(size_t)15);
+}
+
+template <bool kStageGT>
+__global__ void __launch_bounds__(kRewardThreads, 3)
 rewards_kernel(const o3v_rewards_soa s, double* __restrict__ out) {
+  extern __shared__ double smem_gt[];
   const int lane = threadIdx.x & (kLanes - 1);
-  const int64_t r = (int64_t)blockIdx.x * (kRewardThreads / kLanes) + (threadIdx.x / kLanes);
+  const int64_t r0 = (int64_t)blockIdx.x * (kRewardThreads / kLanes);
+  const int64_t r = r0 + (threadIdx.x / kLanes);
   const int base = (threadIdx.x & 31) & ~(kLanes - 1);
   const unsigned gmask = 0xffffu << base;
+  const int64_t q_first = r0 / s.G;
+  if constexpr (kStageGT) {
+    const int64_t r_last = min(r0 + kRewardThreads / kLanes, s.R) - 1;
+    const int nq = (int)(r_last / s.G - q_first) + 1;
+    const int nd = gt_doubles(s), ni = gt_ints(s);
+    const size_t stride = gt_bytes_per_prompt(s);
+    for (int i = threadIdx.x; i < nq * nd; i += kRewardThreads) {
+      const int pq = i / nd, j = i - pq * nd;
+      const int64_t qq = q_first + pq;
+      double* dst = reinterpret_cast<double*>(reinterpret_cast<char*>(smem_gt) + pq * stride);
+      const int kp = gt_kpad(s);
+      dst[j] = (j < kp) ? (j < s.K ? s.kf_time[qq * s.K + j] : 0.0) : s.gt_box[qq * (int64_t)(nd - kp) + (j - kp)];
+    }
+    for (int i = threadIdx.x; i < nq * ni; i += kRewardThreads) {
+      const int pq = i / ni, j = i - pq * ni;
+      const int64_t qq = q_first + pq;
+      int32_t* dst = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(smem_gt) + pq * stride + (size_t)nd * 8);
+      dst[j] = (j < s.K) ? s.n_obj[qq * s.K + j] : s.n_gtbox[qq * (int64_t)(ni - s.K) + (j - s.K)];
+    }
+    __syncthreads();
+  }
   if (r >= s.R) return;   // whole 16-lane group leaves together
   const int64_t q = r / s.G;
+  // per-prompt GT arrays: shared-memory copies when staged, else the global arrays
+  const double* kft; const double* gtb; const int32_t* nobj_p; const int32_t* ngt_p;
+  if constexpr (kStageGT) {
+    const char* rec = reinterpret_cast<const char*>(smem_gt) + (size_t)(q - q_first) * gt_bytes_per_prompt(s);
+    kft = reinterpret_cast<const double*>(rec);
+    gtb = kft + gt_kpad(s);
+    nobj_p = reinterpret_cast<const int32_t*>(rec + (size_t)gt_doubles(s) * 8);
+    ngt_p = nobj_p + s.K;
+  } else {
+    kft = s.kf_time + q * s.K;
+    gtb = s.gt_box + q * (int64_t)s.K * s.O * s.Gb * 4;
+    nobj_p = s.n_obj + q * s.K;
+    ngt_p = s.n_gtbox + q * (int64_t)s.K * s.O;
+  }
 
   const int flags = s.flags[r];
   const int task = s.task[q];
@@ -108,7 +159,6 @@ rewards_kernel(const o3v_rewards_soa s, double* __restrict__ out) {
   }
 
   const int nk = s.n_kf[q];
-  const double* kft = s.kf_time + q * s.K;
 
   // ---- thk_temporal_point_reward: adaptive temporal proximity (:439, :452-467)
   if (has_think && !(task == O3V_TASK_VISUAL_QA || temporal || general) && n_times > 0) {
@@ -176,22 +226,29 @@ rewards_kernel(const o3v_rewards_soa s, double* __restrict__ out) {
               const int nb = s.claim_nbox[r * s.C + c];
               const unsigned valid = s.claim_valid[r * s.C + c];
               const double* cb = s.claim_box + ((r * s.C + c) * (int64_t)s.Bc) * 4;
-              const int nobj = s.n_obj[q * s.K + kf];
+              double cb0[4] = {0, 0, 0, 0}, cb1[4] = {0, 0, 0, 0};          // the common case: <= 2 boxes per claim
+              if (nb > 0) load4(cb, cb0);
+              if (nb > 1) load4(cb + 4, cb1);
+              const int nobj = nobj_p[kf];
               double max_iou = 0.0;
               for (int o = 0; o < nobj; ++o) {                              // :575
-                const int ng = s.n_gtbox[(q * s.K + kf) * s.O + o];
+                const int ng = ngt_p[kf * s.O + o];
                 if (ng <= 0) continue;                                      // :596 empty list
                 double acc = 0.0;
                 for (int gi = 0; gi < ng; ++gi) {                           // :590
                   double nb4[4], g4[4];
-                  load4(s.gt_box + ((((q * s.K + kf) * s.O + o) * (int64_t)s.Gb) + gi) * 4, nb4);
+                  load4(gtb + (((kf * s.O + o) * s.Gb) + gi) * 4, nb4);
                   g4[0] = dmul(nb4[0], W); g4[1] = dmul(nb4[1], H);         // :337-346
                   g4[2] = dmul(nb4[2], W); g4[3] = dmul(nb4[3], H);
                   double best = 0.0;
                   bool first = true;
                   for (int b = 0; b < nb; ++b) {                            // :592-593 max(list)
                     double v = 0.0;
-                    if ((valid >> b) & 1u) { double pb[4]; load4(cb + b * 4, pb); v = box_iou(g4, pb); }
+                    if ((valid >> b) & 1u) {
+                      if (b == 0) v = box_iou(g4, cb0);
+                      else if (b == 1) v = box_iou(g4, cb1);
+                      else { double pb[4]; load4(cb + b * 4, pb); v = box_iou(g4, pb); }
+                    }
                     best = first ? v : fmax(best, v);
                     first = false;
                   }
@@ -237,7 +294,14 @@ extern "C" int o3v_grounded_rewards(const o3v_rewards_soa* soa, double* out, voi
   if (s.R == 0) return O3V_OK;
   const int per_cta = o3v::kRewardThreads / o3v::kLanes;
   const unsigned grid = (unsigned)((s.R + per_cta - 1) / per_cta);
-  o3v::rewards_kernel<<<grid, o3v::kRewardThreads, 0, (cudaStream_t)stream>>>(s, out);
+  // prompts a CTA of 16 consecutive rollouts can touch
+  const int64_t span = std::min<int64_t>(per_cta, (per_cta + s.G - 1) / s.G + 1);
+  const size_t smem = (size_t)span * o3v::gt_bytes_per_prompt(s);
+  if (smem <= 40 * 1024) {
+    o3v::rewards_kernel<true><<<grid, o3v::kRewardThreads, smem, (cudaStream_t)stream>>>(s, out);
+  } else {   // very large K x O x Gb: read the ground truth through L2 instead
+    o3v::rewards_kernel<false><<<grid, o3v::kRewardThreads, 0, (cudaStream_t)stream>>>(s, out);
+  }
   O3V_LAUNCH_CHECK();
   return O3V_OK;
 }
