@@ -13,8 +13,10 @@ all-reduced once per step -> strong scaling, T fixed.
 
 `value`   : device-resident inputs, CUDA events around the K timed steps, max over ranks.
 `e2e`     : same metric through the public API with HOST (pinned) inputs: H2D of hidden
-            states / ids / ref log-probs / mask / rewards and D2H of the loss inside the
+            states / ids / ref log-probs / mask / rewards (each rank copies its 1/N of the
+            sequences and the ranks all-gather over NVLink) and D2H of the loss inside the
             timed region (lm_head.weight is model state and stays on the device).
+            `h2d_bytes_per_step` is per rank.
 `roofline`: dominant kernel (the K1 tcgen05 GEMM with fused softmax-stats epilogue), timed
             live with CUDA events around its launches inside the timed region.
 `cpu_baseline`: the oracle port of the reference's torch path (fp32) on the host cores, on
@@ -231,19 +233,31 @@ def run_ours(args):
     # Every step's inputs start in pinned host memory and its loss ends there.  The copy of
     # step i+1's inputs runs on a side stream while step i computes (double-buffered device
     # staging), as a training loop's prefetcher would; all copies are inside the timed region.
-    host = [t.cpu().pin_memory() for t in (hidden, ids, ref, mask, rpf)]
+    # Vocab-sharded ranks all need every token row: each rank copies only ITS 1/world slice of the
+    # sequences over PCIe and the slices are all-gathered over NVLink (the real data-parallel layout).
+    full = (hidden, ids, ref, mask, rpf)
+    seq_lo, seq_hi = rank * N // world, (rank + 1) * N // world
+    host = [t[seq_lo:seq_hi].cpu().pin_memory() for t in full]
     h2d = sum(t.numel() * t.element_size() for t in host)
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
     copy_stream = torch.cuda.Stream(device=dev)
-    staging = [[torch.empty_like(t, device=dev) for t in host] for _ in range(2)]
+    staging = [[torch.empty_like(t, device=dev) for t in full] for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
+    even = (N % world == 0)
 
     def prefetch(slot):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[slot])          # the step that last used this slot is done
             for d, h in zip(staging[slot], host):
-                d.copy_(h, non_blocking=True)
+                d[seq_lo:seq_hi].copy_(h, non_blocking=True)
+            if world > 1:
+                for d in staging[slot]:
+                    if even:
+                        dist.all_gather_into_tensor(d, d[seq_lo:seq_hi], group=group)
+                    else:
+                        parts = [d[r * N // world:(r + 1) * N // world] for r in range(world)]
+                        dist.all_gather(parts, d[seq_lo:seq_hi], group=group)
             ready[slot].record(copy_stream)
 
     def e2e_run(n):
