@@ -1,9 +1,13 @@
 // K3a (first-EOS mask) and K3 (KL + group advantages + GSPO ratio/clip/loss, fwd+bwd).
 //
 // Replaces trainer/grpo_trainer.py:590-596 and :635-636, 658, 675-681, 691-706, 711, 737
-// of the reference.  Both kernels are HBM/launch bound (about 20 B per token): one CTA
-// per sequence, 128-bit loads, warp-shuffle reductions, and a deterministic last-CTA
-// reduction for the two scalars so that results are run-to-run bit-stable.
+// of the reference.  Both are HBM/launch bound (about 20 B per token).  K3 runs as two tiny
+// launches over a (slice, sequence) grid -- masked partial sums, then sequence totals in fixed
+// slice order + d loss / d logp -- with warp-shuffle reductions and a deterministic last-CTA
+// mean over the sequences, so results are run-to-run bit-stable and long sequences (16 x 16384
+// tokens) still spread over the whole GPU.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace o3v {
@@ -38,15 +42,18 @@ eos_mask_kernel(const int64_t* __restrict__ ids, int64_t Tc, int64_t eos_id,
 // ------------------------------------------------------------------------------------
 // K3
 // ------------------------------------------------------------------------------------
+constexpr int kMaxSlices = 32;   // CTAs per sequence (upper bound; fixes the workspace layout)
+
 struct GspoParams {
   const float* logp; const float* old_logp; const float* ref; const int32_t* mask;
   const float* rpf;
   int64_t N, Tc, F, G;      // N = TOTAL sequences of the step (loss is a mean over N)
-  int64_t seq_offset;       // this launch handles global sequences [seq_offset, seq_offset + gridDim.x)
+  int64_t seq_offset;       // this launch handles global sequences [seq_offset, seq_offset + gridDim.y)
+  int32_t S; int32_t slice_len;   // CTAs per sequence, tokens per CTA
   float beta, eps_lo, eps_hi; int gspo;
   float* loss; float* mean_kl; float* adv; float* rstd; int32_t* clen;
   float* grad; float* kl_out;
-  float* seq_loss; float* seq_kl; unsigned int* ticket;   // workspace
+  float* seq_loss; float* seq_kl; float* partials; unsigned int* ticket;   // workspace
 };
 
 __device__ __forceinline__ float block_sum(float v, float* smem) {
@@ -70,48 +77,44 @@ __device__ __forceinline__ void kl_and_grad(float lp, float rf, float& kl, float
   dkl = (x >= -10.f && x <= 10.f) ? (1.f - e) : 0.f;
 }
 
+// group advantage of global sequence n (grpo_trainer.py:658, 675-681); G is small, one thread does it
+__device__ __forceinline__ void group_advantage(const GspoParams& p, int64_t n, float& adv, float& sd) {
+  const int64_t g0 = (n / p.G) * p.G;
+  float mine = 0.f, mean = 0.f;
+  for (int64_t j = 0; j < p.G; ++j) {
+    float r = 0.f;
+    for (int64_t f = 0; f < p.F; ++f) r += p.rpf[(g0 + j) * p.F + f];
+    if (g0 + j == n) mine = r;
+    mean += r;
+  }
+  mean /= (float)p.G;
+  float var = 0.f;
+  for (int64_t j = 0; j < p.G; ++j) {
+    float r = 0.f;
+    for (int64_t f = 0; f < p.F; ++f) r += p.rpf[(g0 + j) * p.F + f];
+    var += (r - mean) * (r - mean);
+  }
+  sd = sqrtf(var / (float)(p.G - 1));   // unbiased; G == 1 -> NaN like torch.std
+  adv = (mine - mean) / (sd + 1e-4f);
+}
+
+// pass 1: masked partial sums of one slice of one sequence -> partials[n][slice][4]
 __global__ void __launch_bounds__(kGspoThreads)
-gspo_kernel(const GspoParams p) {
+gspo_partial_kernel(const GspoParams p) {
   __shared__ float s_red[kGspoThreads / 32];
-  __shared__ float s_bcast[4];
-  __shared__ bool s_last;
-  const int64_t nl = blockIdx.x;                  // row in this launch's [n_seq, Tc] buffers
-  const int64_t n = p.seq_offset + nl;            // global sequence index (rewards, per-sequence outputs)
+  __shared__ float s_bcast[2];
+  const int64_t nl = blockIdx.y, n = p.seq_offset + nl;
   const int64_t Tc = p.Tc;
+  const int64_t t0 = (int64_t)blockIdx.x * p.slice_len, t1 = min(t0 + p.slice_len, Tc);
   const float* lp_row = p.logp + nl * Tc;
   const float* old_row = p.old_logp ? p.old_logp + nl * Tc : nullptr;
   const float* ref_row = p.ref + nl * Tc;
   const int32_t* m_row = p.mask + nl * Tc;
-
-  // ---- group advantage (grpo_trainer.py:658, 675-681); G is small, one thread does it
-  if (threadIdx.x == 0) {
-    const int64_t g0 = (n / p.G) * p.G;
-    float mine = 0.f, mean = 0.f;
-    for (int64_t j = 0; j < p.G; ++j) {
-      float r = 0.f;
-      for (int64_t f = 0; f < p.F; ++f) r += p.rpf[(g0 + j) * p.F + f];
-      if (g0 + j == n) mine = r;
-      mean += r;
-    }
-    mean /= (float)p.G;
-    float var = 0.f;
-    for (int64_t j = 0; j < p.G; ++j) {
-      float r = 0.f;
-      for (int64_t f = 0; f < p.F; ++f) r += p.rpf[(g0 + j) * p.F + f];
-      var += (r - mean) * (r - mean);
-    }
-    const float sd = sqrtf(var / (float)(p.G - 1));   // unbiased; G == 1 -> NaN like torch.std
-    const float a = (mine - mean) / (sd + 1e-4f);
-    s_bcast[0] = a;
-    if (p.adv) p.adv[n] = a;
-    if (p.rstd) p.rstd[n] = sd;
-  }
+  if (threadIdx.x == 0) { float a, sd; group_advantage(p, n, a, sd); s_bcast[0] = a; }
   __syncthreads();
   const float A = s_bcast[0];
-
-  // ---- pass 1: masked sums
   float cnt = 0.f, sum_lr = 0.f, sum_kl = 0.f, sum_obj = 0.f;
-  for (int64_t t = threadIdx.x; t < Tc; t += kGspoThreads) {
+  for (int64_t t = t0 + threadIdx.x; t < t1; t += kGspoThreads) {
     const float lp = lp_row[t], rf = ref_row[t];
     const float m = (float)m_row[t];
     float kl, dkl;
@@ -130,38 +133,71 @@ gspo_kernel(const GspoParams p) {
   cnt = block_sum(cnt, s_red);
   sum_lr = block_sum(sum_lr, s_red);
   sum_kl = block_sum(sum_kl, s_red);
-  if (!p.gspo) sum_obj = block_sum(sum_obj, s_red);
-
-  const float denom = fmaxf(cnt, 1.f);                      // .clamp(min=1.0) :693, :706
-  float c1_seq = 1.f, gate_seq = 1.f;
-  if (p.gspo) {
-    const float s = sum_lr / denom;                         // :693
-    c1_seq = expf(s);                                       // :698
-    const float c2 = fminf(fmaxf(c1_seq, 1.f - p.eps_lo), 1.f + p.eps_hi);   // :699
-    const float obj = -fminf(c1_seq * A, c2 * A);           // :701-703 (constant over t)
-    sum_obj = obj * cnt;
-    // d(-min(c1 A, clamp(c1) A))/dc1 = -A * gate  (torch.minimum splits ties, clamp passes
-    // gradient on the closed interval, so inside the clip range the two halves add up)
-    gate_seq = (A > 0.f) ? (c1_seq <= 1.f + p.eps_hi ? 1.f : 0.f)
-             : (A < 0.f) ? (c1_seq >= 1.f - p.eps_lo ? 1.f : 0.f) : 1.f;
-  }
+  sum_obj = block_sum(sum_obj, s_red);
   if (threadIdx.x == 0) {
-    p.seq_loss[n] = (sum_obj + p.beta * sum_kl) / denom;    // :704-706
-    p.seq_kl[n] = sum_kl / cnt;                             // :737 (no clamp: 0/0 -> NaN as reference)
-    if (p.clen) p.clen[n] = (int32_t)cnt;                   // :711
+    float* part = p.partials + (n * kMaxSlices + blockIdx.x) * 4;
+    part[0] = cnt; part[1] = sum_lr; part[2] = sum_kl; part[3] = sum_obj;
   }
+}
 
-  // ---- pass 2: d loss / d logp
+// pass 2: sequence totals (fixed slice order), per-sequence outputs, d loss / d logp of the slice,
+// and the deterministic mean over all N sequences by the last CTA of the step
+__global__ void __launch_bounds__(kGspoThreads)
+gspo_finish_kernel(const GspoParams p) {
+  __shared__ float s_red[kGspoThreads / 32];
+  __shared__ float s_tot[8];
+  __shared__ bool s_last;
+  const int64_t nl = blockIdx.y, n = p.seq_offset + nl;
+  const int64_t Tc = p.Tc;
+  const int64_t t0 = (int64_t)blockIdx.x * p.slice_len, t1 = min(t0 + p.slice_len, Tc);
+  if (threadIdx.x == 0) {
+    float cnt = 0.f, sum_lr = 0.f, sum_kl = 0.f, sum_obj = 0.f;
+    for (int sidx = 0; sidx < p.S; ++sidx) {
+      const float* part = p.partials + (n * kMaxSlices + sidx) * 4;
+      cnt += part[0]; sum_lr += part[1]; sum_kl += part[2]; sum_obj += part[3];
+    }
+    float A, sd;
+    group_advantage(p, n, A, sd);
+    const float denom = fmaxf(cnt, 1.f);                      // .clamp(min=1.0) :693, :706
+    float c1_seq = 1.f, gate_seq = 1.f;
+    if (p.gspo) {
+      const float sl = sum_lr / denom;                        // :693
+      c1_seq = expf(sl);                                      // :698
+      const float c2 = fminf(fmaxf(c1_seq, 1.f - p.eps_lo), 1.f + p.eps_hi);   // :699
+      sum_obj = -fminf(c1_seq * A, c2 * A) * cnt;             // :701-703 (constant over t)
+      // d(-min(c1 A, clamp(c1) A))/dc1 = -A * gate  (torch.minimum splits ties, clamp passes
+      // gradient on the closed interval, so inside the clip range the two halves add up)
+      gate_seq = (A > 0.f) ? (c1_seq <= 1.f + p.eps_hi ? 1.f : 0.f)
+               : (A < 0.f) ? (c1_seq >= 1.f - p.eps_lo ? 1.f : 0.f) : 1.f;
+    }
+    if (blockIdx.x == 0) {
+      p.seq_loss[n] = (sum_obj + p.beta * sum_kl) / denom;    // :704-706
+      p.seq_kl[n] = sum_kl / cnt;                             // :737 (no clamp: 0/0 -> NaN as reference)
+      if (p.clen) p.clen[n] = (int32_t)cnt;                   // :711
+      if (p.adv) p.adv[n] = A;
+      if (p.rstd) p.rstd[n] = sd;
+    }
+    s_tot[0] = A; s_tot[1] = cnt; s_tot[2] = denom; s_tot[3] = c1_seq; s_tot[4] = gate_seq;
+  }
+  __syncthreads();
   if (p.grad) {
+    const float A = s_tot[0], cnt = s_tot[1], denom = s_tot[2], c1_seq = s_tot[3], gate_seq = s_tot[4];
+    const float* lp_row = p.logp + nl * Tc;
+    const float* old_row = p.old_logp ? p.old_logp + nl * Tc : nullptr;
+    const float* ref_row = p.ref + nl * Tc;
+    const int32_t* m_row = p.mask + nl * Tc;
     const float scale = 1.f / (denom * (float)p.N);
-    for (int64_t t = threadIdx.x; t < Tc; t += kGspoThreads) {
+    // GSPO: the per-token objective is constant over t, its masked mean is obj*cnt/denom,
+    // and ds/dlogp_t = mask_t/denom, so the factor is (cnt/denom) * mask_t/denom.
+    const float w = p.gspo ? (cnt / denom) : 1.f;
+    for (int64_t t = t0 + threadIdx.x; t < t1; t += kGspoThreads) {
       const float lp = lp_row[t], rf = ref_row[t];
       const float m = (float)m_row[t];
       float kl, dkl;
       kl_and_grad(lp, rf, kl, dkl);
       float dobj;
       if (p.gspo) {
-        dobj = -A * c1_seq * gate_seq;       // chain through s = sum(lr*mask)/denom handled by `scale`
+        dobj = -A * c1_seq * gate_seq;
       } else {
         const float lr = old_row ? (lp - old_row[t]) : 0.f;
         const float c1 = expf(lr);
@@ -169,18 +205,14 @@ gspo_kernel(const GspoParams p) {
                          : (A < 0.f) ? (c1 >= 1.f - p.eps_lo ? 1.f : 0.f) : 1.f;
         dobj = -A * c1 * gate;
       }
-      // GSPO: the per-token objective is constant over t, its masked mean is obj*cnt/denom,
-      // and ds/dlogp_t = mask_t/denom, so the factor is (cnt/denom) * mask_t/denom.
-      const float w = p.gspo ? (cnt / denom) : 1.f;
       p.grad[nl * Tc + t] = m * scale * (dobj * w + p.beta * dkl);
     }
   }
-
-  // ---- deterministic final reduction by the last CTA to finish
+  // ---- deterministic final reduction by the last CTA of the step (across range calls)
   __threadfence();
   if (threadIdx.x == 0) {
     const unsigned int done = atomicAdd(p.ticket, 1u);
-    s_last = (done == (unsigned int)(p.N - 1));
+    s_last = (done == (unsigned int)(p.N * p.S - 1));
   }
   __syncthreads();
   if (s_last) {
@@ -195,7 +227,7 @@ gspo_kernel(const GspoParams p) {
     if (threadIdx.x == 0) {
       *p.loss = a / (float)p.N;                             // .mean() :706
       if (p.mean_kl) *p.mean_kl = b / (float)p.N;           // .mean() :737
-      *p.ticket = 0u;                                       // re-arm for the next call
+      *p.ticket = 0u;                                       // re-arm for the next step
     }
   }
 }
@@ -217,7 +249,7 @@ extern "C" int o3v_eos_mask(const int64_t* completion_ids, int64_t N, int64_t Tc
 
 extern "C" size_t o3v_gspo_workspace_bytes(int64_t N) {
   if (N < 0) return 0;
-  return (size_t)(2 * N + 4) * sizeof(float);
+  return (size_t)(2 * N + 4 + N * o3v::kMaxSlices * 4) * sizeof(float);
 }
 
 extern "C" int o3v_gspo_fwd_bwd(const float* logp, const float* old_logp, const float* ref_logp,
@@ -237,16 +269,26 @@ extern "C" int o3v_gspo_fwd_bwd(const float* logp, const float* old_logp, const 
   o3v::GspoParams p;
   p.logp = logp; p.old_logp = old_logp; p.ref = ref_logp; p.mask = mask; p.rpf = rewards_per_func;
   p.N = N; p.Tc = Tc; p.F = F; p.G = G; p.seq_offset = seq_offset;
+  // CTAs per sequence: fill ~2 waves of SMs over the whole step, at least 512 tokens per CTA; a function
+  // of (N, Tc) only so that every range call of a step uses the same slicing
+  int64_t S = (2 * o3v::num_sms() + N - 1) / N;
+  S = std::min<int64_t>(S, (Tc + 511) / 512);
+  S = std::max<int64_t>(1, std::min<int64_t>(S, o3v::kMaxSlices));
+  p.slice_len = (int32_t)((Tc + S - 1) / S);
+  p.S = (int32_t)((Tc + p.slice_len - 1) / p.slice_len);
   p.beta = beta; p.eps_lo = eps_low; p.eps_hi = eps_high; p.gspo = gspo ? 1 : 0;
   p.loss = loss; p.mean_kl = mean_kl; p.adv = advantages; p.rstd = reward_std; p.clen = completion_len;
   p.grad = grad_logp; p.kl_out = per_token_kl;
   float* ws = (float*)workspace;
-  p.seq_loss = ws; p.seq_kl = ws + N; p.ticket = (unsigned int*)(ws + 2 * N);
+  p.seq_loss = ws; p.seq_kl = ws + N; p.ticket = (unsigned int*)(ws + 2 * N); p.partials = ws + 2 * N + 4;
   cudaStream_t st = (cudaStream_t)stream;
-  // the ticket counts finished sequences ACROSS the range calls of one step; the CTA that
-  // finishes sequence number N reduces loss / mean_kl over all N in index order
+  // the ticket counts finished CTAs ACROSS the range calls of one step; the CTA that finishes last
+  // reduces loss / mean_kl over all N sequences in index order
   if (seq_offset == 0) O3V_CUDA_TRY(cudaMemsetAsync(p.ticket, 0, sizeof(unsigned int), st));
-  o3v::gspo_kernel<<<(unsigned)n_seq, o3v::kGspoThreads, 0, st>>>(p);
+  const dim3 grid((unsigned)p.S, (unsigned)n_seq);
+  o3v::gspo_partial_kernel<<<grid, o3v::kGspoThreads, 0, st>>>(p);
+  O3V_LAUNCH_CHECK();
+  o3v::gspo_finish_kernel<<<grid, o3v::kGspoThreads, 0, st>>>(p);
   O3V_LAUNCH_CHECK();
   return O3V_OK;
 }

@@ -73,7 +73,7 @@ def gspo_raw(logp, ref, mask, rewards_per_func, num_generations, beta, epsilon_l
     rpf = rewards_per_func
     F = rpf.shape[1]
     with torch.cuda.device(dev):
-        _lib.call("o3v_gspo_fwd_bwd", 1, lib.o3v_gspo_fwd_bwd,
+        _lib.call("o3v_gspo_fwd_bwd", 2, lib.o3v_gspo_fwd_bwd,
                   _p(logp), _p(old), _p(ref), _p(mask), _p(rpf), N, Tc, F, int(num_generations),
                   int(seq_offset), n_seq, float(beta), float(epsilon_low), float(epsilon_high), 1 if gspo else 0,
                   _p(state["loss"]), _p(state["mean_kl"]), _p(state["adv"]), _p(state["rstd"]), _p(state["clen"]),
