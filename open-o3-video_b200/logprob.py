@@ -175,6 +175,25 @@ def per_token_logps(hidden: torch.Tensor, weight: torch.Tensor, input_ids: torch
     return fused_logprob(h, weight, tgt, **kw).view(B, L - 1)
 
 
+def sft_cross_entropy(hidden: torch.Tensor, weight: torch.Tensor, labels: torch.Tensor, ignore_index: int = -100,
+                      num_items_in_batch=None, **kw) -> torch.Tensor:
+    """Causal-LM cross-entropy of the SFT stage on the same fused head (the loss the reference's
+    `MySFTTrainer.compute_loss`, sft_multi_task.py:402-409, gets from the HF model for the labels
+    built at :387-398): shift by one, ignore `ignore_index`, mean over the remaining targets (or
+    sum / num_items_in_batch).  hidden [B, L, H] bf16, labels [B, L].  Ignored positions are
+    compacted away before the GEMM, so pad / visual tokens cost nothing; autograd reaches hidden
+    and weight through `fused_logprob`."""
+    B, L, H = hidden.shape
+    tgt = labels[:, 1:].reshape(-1)
+    keep = (tgt != ignore_index).nonzero(as_tuple=True)[0]
+    h = hidden[:, :-1, :].reshape(B * (L - 1), H).index_select(0, keep)
+    if keep.numel() == 0:
+        return (h.sum() * 0.0).to(torch.float32)
+    logp = fused_logprob(h, weight, tgt.index_select(0, keep), **kw)
+    denom = keep.numel() if num_items_in_batch is None else num_items_in_batch
+    return -logp.sum() / denom
+
+
 def fused_logprob_gspo(hidden: torch.Tensor, weight: torch.Tensor, completion_ids: torch.Tensor,
                        ref_per_token_logps: torch.Tensor, completion_mask: torch.Tensor,
                        rewards_per_func: torch.Tensor, num_generations: int, beta: float,

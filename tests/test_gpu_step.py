@@ -134,3 +134,28 @@ def test_trainer_mixin_keeps_reference_contract():
     assert abs(loss.item() - ref["loss"].item()) < 1e-6
     assert set(t._metrics) >= {"completion_length", "all_wrong", "all_correct", "reward", "reward_std", "kl"}
     assert abs(t._metrics["kl"][0] - ref["mean_kl"].item()) < 1e-6
+
+
+@pytest.mark.parametrize("num_items", [None, 37])
+def test_sft_cross_entropy_matches_oracle(num_items):
+    """the SFT loss on the fused head, with -100 labels (pad / visual tokens)."""
+    from open_o3_video_b200 import logprob
+    from oracle import sft as osft
+    B, L, H, V = 3, 50, 128, 3000
+    hidden, weight, _ = synth.head_inputs(B * L, H, V, seed=41)
+    g = torch.Generator().manual_seed(42)
+    labels = torch.randint(0, V, (B, L), generator=g)
+    labels[torch.rand(B, L, generator=g) < 0.4] = -100
+    labels[1, 1:] = -100                                       # a fully ignored sequence
+    h_ref = hidden.view(B, L, H).clone().requires_grad_(True)
+    w_ref = weight.clone().requires_grad_(True)
+    exp = osft.causal_lm_loss(h_ref, w_ref, labels, num_items_in_batch=num_items)
+    exp.backward()
+    h = hidden.view(B, L, H).cuda().bfloat16().requires_grad_(True)
+    w = weight.cuda().bfloat16().requires_grad_(True)
+    loss = logprob.sft_cross_entropy(h, w, labels.cuda(), num_items_in_batch=num_items)
+    loss.backward()
+    assert abs(loss.item() - exp.item()) <= 1e-3 * abs(exp.item())
+    assert (h.grad.float().cpu() - h_ref.grad).norm() / h_ref.grad.norm() < 1e-2
+    assert (w.grad.float().cpu() - w_ref.grad).norm() / w_ref.grad.norm() < 1e-2
+    assert (h.grad[1] == 0).all() and (h.grad[:, -1] == 0).all()
