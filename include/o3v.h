@@ -209,6 +209,31 @@ typedef struct o3v_rewards_soa {
 
 int o3v_grounded_rewards(const o3v_rewards_soa* soa, double* out, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * K5  V-STAR scorer numerics (the offline counterpart of the reward numerics).
+ * Replaces, per result item and answer chain, eval/test/eval_vstar.py:90-109
+ * (calculate_temporal_iou), :112-146 (compute_iou, calculate_bbox_iou) and :148-178
+ * (calculate_spatial_metrics: per-GT-frame max IoU over the predicted boxes, their mean in
+ * numpy's pairwise summation order, AP at IoU >= 0.1/0.3/0.5/0.7/0.9).
+ * out [I, 14] fp64 = chain 1 (tIoU, mIoU, AP x5), chain 2 (same).  F <= 64, Pb <= 32.
+ * ---------------------------------------------------------------------------------- */
+typedef struct o3v_vstar_soa {
+  int64_t I;                /* result items */
+  int32_t F;                /* max GT boxes (annotated frames) per item */
+  int32_t Pb;               /* max predicted boxes per frame */
+  const int32_t* t_valid;   /* [I, 2] chain's temporal answer is a list of 2 numbers (:97-104) */
+  const double* gt_seg;     /* [I, 2] item['timestamps'] */
+  const double* pred_seg;   /* [I, 2, 2] */
+  const int32_t* sp_valid;  /* [I, 2] chain's spatial answer is non-empty (:150, :293) */
+  const int32_t* n_frames;  /* [I] */
+  const double* gt_box;     /* [I, F, 4] xmin, ymin, xmax, ymax */
+  const int32_t* n_pb;      /* [I, 2, F] predicted boxes for the frame (0: frame id absent / empty) */
+  const uint32_t* pb_valid; /* [I, 2, F] bit b: box b is a list of 4 numbers (:114) */
+  const double* pb;         /* [I, 2, F, Pb, 4] */
+} o3v_vstar_soa;
+
+int o3v_vstar_scores(const o3v_vstar_soa* soa, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,12 @@ class RewardsSoA(ctypes.Structure):
                     "kf_time", "n_obj", "n_gtbox", "gt_box")]
 
 
+class VstarSoA(ctypes.Structure):
+    """struct o3v_vstar_soa (include/o3v.h)."""
+    _fields_ = [("I", c_int64), ("F", c_int32), ("Pb", c_int32)] + [(n, c_void_p) for n in (
+        "t_valid", "gt_seg", "pred_seg", "sp_valid", "n_frames", "gt_box", "n_pb", "pb_valid", "pb")]
+
+
 # name -> (restype, argtypes); must list EVERY function include/o3v.h declares
 SIGNATURES = {
     "o3v_version": (c_int, []),
@@ -49,6 +55,7 @@ SIGNATURES = {
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_size_t, c_void_p]),
     "o3v_grounded_rewards": (c_int, [ctypes.POINTER(RewardsSoA), c_void_p, c_void_p]),
+    "o3v_vstar_scores": (c_int, [ctypes.POINTER(VstarSoA), c_void_p, c_void_p]),
 }
 
 _lib = None

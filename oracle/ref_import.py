@@ -81,3 +81,24 @@ class FakeLMHeadModel:
     def __call__(self, input_ids, **kwargs):
         import torch.nn.functional as F
         return types.SimpleNamespace(logits=F.linear(self.hidden, self.weight))
+
+
+def load_vstar_functions():
+    """Numeric functions of the reference's V-STAR scorer (eval/test/eval_vstar.py:90-198).
+
+    The module itself cannot be imported (it parses argv and loads a 72B judge model at import
+    time, :10-25), so the five pure functions are compiled from the reference file's own AST and
+    executed in a namespace holding what they use (np, ast).  Nothing is copied into this repo."""
+    import ast as _ast
+    import numpy as _np
+    path = os.path.join(REFERENCE_ROOT, "eval", "test", "eval_vstar.py")
+    if not os.path.isfile(path):
+        raise RuntimeError("reference not present at %s" % REFERENCE_ROOT)
+    tree = _ast.parse(open(path).read(), filename=path)
+    want = {"calculate_temporal_iou", "compute_iou", "calculate_bbox_iou", "calculate_spatial_metrics",
+            "calculate_spatial_random"}
+    body = [n for n in tree.body if isinstance(n, _ast.FunctionDef) and n.name in want]
+    assert {n.name for n in body} == want
+    ns = {"np": _np, "ast": _ast}
+    exec(compile(_ast.Module(body=body, type_ignores=[]), path, "exec"), ns)
+    return types.SimpleNamespace(**{k: ns[k] for k in want})

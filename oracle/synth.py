@@ -158,3 +158,53 @@ def rollouts(n_prompts, G, P=16, K=8, O=4, Gb=1, Bc=2, seed=SEED, tasks=None):
                 r["think_times"], r["think_boxes"], r["claims"] = [], [], []
             out.append(r)
     return out
+
+
+def vstar_items(n, F=12, Pb=3, seed=SEED):
+    """Synthetic V-STAR result items in the JSON shape eval_vstar.py reads (:213-312): GT segment
+    `timestamps`, GT `bboxes` (one per annotated second), two answer chains with a temporal range and
+    a {frame_id: box | [boxes]} spatial answer; 10 % missing / malformed answers."""
+    rng = random.Random(seed + 3)
+    items = []
+    for i in range(n):
+        W, H = _SIZES[i % len(_SIZES)]
+        dur = _r2(rng.uniform(5, 200))
+        a, b = sorted((_r2(rng.uniform(0, dur)), _r2(rng.uniform(0, dur))))
+        nf = rng.randint(0 if i % 17 == 0 else 1, F)
+        stamps = sorted(rng.sample(range(0, 400), nf))
+        bboxes = []
+        for t in stamps:
+            x0, x1 = sorted((rng.randint(0, W), rng.randint(0, W)))
+            y0, y1 = sorted((rng.randint(0, H), rng.randint(0, H)))
+            bboxes.append({"timestamp": t, "xmin": x0, "ymin": y0, "xmax": x1, "ymax": y1})
+        item = dict(timestamps=[a, b], bboxes=bboxes, width=W, height=H)
+        for suffix in ("", "_2"):
+            u = rng.random()
+            if u < 0.08:
+                at = []
+            elif u < 0.12:
+                at = [_r2(rng.uniform(0, dur))]                      # wrong arity -> 0
+            else:
+                s_, e_ = _r2(rng.uniform(0, dur)), _r2(rng.uniform(0, dur))
+                at = [min(s_, e_), max(s_, e_)] if rng.random() < 0.85 else [max(s_, e_), min(s_, e_)]
+            item["answer_temporal" + suffix] = at
+            sp = {}
+            for bx in bboxes:
+                if rng.random() < 0.75:
+                    def pb():
+                        x0, x1 = sorted((rng.randint(0, W), rng.randint(0, W)))
+                        y0, y1 = sorted((rng.randint(0, H), rng.randint(0, H)))
+                        if rng.random() < 0.3:        # near the GT box
+                            x0, y0, x1, y1 = bx["xmin"] + rng.randint(-9, 9), bx["ymin"] + rng.randint(-9, 9), \
+                                bx["xmax"] + rng.randint(-9, 9), bx["ymax"] + rng.randint(-9, 9)
+                        v = rng.random()
+                        if v < 0.04:
+                            return [x0, y0, x1]       # malformed -> IoU 0
+                        return [x0, y0, x1, y1]
+                    k = rng.randint(1, Pb)
+                    sp[str(bx["timestamp"])] = pb() if (k == 1 and rng.random() < 0.5) else [pb() for _ in range(k)]
+            if rng.random() < 0.05:
+                sp = {}
+            item["answer_spatial" + suffix] = sp
+        items.append(item)
+    return items

@@ -87,6 +87,27 @@ def gen_rewards():
     print("calculate_iou KAT", iou, type(iou[0]))
 
 
+def gen_vstar():
+    """Reference eval/test/eval_vstar.py numeric functions on synthetic result items."""
+    rf = ref_import.load_vstar_functions()
+    items = synth.vstar_items(150)
+    rows = []
+    for it in items:
+        row = []
+        for suffix in ("", "_2"):
+            at = it.get("answer_temporal" + suffix)
+            t = rf.calculate_temporal_iou(it["timestamps"], at) if at else 0.0
+            sp = it.get("answer_spatial" + suffix)
+            aps, miou = rf.calculate_spatial_metrics(it["bboxes"], sp) if sp else ([0.0] * 5, 0.0)
+            row += [t, miou] + list(aps)
+        rows.append([repr(float(x)) for x in row])
+    with open(os.path.join(HERE, "vstar_small.json"), "w") as f:
+        json.dump(dict(seed=synth.SEED, n=150, expected=rows), f)
+    arr = np.array([[float(x) for x in r] for r in rows])
+    print("vstar_small.json", arr.shape, "means", arr.mean(0).round(4).tolist())
+
+
 if __name__ == "__main__":
     gen_logps()
     gen_rewards()
+    gen_vstar()

@@ -132,3 +132,21 @@ def test_rewards_c4_scale_properties():
     ro2 = [ro[q * 8 + g] for q in perm for g in range(8)]
     got2 = rewards.rewards_from_rollouts(ro2, 8).cpu().numpy().reshape(8192, 8, 5)
     assert np.array_equal(got2, got.reshape(8192, 8, 5)[perm])
+
+
+def test_vstar_scores_parity(golden_dir):
+    """K5 against the oracle (itself pinned to the reference's eval_vstar.py): bit-exact."""
+    import json, os
+    from open_o3_video_b200 import vstar
+    from oracle import vstar as ovs
+    for n, F, Pb, seed in ((150, 12, 3, synth.SEED), (400, 40, 6, 5), (3, 1, 1, 9)):
+        items = synth.vstar_items(n, F=F, Pb=Pb, seed=seed)
+        got = vstar.score_items(items).cpu().numpy()
+        exp = np.array([ovs.item_scores(it) for it in items])
+        assert np.array_equal(got, exp), np.abs(got - exp).max()
+    assert vstar.score_items([]).shape == (0, 14)
+    items = synth.vstar_items(150)
+    vqa = [i % 4 for i in range(150)]
+    agg, ref = vstar.evaluate(items, vqa), ovs.aggregate(np.array([ovs.item_scores(it) for it in items]), vqa)
+    for k, v in ref.items():
+        assert np.allclose(agg[k], v, rtol=0, atol=1e-15), k
