@@ -165,6 +165,9 @@ def run_ours(args):
         _lib.set_tunable("cta_pair", args.cta_pair)
     if args.fwd_groups:
         _lib.set_tunable("fwd_groups", args.fwd_groups)
+    for kv in args.tunable:
+        k, v = kv.split("=")
+        _lib.set_tunable(k, int(v))
 
     H, V, G, Tc = cfg["H"], cfg["V"], cfg["G"], cfg["Tc"]
     N = cfg["prompts"] * G
@@ -344,6 +347,7 @@ def main():
     ap.add_argument("--chunk-tokens", type=int, default=0, help="0 = size the chunk from a 10 GB logits buffer")
     ap.add_argument("--cta-pair", type=int, default=0)
     ap.add_argument("--fwd-groups", type=int, default=0)
+    ap.add_argument("--tunable", action="append", default=[], help="name=value for o3v_set_tunable (diagnostics)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
