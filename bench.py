@@ -156,10 +156,10 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    group = None
+    group = pg = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-        group = dist.group.WORLD
+        group = pg = dist.group.WORLD
     _lib.check(_lib.load().o3v_check_device(), "o3v_check_device")
     if args.cta_pair:
         _lib.set_tunable("cta_pair", args.cta_pair)
@@ -182,6 +182,8 @@ def run_ours(args):
     ids[torch.arange(N, device=dev), lens - 1] = eos_id      # planted EOS drives the mask
     _, mask = gspo.eos_mask(ids, eos_id)
     weight, v_off = sharded.shard_weight(w_full, rank, world)
+    if world > 1 and args.exchange == "peer":
+        group = sharded.PeerExchange(dist.group.WORLD, capacity_tokens=T)
     if not args.chunk_tokens:
         per_seq = max(1, min(N, logprob.auto_chunk_tokens(weight.shape[0]) // Tc))
         args.chunk_tokens = -(-N // (-(-N // per_seq))) * Tc      # evened out over whole sequences
@@ -257,10 +259,10 @@ def run_ours(args):
             if world > 1:
                 for d in staging[slot]:
                     if even:
-                        dist.all_gather_into_tensor(d, d[seq_lo:seq_hi], group=group)
+                        dist.all_gather_into_tensor(d, d[seq_lo:seq_hi], group=pg)
                     else:
                         parts = [d[r * N // world:(r + 1) * N // world] for r in range(world)]
-                        dist.all_gather(parts, d[seq_lo:seq_hi], group=group)
+                        dist.all_gather(parts, d[seq_lo:seq_hi], group=pg)
             ready[slot].record(copy_stream)
 
     def e2e_run(n):
@@ -316,7 +318,8 @@ def run_ours(args):
         dtype="bf16", data="synthetic",
         config=dict(workload="%s: %s head (H=%d, V=%d), %d prompts x G=%d x %d completion tokens = %d tokens/step, "
                              "fused logprob+GSPO fwd+bwd" % (args.config, cfg["head"], H, V, cfg["prompts"], G, Tc, T),
-                    parallelism="vocab-sharded x%d (NCCL all-gather of softmax triples, all-reduce of dHidden)" % world
+                    parallelism="vocab-sharded x%d (%s exchange of softmax triples, NCCL all-reduce of dHidden)"
+                                % (world, "fused NVLink peer-memory" if args.exchange == "peer" else "NCCL all-gather")
                     if world > 1 else "single GPU", chunk_tokens=args.chunk_tokens,
                     cache="inputs (%.1f GB) and per-chunk logits are far larger than the 126 MB L2; no flush needed"
                           % ((hidden.numel() * 2 + weight.numel() * 2) / 1e9), loss=loss),
@@ -347,6 +350,8 @@ def main():
     ap.add_argument("--chunk-tokens", type=int, default=0, help="0 = size the chunk from a 10 GB logits buffer")
     ap.add_argument("--cta-pair", type=int, default=0)
     ap.add_argument("--fwd-groups", type=int, default=0)
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: forward exchange of the softmax triples (peer = fused NVLink merge kernel)")
     ap.add_argument("--tunable", action="append", default=[], help="name=value for o3v_set_tunable (diagnostics)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -94,6 +94,13 @@ int o3v_lmhead_fwd(const void* hidden, const void* weight, const int64_t* target
 int o3v_lmhead_merge_stats(const float* parts, int64_t P, int64_t T,
                            float* logp, float* lse, void* stream);
 
+/* Same merge fused with the vocab-parallel exchange: part_ptrs[p] (a HOST array of P <= 16 device
+ * pointers) is rank p's [3, row_stride] triple in peer-mapped memory (NVLink P2P / symmetric
+ * memory); every rank loads all P triples directly over NVLink instead of all-gathering them
+ * first.  The caller orders the launch after a cross-rank barrier on `stream`. */
+int o3v_lmhead_merge_stats_peers(const float* const* part_ptrs, int64_t P, int64_t row_stride, int64_t T,
+                                 float* logp, float* lse, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * K2  chunked fused backward of K1 (replaces the autograd backward of
  * grpo_trainer.py:375-383: softmax-backward + two GEMMs).

@@ -163,6 +163,32 @@ __global__ void merge_stats_kernel(const float* __restrict__ parts, int64_t P, i
   }
 }
 
+// Same merge, reading each rank's [3, row_stride] triple through its peer-mapped pointer (NVLink
+// loads, 12 B per token per rank): the all-gather and the merge are one kernel.
+struct PeerPtrs { const float* p[16]; };
+__global__ void merge_stats_peers_kernel(const PeerPtrs ptrs, int P, int64_t row_stride, int64_t T,
+                                         float* __restrict__ logp, float* __restrict__ lse) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  float m[16], sv[16], z = 0.f, M = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    if (i < P) {                                   // issue every peer load before the first use
+      m[i] = __ldcv(ptrs.p[i] + t);
+      sv[i] = __ldcv(ptrs.p[i] + row_stride + t);
+      z += __ldcv(ptrs.p[i] + 2 * row_stride + t);
+      M = fmaxf(M, m[i]);
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    if (i < P) s += sv[i] * ((m[i] == -INFINITY) ? 0.f : expf(m[i] - M));   // fixed rank order: deterministic
+  const float l = M + logf(s);
+  if (lse) lse[t] = l;
+  if (logp) logp[t] = z - l;
+}
+
 // ------------------------------------------------------------------------------------
 // dlogits: P[t,v] = g[t] * ([v + v_offset == target[t]] - exp(z[t,v] - lse[t])), in place, bf16
 // ------------------------------------------------------------------------------------
@@ -268,6 +294,21 @@ extern "C" int o3v_lmhead_merge_stats(const float* parts, int64_t P, int64_t T, 
   int rc = check_device();
   if (rc) return rc;
   merge_stats_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, (cudaStream_t)stream>>>(parts, P, T, nullptr, logp, lse);
+  O3V_LAUNCH_CHECK();
+  return O3V_OK;
+}
+
+extern "C" int o3v_lmhead_merge_stats_peers(const float* const* part_ptrs, int64_t P, int64_t row_stride, int64_t T,
+                                            float* logp, float* lse, void* stream) {
+  if (!part_ptrs || (!logp && !lse) || P <= 0 || P > 16 || T <= 0 || row_stride < T) return O3V_ERR_INVALID_ARG;
+  int rc = check_device();
+  if (rc) return rc;
+  PeerPtrs ptrs = {};
+  for (int64_t i = 0; i < P; ++i) {
+    if (!part_ptrs[i]) return O3V_ERR_INVALID_ARG;
+    ptrs.p[i] = part_ptrs[i];
+  }
+  merge_stats_peers_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, (cudaStream_t)stream>>>(ptrs, (int)P, row_stride, T, logp, lse);
   O3V_LAUNCH_CHECK();
   return O3V_OK;
 }

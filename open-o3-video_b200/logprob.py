@@ -38,14 +38,15 @@ def _check_head(hidden, weight, targets):
         raise ValueError("targets must be [T]")
 
 
-def lmhead_stats(hidden, weight, targets, v_offset=0, logits_out=None):
+def lmhead_stats(hidden, weight, targets, v_offset=0, logits_out=None, stats_out=None):
     """K1 on one vocab slice -> stats [3, T] fp32 (row max, sum exp(z - max), target logit).
-    `logits_out` ([T, ld] bf16, optional) also receives the bf16 logits."""
+    `logits_out` ([T, ld] bf16, optional) also receives the bf16 logits; `stats_out` (a contiguous
+    [3, T] fp32 buffer, e.g. in peer-mapped memory) receives the triple instead of a new tensor."""
     T, H = hidden.shape
     V = weight.shape[0]
     lib = _lib.load()
     dev = hidden.device
-    stats = torch.empty(3, T, dtype=torch.float32, device=dev)
+    stats = torch.empty(3, T, dtype=torch.float32, device=dev) if stats_out is None else stats_out
     ws = torch.empty(int(lib.o3v_lmhead_fwd_workspace_bytes(T, V, H)), dtype=torch.uint8, device=dev)
     ld = 0 if logits_out is None else logits_out.stride(0)
     with torch.cuda.device(dev):
@@ -64,6 +65,35 @@ def merge_stats(parts):
         _lib.call("o3v_lmhead_merge_stats", 1, _lib.load().o3v_lmhead_merge_stats, _p(parts), P, T, _p(logp),
                   _p(lse), _stream())
     return logp, lse
+
+
+def _is_peer(group):
+    return group is not None and hasattr(group, "merge") and hasattr(group, "local_stats")
+
+
+def _pg(group):
+    """The torch.distributed group behind `group` (a ProcessGroup or a sharded.PeerExchange)."""
+    return group.group if _is_peer(group) else group
+
+
+def _stats_to_logp(hidden, weight, targets, v_offset, logits_out, group):
+    """K1 on this rank's vocab slice + the cross-rank merge -> (logp, lse) over the full vocabulary."""
+    if _is_peer(group):
+        T = hidden.shape[0]
+        if T > group.cap:
+            raise ValueError("PeerExchange capacity %d < %d tokens" % (group.cap, T))
+        slot = group.next_slot()
+        # the kernel writes rows of length T; the peer buffer has row stride cap: stage through a [3, T]
+        # view only when T == cap, else write compactly and let merge use row_stride = cap
+        buf = group.local_stats(slot)
+        if T == group.cap:
+            lmhead_stats(hidden, weight, targets, v_offset, logits_out, stats_out=buf)
+        else:
+            st = lmhead_stats(hidden, weight, targets, v_offset, logits_out)
+            buf[:, :T].copy_(st)
+        return group.merge(slot, T)
+    stats = lmhead_stats(hidden, weight, targets, v_offset, logits_out)
+    return merge_stats(_gather_stats(stats, group))
 
 
 def _gather_stats(stats, group):
@@ -118,8 +148,7 @@ class _FusedLogprobFn(torch.autograd.Function):
         need_grad = hidden.requires_grad or weight.requires_grad
         keep = need_grad and (T * V * 2 <= SAVE_LOGITS_BYTES)
         logits = torch.empty(T, V, dtype=torch.bfloat16, device=hidden.device) if keep else None
-        stats = lmhead_stats(hidden, weight, targets, v_offset, logits)
-        logp, lse = merge_stats(_gather_stats(stats, group))
+        logp, lse = _stats_to_logp(hidden, weight, targets, v_offset, logits, group)
         ctx.save_for_backward(hidden, weight, targets, lse)
         ctx.logits, ctx.v_offset, ctx.group, ctx.chunk_tokens = logits, v_offset, group, chunk_tokens
         ctx.mark_non_differentiable(lse)
@@ -150,7 +179,7 @@ class _FusedLogprobFn(torch.autograd.Function):
         ctx.logits = None
         if ctx.group is not None:                   # partial sums over vocab slices
             import torch.distributed as dist
-            dist.all_reduce(d_hidden, group=ctx.group)
+            dist.all_reduce(d_hidden, group=_pg(ctx.group))
         return d_hidden, d_weight.to(weight.dtype), None, None, None, None
 
 
@@ -237,8 +266,7 @@ def fused_logprob_gspo(hidden: torch.Tensor, weight: torch.Tensor, completion_id
         n1 = min(N, n0 + seqs)
         s, e = n0 * Tc, n1 * Tc
         z = zbuf[: e - s] if need_grad else None
-        stats = lmhead_stats(hidden2[s:e], weight, targets[s:e], v_offset, z)
-        lp, lse = merge_stats(_gather_stats(stats, group))
+        lp, lse = _stats_to_logp(hidden2[s:e], weight, targets[s:e], v_offset, z, group)
         logp[n0:n1] = lp.view(n1 - n0, Tc)
         state, g, _ = gspo_raw(logp[n0:n1], ref[n0:n1], mask[n0:n1], rpf, num_generations, beta, epsilon_low,
                                epsilon_high, gspo, None if old is None else old[n0:n1], want_grad=need_grad,
@@ -249,7 +277,7 @@ def fused_logprob_gspo(hidden: torch.Tensor, weight: torch.Tensor, completion_id
             bwd_dweight(z, hidden2[s:e], d_weight, accumulate=(ci > 0) or (d_weight_out is not None))
     if need_grad and group is not None:
         import torch.distributed as dist
-        dist.all_reduce(d_hidden, group=group)
+        dist.all_reduce(d_hidden, group=_pg(group))
     return dict(loss=state["loss"].reshape(()), per_token_logps=logp, advantages=state["adv"],
                 mean_kl=state["mean_kl"].reshape(()), completion_length=state["clen"], reward_std=state["rstd"],
                 d_hidden=None if d_hidden is None else d_hidden.view(N, Tc, H), d_weight=d_weight)

@@ -36,6 +36,16 @@ def main():
     lp2 = logprob.fused_logprob(h2, w_local, ids.view(-1), v_offset=v0, group=dist.group.WORLD)
     lp2.sum().backward()
     torch.cuda.synchronize()
+    # fused peer-memory exchange (symmetric memory + merge kernel reading every rank over NVLink)
+    peer_err = 0.0
+    ex = sharded.PeerExchange(dist.group.WORLD, capacity_tokens=2 * Tc)
+    outp = logprob.fused_logprob_gspo(h, w_local, ids, *args, v_offset=v0, group=ex, chunk_tokens=2 * Tc)
+    lp3 = logprob.fused_logprob(h.view(-1, H)[: Tc + 7], w_local, ids.view(-1)[: Tc + 7], v_offset=v0, group=ex)   # T < capacity
+    lp4 = logprob.fused_logprob(h.view(-1, H)[: Tc + 7], w_local, ids.view(-1)[: Tc + 7], v_offset=v0, group=dist.group.WORLD)
+    torch.cuda.synchronize()
+    peer_err = max((outp["per_token_logps"] - out["per_token_logps"]).abs().max().item(),
+                   (outp["d_hidden"].float() - out["d_hidden"].float()).abs().max().item(),
+                   abs(outp["loss"].item() - out["loss"].item()), (lp3 - lp4).abs().max().item())
     ok = True
     if rank == 0:
         one = logprob.fused_logprob_gspo(h, w, ids, *args, chunk_tokens=2 * Tc)
@@ -47,12 +57,14 @@ def main():
         h3 = h.view(-1, H).clone().requires_grad_(True)
         logprob.fused_logprob(h3, w, ids.view(-1)).sum().backward()
         e_ag = ((h2.grad.float() - h3.grad.float()).norm() / h3.grad.float().norm()).item()
-        print("multi-gpu world=%d: dlogp %.2e dloss %.2e dH %.2e dW %.2e autograd-dH %.2e" %
-              (world, e_lp, e_loss, e_dh, e_dw, e_ag), flush=True)
+        print("multi-gpu world=%d: dlogp %.2e dloss %.2e dH %.2e dW %.2e autograd-dH %.2e peer-vs-nccl %.2e" %
+              (world, e_lp, e_loss, e_dh, e_dw, e_ag, peer_err), flush=True)
         # log-probs: same fp32 arithmetic, different summation tree; dH: bf16 partial sums per slice
-        ok = e_lp < 5e-5 and e_loss < 1e-6 and e_dh < 1e-2 and e_dw < 1e-3 and e_ag < 1e-2
+        ok = e_lp < 5e-5 and e_loss < 1e-6 and e_dh < 1e-2 and e_dw < 1e-3 and e_ag < 1e-2 and peer_err == 0.0
+    if peer_err != 0.0:
+        ok = False                      # same arithmetic in the same rank order: must be bit-identical
     flag = torch.tensor([1 if ok else 0], device=dev)
-    dist.broadcast(flag, 0)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) == 1 else 1)
 
