@@ -183,7 +183,7 @@ def run_ours(args):
     _, mask = gspo.eos_mask(ids, eos_id)
     weight, v_off = sharded.shard_weight(w_full, rank, world)
     if world > 1 and args.exchange == "peer":
-        group = sharded.PeerExchange(dist.group.WORLD, capacity_tokens=T)
+        group = sharded.PeerExchange(dist.group.WORLD, capacity_tokens=T, hidden_size=H if args.overlap_allreduce else 0)
     if not args.chunk_tokens:
         per_seq = max(1, min(N, logprob.auto_chunk_tokens(weight.shape[0]) // Tc))
         args.chunk_tokens = -(-N // (-(-N // per_seq))) * Tc      # evened out over whole sequences
@@ -352,6 +352,8 @@ def main():
     ap.add_argument("--fwd-groups", type=int, default=0)
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: forward exchange of the softmax triples (peer = fused NVLink merge kernel)")
+    ap.add_argument("--overlap-allreduce", type=int, default=1,
+                    help="N > 1 with --exchange peer: one-shot P2P all-reduce of dHidden beside the dW GEMM (0 = NCCL)")
     ap.add_argument("--tunable", action="append", default=[], help="name=value for o3v_set_tunable (diagnostics)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

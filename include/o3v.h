@@ -101,6 +101,17 @@ int o3v_lmhead_merge_stats(const float* parts, int64_t P, int64_t T,
 int o3v_lmhead_merge_stats_peers(const float* const* part_ptrs, int64_t P, int64_t row_stride, int64_t T,
                                  float* logp, float* lse, void* stream);
 
+/* One-shot all-reduce (sum) of a bf16 buffer replicated in peer-mapped memory: bufs[p] (HOST array of
+ * P <= 16 device pointers) is rank p's copy.  Rank `rank` owns the 1/P slice of 16-byte vectors:
+ * it loads that slice from every peer over NVLink, adds in fp32 in rank order (deterministic,
+ * identical on all ranks) and stores the bf16 result into every peer's buffer.  The kernel uses no
+ * shared memory and few registers so that its `num_ctas` CTAs co-reside with the persistent GEMM
+ * CTAs: it is meant to run on a side stream while K2b computes.  The caller brackets it with
+ * cross-rank barriers (all partial sums written before, all results visible after).
+ * n_elems % 8 == 0. */
+int o3v_allreduce_bf16_peers(void* const* bufs, int64_t P, int64_t rank, int64_t n_elems, int32_t num_ctas,
+                             void* stream);
+
 /* ------------------------------------------------------------------------------------
  * K2  chunked fused backward of K1 (replaces the autograd backward of
  * grpo_trainer.py:375-383: softmax-backward + two GEMMs).

@@ -189,6 +189,40 @@ __global__ void merge_stats_peers_kernel(const PeerPtrs ptrs, int P, int64_t row
   if (logp) logp[t] = z - l;
 }
 
+// One-shot P2P all-reduce of bf16 partial sums (dHidden of the vocab-parallel path).
+struct PeerBufs { uint4* p[16]; };
+constexpr int kArThreads = 256;
+// <= 64 registers x 256 threads and no shared memory: fits beside a persistent GEMM CTA on the same SM
+__global__ void __launch_bounds__(kArThreads, 4)
+allreduce_bf16_peers_kernel(const PeerBufs bufs, int P, int64_t v0, int64_t v1) {
+  // this rank's slice of 16-byte vectors [v0, v1), grid-stride; peers are read four at a time
+  const int64_t stride = (int64_t)gridDim.x * kArThreads;
+  for (int64_t i = v0 + (int64_t)blockIdx.x * kArThreads + threadIdx.x; i < v1; i += stride) {
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int p0 = 0; p0 < P; p0 += 4) {
+      uint4 a[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (p0 + j < P) a[j] = __ldcv(bufs.p[p0 + j] + i);   // four NVLink loads in flight
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (p0 + j < P) {                                    // fixed rank order: identical result everywhere
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a[j]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 f = __bfloat1622float2(h[k]);
+            s[2 * k] += f.x; s[2 * k + 1] += f.y;
+          }
+        }
+    }
+    uint4 r;
+    __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = __floats2bfloat162_rn(s[2 * k], s[2 * k + 1]);
+    for (int p = 0; p < P; ++p) bufs.p[p][i] = r;
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // dlogits: P[t,v] = g[t] * ([v + v_offset == target[t]] - exp(z[t,v] - lse[t])), in place, bf16
 // ------------------------------------------------------------------------------------
@@ -309,6 +343,27 @@ extern "C" int o3v_lmhead_merge_stats_peers(const float* const* part_ptrs, int64
     ptrs.p[i] = part_ptrs[i];
   }
   merge_stats_peers_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, (cudaStream_t)stream>>>(ptrs, (int)P, row_stride, T, logp, lse);
+  O3V_LAUNCH_CHECK();
+  return O3V_OK;
+}
+
+extern "C" int o3v_allreduce_bf16_peers(void* const* bufs, int64_t P, int64_t rank, int64_t n_elems, int32_t num_ctas,
+                                        void* stream) {
+  if (!bufs || P <= 0 || P > 16 || rank < 0 || rank >= P || n_elems < 0 || (n_elems % 8) != 0) return O3V_ERR_INVALID_ARG;
+  int rc = check_device();
+  if (rc) return rc;
+  if (n_elems == 0 || P == 1) return O3V_OK;
+  PeerBufs pb = {};
+  for (int64_t i = 0; i < P; ++i) {
+    if (!bufs[i] || (reinterpret_cast<uintptr_t>(bufs[i]) & 15u)) return O3V_ERR_ALIGNMENT;
+    pb.p[i] = reinterpret_cast<uint4*>(bufs[i]);
+  }
+  const int64_t nvec = n_elems / 8;
+  const int64_t v0 = rank * nvec / P, v1 = (rank + 1) * nvec / P;
+  if (v1 <= v0) return O3V_OK;
+  int ctas = num_ctas > 0 ? num_ctas : 2 * num_sms();
+  ctas = (int)std::min<int64_t>(ctas, ceil_div(v1 - v0, kArThreads));
+  allreduce_bf16_peers_kernel<<<ctas, kArThreads, 0, (cudaStream_t)stream>>>(pb, (int)P, v0, v1);
   O3V_LAUNCH_CHECK();
   return O3V_OK;
 }

@@ -257,7 +257,13 @@ def fused_logprob_gspo(hidden: torch.Tensor, weight: torch.Tensor, completion_id
     seqs = -(-N // n_chunks)                                  # even out the chunks
     logp = torch.empty(N, Tc, dtype=torch.float32, device=dev)
     zbuf = torch.empty(seqs * Tc, V, dtype=torch.bfloat16, device=dev) if need_grad else None
-    d_hidden = torch.empty(N * Tc, H, dtype=torch.bfloat16, device=dev) if need_grad else None
+    d_hidden = None
+    peer_dh = False
+    if need_grad:
+        d_hidden = group.dh_view(N * Tc, H) if _is_peer(group) else None      # peer-mapped: overlapped all-reduce
+        peer_dh = d_hidden is not None
+        if d_hidden is None:
+            d_hidden = torch.empty(N * Tc, H, dtype=torch.bfloat16, device=dev)
     d_weight = None
     if need_grad:
         d_weight = d_weight_out if d_weight_out is not None else torch.empty(V, H, dtype=torch.float32, device=dev)
@@ -274,8 +280,12 @@ def fused_logprob_gspo(hidden: torch.Tensor, weight: torch.Tensor, completion_id
         if need_grad:
             dlogits_(z, lse, g.view(-1), targets[s:e], v_offset)
             bwd_dhidden(z, weight, out=d_hidden[s:e])
+            if peer_dh:
+                group.allreduce_dh_async(s, e - s)            # runs beside the dW GEMM below
             bwd_dweight(z, hidden2[s:e], d_weight, accumulate=(ci > 0) or (d_weight_out is not None))
-    if need_grad and group is not None:
+    if need_grad and peer_dh:
+        group.wait_allreduce()
+    elif need_grad and group is not None:
         import torch.distributed as dist
         dist.all_reduce(d_hidden, group=_pg(group))
     return dict(loss=state["loss"].reshape(()), per_token_logps=logp, advantages=state["adv"],

@@ -43,7 +43,11 @@ class PeerExchange:
     `.group` is the torch.distributed group used for the remaining collective (dHidden all-reduce).
     """
 
-    def __init__(self, group, capacity_tokens: int, device=None):
+    def __init__(self, group, capacity_tokens: int, hidden_size: int = 0, device=None, allreduce_ctas: int = 0):
+        """`hidden_size` > 0 also allocates a peer-mapped [capacity, hidden] bf16 dHidden buffer: the
+        partial dHidden of every token chunk is then all-reduced by `o3v_allreduce_bf16_peers` on a side
+        stream WHILE the dW GEMM of the chunk runs (the kernel has no smem and ~43 registers, so its
+        CTAs share SMs with the persistent GEMM CTAs), instead of one exposed NCCL all-reduce."""
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
@@ -58,6 +62,44 @@ class PeerExchange:
         self.rank = self.handle.rank
         self._ptrs = [int(p) for p in self.handle.buffer_ptrs]
         self._calls = 0
+        self.hidden_size = int(hidden_size)
+        self.dh = None
+        if self.hidden_size > 0:
+            self.dh = symm.empty((self.cap, self.hidden_size), dtype=torch.bfloat16, device=device)
+            self.dh_handle = symm.rendezvous(self.dh, group)
+            self._dh_ptrs = [int(p) for p in self.dh_handle.buffer_ptrs]
+            self.side = torch.cuda.Stream(device=device)
+            self.ar_ctas = int(allreduce_ctas) if allreduce_ctas else torch.cuda.get_device_properties(device).multi_processor_count
+
+    def dh_view(self, tokens: int, hidden: int):
+        """[tokens, hidden] bf16 view of the peer-mapped dHidden buffer (valid until the next step)."""
+        if self.dh is None or hidden != self.hidden_size or tokens > self.cap:
+            return None
+        return self.dh[:tokens]
+
+    def allreduce_dh_async(self, row0: int, rows: int):
+        """Sum rows [row0, row0 + rows) of every rank's dHidden buffer, on the side stream, ordered
+        after everything enqueued so far on the current stream."""
+        import ctypes
+        import torch
+        from . import _lib
+        cur = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        off = row0 * self.hidden_size * 2
+        arr = (ctypes.c_void_p * self.world)(*[p + off for p in self._dh_ptrs])
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ev)
+            self.dh_handle.barrier(channel=2)          # every rank has written its partial sums of these rows
+            with torch.cuda.device(self.dh.device):
+                _lib.call("o3v_allreduce_bf16_peers", 1, _lib.load().o3v_allreduce_bf16_peers, arr, self.world,
+                          self.rank, rows * self.hidden_size, self.ar_ctas,
+                          ctypes.c_void_p(self.side.cuda_stream))
+            self.dh_handle.barrier(channel=3)          # every rank's results have landed in every buffer
+
+    def wait_allreduce(self):
+        import torch
+        torch.cuda.current_stream().wait_stream(self.side)
 
     def next_slot(self) -> int:
         slot = self._calls & 1
