@@ -85,12 +85,14 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
                        cudaStream_t st) {
   using S = GemmShape<kNCta, kEpi == EPI_STATS, kAcc>;
   auto kern = lmhead_gemm_kernel<kAMN, kBMN, kNCta, kEpi, kAcc>;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES);
-  });
-  if (attr_err != cudaSuccess) return (int)attr_err;
+  // the opt-in shared-memory size is a per-device (per-context) function attribute
+  static std::atomic<bool> attr_set[64];
+  int dev = 0;
+  O3V_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_acquire)) {
+    O3V_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES));
+    if (dev >= 0 && dev < 64) attr_set[dev].store(true, std::memory_order_release);
+  }
   int sms = num_sms();
   if (g_max_ctas > 0 && g_max_ctas < sms) sms = g_max_ctas;
   const int64_t items = (int64_t)p.num_m_blocks * p.num_n_groups;

@@ -226,7 +226,10 @@ def grounded_rewards(completions, **kwargs) -> np.ndarray:
     contents = [c[0]["content"] for c in completions]
     task = kwargs["task"][0]                                   # the reference reads element 0 for the batch
     step = kwargs["step_percent"][0] if "step_percent" in kwargs else 0.0
-    key = (tuple(contents), task, step, id(kwargs.get("answer")), id(kwargs.get("key_frames")))
+    # the trainer calls every reward callable with the same batch (grpo_trainer.py:646-656): compute the
+    # five columns once per batch.  The key holds the VALUES that reach the kernel, not object identities.
+    key = (tuple(contents), task, step, repr(kwargs.get("answer")), repr(kwargs.get("key_frames")),
+           repr(kwargs.get("key_items")), repr(kwargs.get("image_size")), repr(kwargs.get("image_size_refine")))
     if _cache["key"] == key:
         return _cache["val"]
     get = lambda name, i: (kwargs[name][i] if name in kwargs and kwargs[name] is not None else None)
