@@ -252,6 +252,51 @@ typedef struct o3v_vstar_soa {
 
 int o3v_vstar_scores(const o3v_vstar_soa* soa, double* out, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * K6  completion text -> the per-rollout arrays of o3v_rewards_soa (SURVEY.md 8f rank 1:
+ * the step before K4).  Replaces, bit for bit, the regex / json / float() extraction of
+ * reward_func.py: the <think> / <answer> spans (:91-93, :394, :437, :481-482), the answer's
+ * "<t>a</t>s to <t>b</t>s" (:119-126, temporal tasks), the answer's first <box> (:211-223,
+ * visual QA), every "<t>x</t>s" of <think> (:405-412, :447-449), the <box>es of <think>
+ * (:492-511, visual QA) and parse_temporal_spatial_reasoning_process (:308-335, other tasks).
+ *
+ *   text     UTF-8 bytes of the R completions back to back, 16-byte aligned; the allocation
+ *            must be readable up to the next multiple of 16 bytes past offsets[R]
+ *   offsets  [R + 1] int64 byte offsets (offsets[0] = 0 is not required)
+ *   task     [Q = R / G] O3V_TASK_* of each prompt (kwargs['task'][0] of its batch)
+ *   P, C, Bc, Tb  capacities of the output rows (as in o3v_rewards_soa).  Counts are always the
+ *            TRUE counts; entries beyond a capacity are dropped and overflow[i] reports the
+ *            largest count that did not fit (0 = everything fitted; the caller re-runs with
+ *            larger rows).  overflow = (think times, claims, boxes per claim, think boxes).
+ *   outputs  rows are written only up to the counts (no zero fill).
+ * workspace: o3v_parse_workspace_bytes() bytes, 8-byte aligned (work ticket).
+ * ---------------------------------------------------------------------------------- */
+typedef struct o3v_parse_args {
+  int64_t R;
+  int64_t G;
+  int32_t P, C, Bc, Tb;
+  const uint8_t* text;
+  const int64_t* offsets;
+  const int32_t* task;
+  int32_t* flags;        /* [R] */
+  double* ans_seg;       /* [R, 2] */
+  double* ans_box;       /* [R, 4] */
+  int32_t* n_times;      /* [R] */
+  double* think_times;   /* [R, P] */
+  int32_t* n_claims;     /* [R] */
+  double* claim_t;       /* [R, C] */
+  int32_t* claim_nbox;   /* [R, C] */
+  uint32_t* claim_valid; /* [R, C] */
+  double* claim_box;     /* [R, C, Bc, 4] */
+  int32_t* n_tboxes;     /* [R] */
+  uint32_t* tbox_valid;  /* [R] */
+  double* think_box;     /* [R, Tb, 4] */
+  int32_t* overflow;     /* [4] */
+} o3v_parse_args;
+
+size_t o3v_parse_workspace_bytes(void);
+int o3v_parse_completions(const o3v_parse_args* args, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

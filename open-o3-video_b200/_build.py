@@ -7,7 +7,7 @@ import subprocess
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "lib", "libo3v.so")
-SOURCES = ["api.cu", "gspo.cu", "rewards.cu", "vstar.cu", "lmhead.cu"]
+SOURCES = ["api.cu", "gspo.cu", "rewards.cu", "vstar.cu", "parse.cu", "lmhead.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -29,6 +29,15 @@ class VstarSoA(ctypes.Structure):
         "t_valid", "gt_seg", "pred_seg", "sp_valid", "n_frames", "gt_box", "n_pb", "pb_valid", "pb")]
 
 
+class ParseArgs(ctypes.Structure):
+    """struct o3v_parse_args (include/o3v.h)."""
+    _fields_ = [("R", c_int64), ("G", c_int64),
+                ("P", c_int32), ("C", c_int32), ("Bc", c_int32), ("Tb", c_int32)] + [(n, c_void_p) for n in (
+                    "text", "offsets", "task", "flags", "ans_seg", "ans_box", "n_times", "think_times", "n_claims",
+                    "claim_t", "claim_nbox", "claim_valid", "claim_box", "n_tboxes", "tbox_valid", "think_box",
+                    "overflow")]
+
+
 # name -> (restype, argtypes); must list EVERY function include/o3v.h declares
 SIGNATURES = {
     "o3v_version": (c_int, []),
@@ -58,6 +67,8 @@ SIGNATURES = {
                                  c_void_p, c_size_t, c_void_p]),
     "o3v_grounded_rewards": (c_int, [ctypes.POINTER(RewardsSoA), c_void_p, c_void_p]),
     "o3v_vstar_scores": (c_int, [ctypes.POINTER(VstarSoA), c_void_p, c_void_p]),
+    "o3v_parse_workspace_bytes": (c_size_t, []),
+    "o3v_parse_completions": (c_int, [ctypes.POINTER(ParseArgs), c_void_p, c_size_t, c_void_p]),
 }
 
 _lib = None

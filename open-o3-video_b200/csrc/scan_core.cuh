@@ -1,0 +1,910 @@
+// K6 core: byte-level scanner that turns completion text into the rollout side of
+// o3v_rewards_soa (the step before K4).
+//
+// Replaces, bit for bit, the regex / json / float() extraction of the reference's
+// src/r1-v/src/open_r1/reward_func.py:
+//   :91-93, :189 extract_answer      :119 / :149  answer "<t>a</t>s to <t>b</t>s"
+//   :211-223     answer <box>        :308-335     parse_temporal_spatial_reasoning_process
+//   :394, :437, :481-482 think/answer spans      :405-412, :447-449 think "<t>x</t>s"
+//   :492-511     visual-QA think boxes
+//
+// The reference's patterns are lazy-quantifier regexes over literal tags.  Each of them reduces to
+// an ordered sequence of "first occurrence of literal X at or after p" searches (derivation in
+// DESIGN.md section 8); numbers go through an exactly rounded decimal -> binary64 conversion (what
+// Python's float() and json.loads produce) and box payloads through a JSON recogniser that accepts
+// what CPython's C scanner accepts.
+//
+// Everything here is `O3V_HD` (host + device).  The device build runs one WARP per rollout:
+// literal searches are warp-cooperative (16 bytes per lane, 512 bytes per step); the short
+// sequential pieces (number tokens, box payloads) are executed redundantly by all lanes on
+// broadcast loads, and lane 0 stores.  The host build of this same header exists only so that
+// tests can fuzz the logic against Python on the CPU box (tests/hostbuild/); the product path is
+// the kernel in parse.cu.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define O3V_HD __host__ __device__ __forceinline__
+#define O3V_HD_NOINLINE __host__ __device__ __noinline__
+#define O3V_TABLE static __device__ const
+#define O3V_CONSTEXPR __host__ __device__ constexpr
+#else
+#define O3V_CONSTEXPR constexpr
+#define O3V_HD inline
+#define O3V_HD_NOINLINE inline
+#endif
+
+namespace o3v {
+namespace scan {
+
+// ------------------------------------------------------------------------------------------
+// Tables.  Unicode 15.0 decimal digits (category Nd; what Python 3.12's `\d` and float() accept):
+// first code point of every run of ten, value = (cp - start) % 10 (generated and checked by
+// tools/gen_unicode_tables.py).  The mathematical digits U+1D7CE..1D7FF are five runs of ten.
+// ------------------------------------------------------------------------------------------
+#define O3V_ND_STARTS                                                                                        \
+  {0x0660, 0x06F0, 0x07C0, 0x0966, 0x09E6, 0x0A66, 0x0AE6, 0x0B66, 0x0BE6, 0x0C66, 0x0CE6, 0x0D66, 0x0DE6,   \
+   0x0E50, 0x0ED0, 0x0F20, 0x1040, 0x1090, 0x17E0, 0x1810, 0x1946, 0x19D0, 0x1A80, 0x1A90, 0x1B50, 0x1BB0,   \
+   0x1C40, 0x1C50, 0xA620, 0xA8D0, 0xA900, 0xA9D0, 0xA9F0, 0xAA50, 0xABF0, 0xFF10, 0x104A0, 0x10D30,         \
+   0x11066, 0x110F0, 0x11136, 0x111D0, 0x112F0, 0x11450, 0x114D0, 0x11650, 0x116C0, 0x11730, 0x118E0,        \
+   0x11950, 0x11C50, 0x11D50, 0x11DA0, 0x11F50, 0x16A60, 0x16AC0, 0x16B50, 0x1D7CE, 0x1D7D8, 0x1D7E2,        \
+   0x1D7EC, 0x1D7F6, 0x1E140, 0x1E2F0, 0x1E4F0, 0x1E950, 0x1FBF0}
+constexpr int kNdRuns = 67;
+#define O3V_POW10                                                                                            \
+  {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18,   \
+   1e19, 1e20, 1e21, 1e22}
+
+static const uint32_t kNdStartsHost[kNdRuns] = O3V_ND_STARTS;
+static const double kPow10Host[23] = O3V_POW10;
+#if defined(__CUDACC__)
+O3V_TABLE uint32_t kNdStartsDev[kNdRuns] = O3V_ND_STARTS;
+O3V_TABLE double kPow10Dev[23] = O3V_POW10;
+#endif
+
+O3V_HD const uint32_t* nd_starts() {
+#if defined(__CUDA_ARCH__)
+  return kNdStartsDev;
+#else
+  return kNdStartsHost;
+#endif
+}
+O3V_HD double pow10_exact(int e) {
+#if defined(__CUDA_ARCH__)
+  return kPow10Dev[e];
+#else
+  return kPow10Host[e];
+#endif
+}
+
+// ------------------------------------------------------------------------------------------
+// Literals, packed at compile time (no memory traffic for the needle).
+// ------------------------------------------------------------------------------------------
+struct Lit {
+  uint64_t lo, hi;
+  int n;
+};
+template <int N>
+O3V_CONSTEXPR Lit make_lit(const char (&s)[N]) {
+  Lit l{0, 0, N - 1};
+  for (int i = 0; i < N - 1; ++i) {
+    if (i < 8) l.lo |= (uint64_t)(uint8_t)s[i] << (8 * i);
+    else l.hi |= (uint64_t)(uint8_t)s[i] << (8 * (i - 8));
+  }
+  return l;
+}
+O3V_HD uint8_t lit_byte(const Lit& l, int i) { return (uint8_t)((i < 8 ? l.lo >> (8 * i) : l.hi >> (8 * (i - 8))) & 0xff); }
+
+// t[p .. p+n) == literal, with p + n <= end
+O3V_HD bool lit_at(const uint8_t* t, int64_t p, int64_t end, const Lit& l) {
+  if (p < 0 || p + l.n > end) return false;
+  for (int i = 0; i < l.n; ++i)
+    if (t[p + i] != lit_byte(l, i)) return false;
+  return true;
+}
+
+// First p in [from, end - n] with t[p .. p+n) == literal, else -1.
+// Device: called by all 32 lanes of a warp with identical arguments; `t` is the 16-byte aligned
+// base of the whole text buffer (positions are absolute), padded to a multiple of 16 bytes.
+O3V_HD int64_t find_lit(const uint8_t* t, int64_t from, int64_t end, const Lit& l) {
+  const int64_t last = end - l.n;
+  if (from < 0) return -1;
+  if (from > last) return -1;
+#if defined(__CUDA_ARCH__)
+  const int lane = threadIdx.x & 31;
+  const uint32_t c0 = (uint32_t)(l.lo & 0xff) * 0x01010101u;
+  for (int64_t base = from & ~(int64_t)15; base <= last; base += 512) {
+    const int64_t p0 = base + lane * 16;
+    uint32_t best = 0xffffffffu;
+    if (p0 <= last) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(t + p0));
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      uint32_t m = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t eq = __vcmpeq4(w[i], c0);   // 0xff per equal byte
+        m |= (((eq >> 7) & 1u) | ((eq >> 14) & 2u) | ((eq >> 21) & 4u) | ((eq >> 28) & 8u)) << (4 * i);
+      }
+      while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        const int64_t p = p0 + j;
+        if (p >= from && p <= last && lit_at(t, p, end, l)) { best = (uint32_t)(p - base); break; }
+      }
+    }
+    best = __reduce_min_sync(0xffffffffu, best);
+    if (best != 0xffffffffu) return base + best;
+  }
+  return -1;
+#else
+  const uint8_t c0 = lit_byte(l, 0);
+  for (int64_t p = from; p <= last; ++p)
+    if (t[p] == c0 && lit_at(t, p, end, l)) return p;
+  return -1;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------
+// UTF-8 helpers.  The text is Python str encoded as UTF-8 (well formed); malformed bytes are
+// treated as single opaque characters.
+// ------------------------------------------------------------------------------------------
+O3V_HD uint32_t decode_utf8(const uint8_t* t, int64_t p, int64_t end, int* len) {
+  const uint32_t b0 = t[p];
+  if (b0 < 0x80) { *len = 1; return b0; }
+  if (b0 >= 0xC2 && b0 <= 0xDF && p + 1 < end) { *len = 2; return ((b0 & 0x1F) << 6) | (t[p + 1] & 0x3F); }
+  if (b0 >= 0xE0 && b0 <= 0xEF && p + 2 < end) {
+    *len = 3;
+    return ((b0 & 0x0F) << 12) | ((uint32_t)(t[p + 1] & 0x3F) << 6) | (t[p + 2] & 0x3F);
+  }
+  if (b0 >= 0xF0 && b0 <= 0xF4 && p + 3 < end) {
+    *len = 4;
+    return ((b0 & 0x07) << 18) | ((uint32_t)(t[p + 1] & 0x3F) << 12) | ((uint32_t)(t[p + 2] & 0x3F) << 6) |
+           (t[p + 3] & 0x3F);
+  }
+  *len = 1;
+  return 0xFFFFFFFFu;
+}
+
+// Unicode decimal digit at p: value 0..9 and its byte length, else -1.
+O3V_HD int digit_at(const uint8_t* t, int64_t p, int64_t end, int* len) {
+  if (p >= end) return -1;
+  const uint8_t b = t[p];
+  if (b < 0x80) {
+    *len = 1;
+    return (b >= '0' && b <= '9') ? (int)(b - '0') : -1;
+  }
+  const uint32_t cp = decode_utf8(t, p, end, len);
+  const uint32_t* starts = nd_starts();
+  for (int i = 0; i < kNdRuns; ++i)
+    if (cp - starts[i] < 10u) return (int)(cp - starts[i]);
+  return -1;
+}
+
+// str.isspace() set (what re's \s and str.strip() treat as whitespace).  float() itself strips the
+// same set minus the separators U+001C..U+001F (`strict` = false).
+O3V_HD bool is_space_cp(uint32_t cp, bool strip_mode) {
+  if (cp >= 0x1C && cp <= 0x1F) return strip_mode;
+  return (cp >= 0x09 && cp <= 0x0D) || cp == 0x20 || cp == 0x85 || cp == 0xA0 || cp == 0x1680 ||
+         (cp >= 0x2000 && cp <= 0x200A) || cp == 0x2028 || cp == 0x2029 || cp == 0x202F || cp == 0x205F ||
+         cp == 0x3000;
+}
+// [s, e) -> stripped of leading / trailing Unicode whitespace (strip_mode: str.strip(), else float()'s own)
+O3V_HD void strip_space(const uint8_t* t, int64_t* s, int64_t* e, bool strip_mode) {
+  int64_t a = *s, b = *e;
+  while (a < b) {
+    int len;
+    const uint32_t cp = decode_utf8(t, a, b, &len);
+    if (!is_space_cp(cp, strip_mode)) break;
+    a += len;
+  }
+  while (b > a) {
+    int64_t q = b - 1;                       // start of the last character
+    while (q > a && (t[q] & 0xC0) == 0x80 && b - q < 4) --q;
+    int len;
+    const uint32_t cp = decode_utf8(t, q, b, &len);
+    if (q + len != b || !is_space_cp(cp, strip_mode)) break;
+    b = q;
+  }
+  *s = a;
+  *e = b;
+}
+
+// ------------------------------------------------------------------------------------------
+// Exact decimal -> binary64.
+//
+// A number is handed over as a mantissa range of the text (digits of any Nd script, at most one
+// '.', '_' separators; the caller has validated the grammar) plus an explicit power of ten.
+// Fast path (Clinger): <= 19 significant digits, integer < 2^53, |exponent| <= 22 -> one exact
+// multiply or divide.  Everything else goes through a big decimal (800 digits + sticky flag,
+// enough for any binary64 rounding decision) that is scaled by powers of two until it lies in
+// [1/2, 1), then 53 bits are extracted and rounded half-even.
+// ------------------------------------------------------------------------------------------
+constexpr int kBigDigits = 800;
+struct BigDec {
+  uint8_t d[kBigDigits];
+  int nd;       // digits in use
+  int64_t dp;   // value = 0.d0 d1 ... x 10^dp
+  bool sticky;  // non-zero digits were dropped below d[nd-1]
+};
+
+O3V_HD void big_trim(BigDec& b) {
+  while (b.nd > 0 && b.d[b.nd - 1] == 0) --b.nd;
+  if (b.nd == 0) b.dp = 0;
+}
+
+// b /= 2^k, 1 <= k <= 60
+O3V_HD void big_shr(BigDec& b, int k) {
+  int r = 0, w = 0;
+  uint64_t n = 0;
+  while ((n >> k) == 0) {
+    if (r >= b.nd) {
+      if (n == 0) { b.nd = 0; b.dp = 0; return; }
+      while ((n >> k) == 0) { n *= 10; ++r; }
+      break;
+    }
+    n = n * 10 + b.d[r++];
+  }
+  b.dp -= r - 1;
+  const uint64_t mask = ((uint64_t)1 << k) - 1;
+  for (; r < b.nd; ++r) {
+    const uint64_t dig = n >> k;
+    n &= mask;
+    b.d[w++] = (uint8_t)dig;
+    n = n * 10 + b.d[r];
+  }
+  while (n > 0) {
+    const uint64_t dig = n >> k;
+    n &= mask;
+    if (w < kBigDigits) b.d[w++] = (uint8_t)dig;
+    else if (dig > 0) b.sticky = true;
+    n *= 10;
+  }
+  b.nd = w;
+  big_trim(b);
+}
+
+// b *= 2^k, 1 <= k <= 60
+O3V_HD void big_shl(BigDec& b, int k) {
+  if (b.nd == 0) return;
+  const int delta = (k * 30103) / 100000 + 1;   // >= number of new leading digits
+  int w = b.nd + delta - 1;
+  uint64_t n = 0;
+  for (int r = b.nd - 1; r >= 0; --r, --w) {
+    n += (uint64_t)b.d[r] << k;
+    const uint64_t q = n / 10, rem = n - 10 * q;
+    if (w < kBigDigits) b.d[w] = (uint8_t)rem;
+    else if (rem) b.sticky = true;
+    n = q;
+  }
+  for (; n > 0; --w) {
+    const uint64_t q = n / 10, rem = n - 10 * q;
+    if (w < kBigDigits) b.d[w] = (uint8_t)rem;
+    else if (rem) b.sticky = true;
+    n = q;
+  }
+  const int lead = w + 1;                       // unused positions in front
+  int nd = b.nd + delta - lead;
+  if (nd > kBigDigits - lead) nd = kBigDigits - lead;
+  if (lead > 0)
+    for (int i = 0; i < nd; ++i) b.d[i] = b.d[i + lead];
+  b.nd = nd;
+  b.dp += delta - lead;
+  big_trim(b);
+}
+
+O3V_HD void big_shift(BigDec& b, int k) {   // k > 0: multiply by 2^k, k < 0: divide
+  while (k > 60) { big_shl(b, 60); k -= 60; }
+  while (k < -60) { big_shr(b, 60); k += 60; }
+  if (k > 0) big_shl(b, k);
+  else if (k < 0) big_shr(b, -k);
+}
+
+// integer part of b (dp <= 18) rounded half-even on the dropped digits (+ sticky)
+O3V_HD uint64_t big_rounded_integer(const BigDec& b) {
+  uint64_t n = 0;
+  int i = 0;
+  for (; i < b.dp && i < b.nd; ++i) n = n * 10 + b.d[i];
+  for (; i < b.dp; ++i) n *= 10;
+  bool up = false;
+  if (b.dp >= 0 && b.dp < b.nd) {
+    const int idx = (int)b.dp;
+    if (b.d[idx] == 5 && idx + 1 == b.nd) up = b.sticky || (idx > 0 && (b.d[idx - 1] & 1));   // exactly half: even
+    else up = b.d[idx] >= 5;
+  }
+  return n + (up ? 1 : 0);
+}
+
+O3V_HD double bits_to_double(uint64_t bits) {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double((long long)bits);
+#else
+  union { uint64_t u; double d; } c;
+  c.u = bits;
+  return c.d;
+#endif
+}
+
+// Slow path: rebuild the digits from the text.  Kept out of line: it needs an 800-byte frame.
+O3V_HD_NOINLINE double big_to_double(const uint8_t* t, int64_t ms, int64_t me, int64_t exp10) {
+  BigDec b;
+  b.nd = 0; b.dp = 0; b.sticky = false;
+  int64_t int_digits = 0, lead_zeros = 0;
+  bool seen_point = false, seen_nonzero = false;
+  for (int64_t p = ms; p < me;) {
+    const uint8_t c = t[p];
+    if (c == '.') { seen_point = true; ++p; continue; }
+    if (c == '_') { ++p; continue; }
+    int len = 1;
+    const int v = digit_at(t, p, me, &len);
+    p += len;
+    if (v < 0) continue;                     // not reachable for validated input
+    if (!seen_point) ++int_digits;
+    if (!seen_nonzero) {
+      if (v == 0) { ++lead_zeros; continue; }
+      seen_nonzero = true;
+    }
+    if (b.nd < kBigDigits) b.d[b.nd++] = (uint8_t)v;
+    else if (v) b.sticky = true;
+  }
+  if (b.nd == 0) return 0.0;
+  b.dp = int_digits - lead_zeros + exp10;
+  big_trim(b);
+  if (b.dp > 310) return bits_to_double(0x7FF0000000000000ull);
+  if (b.dp < -330) return 0.0;
+  const int tab[9] = {0, 3, 6, 9, 13, 16, 19, 23, 26};
+  int exp2 = 0;
+  while (b.dp > 0) {
+    const int n = b.dp >= 9 ? 27 : tab[b.dp];
+    big_shr(b, n);
+    exp2 += n;
+  }
+  while (b.dp < 0 || (b.dp == 0 && b.d[0] < 5)) {
+    const int n = -b.dp >= 9 ? 27 : (b.dp == 0 ? 1 : tab[-b.dp]);
+    big_shl(b, n);
+    exp2 -= n;
+  }
+  exp2 -= 1;                                  // value = [1/2, 1) x 2^(exp2+1) = [1, 2) x 2^exp2
+  if (exp2 < -1022) {                         // subnormal: fewer mantissa bits
+    const int n = -1022 - exp2;
+    big_shift(b, -n);
+    exp2 += n;
+  }
+  if (exp2 > 1023) return bits_to_double(0x7FF0000000000000ull);
+  big_shift(b, 53);
+  uint64_t mant = big_rounded_integer(b);
+  if (mant == ((uint64_t)2 << 52)) {
+    mant >>= 1;
+    ++exp2;
+    if (exp2 > 1023) return bits_to_double(0x7FF0000000000000ull);
+  }
+  uint64_t biased = (uint64_t)(exp2 + 1023);
+  if ((mant & ((uint64_t)1 << 52)) == 0) biased = 0;   // subnormal (or zero)
+  return bits_to_double((mant & (((uint64_t)1 << 52) - 1)) | (biased << 52));
+}
+
+// value of mantissa text [ms, me) x 10^exp10 (unsigned), correctly rounded.
+O3V_HD double dec_to_double(const uint8_t* t, int64_t ms, int64_t me, int64_t exp10) {
+  uint64_t w = 0;
+  int nsig = 0;
+  int64_t frac_digits = 0, dropped = 0;
+  bool seen_point = false, exact = true;
+  for (int64_t p = ms; p < me;) {
+    const uint8_t c = t[p];
+    if (c == '.') { seen_point = true; ++p; continue; }
+    if (c == '_') { ++p; continue; }
+    int len = 1;
+    const int v = digit_at(t, p, me, &len);
+    p += len;
+    if (v < 0) continue;
+    if (seen_point) ++frac_digits;
+    if (nsig == 0 && v == 0) continue;        // leading zero
+    if (nsig < 19) { w = w * 10 + (uint64_t)v; ++nsig; }
+    else { ++dropped; if (v) exact = false; }
+  }
+  if (nsig == 0) return 0.0;
+  // value = w x 10^(dropped - frac_digits + exp10) when exact
+  const int64_t e = dropped - frac_digits + exp10;
+  if (exact && w < ((uint64_t)1 << 53)) {
+#if defined(__CUDA_ARCH__)
+    if (e >= 0 && e <= 22) return __dmul_rn((double)w, pow10_exact((int)e));
+    if (e < 0 && e >= -22) return __ddiv_rn((double)w, pow10_exact((int)-e));
+#else
+    if (e >= 0 && e <= 22) return (double)w * pow10_exact((int)e);
+    if (e < 0 && e >= -22) return (double)w / pow10_exact((int)-e);
+#endif
+  }
+  return big_to_double(t, ms, me, exp10);
+}
+
+// ------------------------------------------------------------------------------------------
+// Number grammars.
+// ------------------------------------------------------------------------------------------
+// `[\d.]+` at p (reward_func.py:405, :447): returns the end of the run (p if empty); *ok says
+// whether float() accepts it (>= 1 digit, <= 1 dot).
+O3V_HD int64_t scan_digits_dots(const uint8_t* t, int64_t p, int64_t end, bool* ok) {
+  int digits = 0, dots = 0;
+  while (p < end) {
+    if (t[p] == '.') { ++dots; ++p; continue; }
+    int len;
+    if (digit_at(t, p, end, &len) < 0) break;
+    ++digits;
+    p += len;
+  }
+  *ok = digits >= 1 && dots <= 1;
+  return p;
+}
+// `\d+\.?\d*` at p (reward_func.py:119): end of the match, or -1.
+O3V_HD int64_t scan_simple_decimal(const uint8_t* t, int64_t p, int64_t end) {
+  int len, n = 0;
+  while (p < end && digit_at(t, p, end, &len) >= 0) { p += len; ++n; }
+  if (n == 0) return -1;
+  if (p < end && t[p] == '.') ++p;
+  while (p < end && digit_at(t, p, end, &len) >= 0) p += len;
+  return p;
+}
+
+O3V_HD uint8_t lower_ascii(uint8_t c) { return (c >= 'A' && c <= 'Z') ? (uint8_t)(c + 32) : c; }
+O3V_HD bool word_at_ci(const uint8_t* t, int64_t p, int64_t end, const Lit& l) {
+  if (p + l.n > end) return false;
+  for (int i = 0; i < l.n; ++i)
+    if (lower_ascii(t[p + i]) != lit_byte(l, i)) return false;
+  return true;
+}
+
+// digits with optional single '_' between digits; returns end or -1 if no digit at p.
+O3V_HD int64_t scan_digitpart(const uint8_t* t, int64_t p, int64_t end, bool* any) {
+  int len;
+  *any = false;
+  if (digit_at(t, p, end, &len) < 0) return p;
+  p += len;
+  *any = true;
+  for (;;) {
+    if (p < end && t[p] == '_') {
+      if (digit_at(t, p + 1, end, &len) < 0) return -1;    // '_' must sit between two digits
+      p += 1 + len;
+      continue;
+    }
+    if (digit_at(t, p, end, &len) < 0) break;
+    p += len;
+  }
+  return p;
+}
+
+// explicit exponent digits -> saturated int64
+O3V_HD int64_t exp_value(const uint8_t* t, int64_t s, int64_t e) {
+  int64_t v = 0;
+  for (int64_t p = s; p < e;) {
+    if (t[p] == '_') { ++p; continue; }
+    int len = 1;
+    const int d = digit_at(t, p, e, &len);
+    p += len;
+    if (d < 0) continue;
+    if (v < ((int64_t)1 << 40)) v = v * 10 + d;
+  }
+  return v;
+}
+
+// Python float(str) on the (already stripped) range [s, e): reward_func.py:318.
+O3V_HD bool python_float(const uint8_t* t, int64_t s, int64_t e, double* out) {
+  constexpr Lit kInf = make_lit("inf"), kInfinity = make_lit("infinity"), kNan = make_lit("nan");
+  int64_t p = s;
+  bool neg = false;
+  if (p < e && (t[p] == '+' || t[p] == '-')) { neg = t[p] == '-'; ++p; }
+  if (p >= e) return false;
+  const uint8_t c = lower_ascii(t[p]);
+  if (c == 'i' || c == 'n') {
+    double v;
+    if (word_at_ci(t, p, e, kInfinity) && p + 8 == e) v = bits_to_double(0x7FF0000000000000ull);
+    else if (word_at_ci(t, p, e, kInf) && p + 3 == e) v = bits_to_double(0x7FF0000000000000ull);
+    else if (word_at_ci(t, p, e, kNan) && p + 3 == e) v = bits_to_double(0x7FF8000000000000ull);
+    else return false;
+    *out = neg ? -v : v;
+    return true;
+  }
+  const int64_t ms = p;
+  bool any_int = false, any_frac = false;
+  p = scan_digitpart(t, p, e, &any_int);
+  if (p < 0) return false;
+  if (p < e && t[p] == '.') {
+    ++p;
+    p = scan_digitpart(t, p, e, &any_frac);
+    if (p < 0) return false;
+  }
+  if (!any_int && !any_frac) return false;
+  const int64_t me = p;
+  int64_t exp10 = 0;
+  if (p < e && (t[p] == 'e' || t[p] == 'E')) {
+    ++p;
+    bool eneg = false;
+    if (p < e && (t[p] == '+' || t[p] == '-')) { eneg = t[p] == '-'; ++p; }
+    bool any_exp = false;
+    const int64_t es = p;
+    p = scan_digitpart(t, p, e, &any_exp);
+    if (p < 0 || !any_exp) return false;
+    exp10 = exp_value(t, es, p);
+    if (eneg) exp10 = -exp10;
+  }
+  if (p != e) return false;
+  const double v = dec_to_double(t, ms, me, exp10);
+  *out = neg ? -v : v;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// JSON recogniser for a box payload (json.loads of CPython's C scanner, reward_func.py:216, :223,
+// :322, :511).  The payload starts with '['.  Result:
+//   kJsonInvalid : json.loads raises (JSONDecodeError)
+//   otherwise    : *n_elems = len(list); *numeric = np.array(list, dtype=float) succeeds
+//                  (reward_func.py:364-365): numbers, true / false (1.0 / 0.0), null and NaN (nan),
+//                  +-Infinity, and strings that float() accepts; elements 0..3 are in out[].
+// Other strings, objects and ragged nested lists raise inside np.array and are caught (:367):
+// `numeric = false`, the box scores 0.  Not reproduced: strings with backslash
+// escapes that unescape to a float (treated as non-numeric) and homogeneous nested lists
+// ([[1],[2],[3],[4]]: a 2-D array in the reference, which then fails on an ambiguous truth value).
+// ------------------------------------------------------------------------------------------
+constexpr int kJsonInvalid = 0, kJsonList = 1;
+constexpr int kJsonMaxDepth = 64;
+
+O3V_HD bool json_ws(uint8_t c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r'; }
+O3V_HD bool is_hex(uint8_t c) {
+  return (c >= '0' && c <= '9') || (c >= 'a' && c <= 'f') || (c >= 'A' && c <= 'F');
+}
+
+// string body after the opening quote; returns position after the closing quote or -1
+O3V_HD int64_t json_string(const uint8_t* t, int64_t p, int64_t e) {
+  while (p < e) {
+    const uint8_t c = t[p];
+    if (c == '"') return p + 1;
+    if (c < 0x20) return -1;                               // strict: no control characters
+    if (c == '\\') {
+      if (p + 1 >= e) return -1;
+      const uint8_t x = t[p + 1];
+      if (x == 'u') {
+        if (p + 6 > e) return -1;
+        for (int i = 2; i < 6; ++i)
+          if (!is_hex(t[p + i])) return -1;
+        p += 6;
+      } else if (x == '"' || x == '\\' || x == '/' || x == 'b' || x == 'f' || x == 'n' || x == 'r' || x == 't') {
+        p += 2;
+      } else {
+        return -1;
+      }
+      continue;
+    }
+    ++p;
+  }
+  return -1;
+}
+
+// JSON number at p: -?(0|[1-9]\d*)(\.\d+)?([eE][-+]?\d+)?  -> end, value; -1 if none
+O3V_HD int64_t json_number(const uint8_t* t, int64_t p, int64_t e, double* out) {
+  bool neg = false;
+  if (p < e && t[p] == '-') { neg = true; ++p; }
+  const int64_t ms = p;
+  if (p >= e || t[p] < '0' || t[p] > '9') return -1;
+  if (t[p] == '0') ++p;
+  else while (p < e && t[p] >= '0' && t[p] <= '9') ++p;
+  bool is_float = false;
+  if (p + 1 < e && t[p] == '.' && t[p + 1] >= '0' && t[p + 1] <= '9') {
+    is_float = true;
+    ++p;
+    while (p < e && t[p] >= '0' && t[p] <= '9') ++p;
+  }
+  const int64_t me = p;
+  int64_t exp10 = 0;
+  if (p < e && (t[p] == 'e' || t[p] == 'E')) {
+    int64_t q = p + 1;
+    bool eneg = false;
+    if (q < e && (t[q] == '+' || t[q] == '-')) { eneg = t[q] == '-'; ++q; }
+    if (q < e && t[q] >= '0' && t[q] <= '9') {
+      const int64_t es = q;
+      while (q < e && t[q] >= '0' && t[q] <= '9') ++q;
+      exp10 = exp_value(t, es, q);
+      if (eneg) exp10 = -exp10;
+      is_float = true;
+      p = q;
+    }
+  }
+  const double v = dec_to_double(t, ms, me, exp10);
+  // an integer literal becomes a Python int: "-0" is int 0 -> +0.0 in np.array(dtype=float)
+  *out = (neg && (is_float || v != 0.0)) ? -v : v;
+  return p;
+}
+
+O3V_HD int json_box(const uint8_t* t, int64_t s, int64_t e, int* n_elems, bool* numeric, double out[4]) {
+  constexpr Lit kNull = make_lit("null"), kTrue = make_lit("true"), kFalse = make_lit("false"),
+                kNaN = make_lit("NaN"), kInfinity = make_lit("Infinity"), kNegInfinity = make_lit("-Infinity");
+  int64_t p = s;
+  uint64_t is_array = 0;     // bit d: container at depth d+1 is an array
+  int depth = 0;
+  int n_top = 0;
+  bool all_numeric = true;
+  // states
+  enum { kValueOrClose, kValue, kAfterValue, kKeyOrClose, kKey, kColon, kDone };
+  int state = kValue;
+  while (true) {
+    while (p < e && json_ws(t[p])) ++p;
+    if (state == kDone) break;
+    if (p >= e) return kJsonInvalid;
+    const uint8_t c = t[p];
+    if (state == kValue || state == kValueOrClose) {
+      if (state == kValueOrClose && c == ']') {            // empty array
+        --depth; ++p;
+        state = depth == 0 ? kDone : kAfterValue;
+        if (depth == 1) { ++n_top; all_numeric = false; }  // a nested [] element
+        continue;
+      }
+      const bool top_elem = depth == 1;
+      if (c == '[' || c == '{') {
+        if (depth >= kJsonMaxDepth) return kJsonInvalid;
+        if (c == '[') is_array |= (uint64_t)1 << depth; else is_array &= ~((uint64_t)1 << depth);
+        ++depth; ++p;
+        state = c == '[' ? kValueOrClose : kKeyOrClose;
+        continue;                                          // the element is counted when it closes
+      }
+      double v = 0.0;
+      bool num = false;
+      if (c == '"') {
+        const int64_t q = json_string(t, p + 1, e);
+        if (q < 0) return kJsonInvalid;
+        if (top_elem) {                                      // np.array(dtype=float) calls float(str)
+          int64_t fs = p + 1, fe = q - 1;
+          bool escaped = false;
+          for (int64_t i = fs; i < fe; ++i) escaped |= t[i] == '\\';
+          strip_space(t, &fs, &fe, false);
+          num = !escaped && python_float(t, fs, fe, &v);
+        }
+        p = q;
+      } else if (c == 'n' && lit_at(t, p, e, kNull)) { p += 4; v = bits_to_double(0x7FF8000000000000ull); num = true;
+      } else if (c == 't' && lit_at(t, p, e, kTrue)) { p += 4; v = 1.0; num = true;
+      } else if (c == 'f' && lit_at(t, p, e, kFalse)) { p += 5; v = 0.0; num = true;
+      } else if (c == 'N' && lit_at(t, p, e, kNaN)) { p += 3; v = bits_to_double(0x7FF8000000000000ull); num = true;
+      } else if (c == 'I' && lit_at(t, p, e, kInfinity)) { p += 8; v = bits_to_double(0x7FF0000000000000ull); num = true;
+      } else if (c == '-' && lit_at(t, p, e, kNegInfinity)) { p += 9; v = bits_to_double(0xFFF0000000000000ull); num = true;
+      } else {
+        const int64_t q = json_number(t, p, e, &v);
+        if (q < 0) return kJsonInvalid;
+        p = q;
+        num = true;
+      }
+      if (top_elem) {
+        if (num && n_top < 4) out[n_top] = v;
+        if (!num) all_numeric = false;
+        ++n_top;
+      }
+      state = kAfterValue;
+      continue;
+    }
+    if (state == kAfterValue) {
+      const bool arr = (is_array >> (depth - 1)) & 1;
+      if (c == ',') { ++p; state = arr ? kValue : kKey; continue; }
+      if ((arr && c == ']') || (!arr && c == '}')) {
+        --depth; ++p;
+        if (depth == 0) { state = kDone; continue; }
+        if (depth == 1) { ++n_top; all_numeric = false; }  // a nested container element closed
+        state = kAfterValue;
+        continue;
+      }
+      return kJsonInvalid;
+    }
+    if (state == kKeyOrClose || state == kKey) {
+      if (state == kKeyOrClose && c == '}') {
+        --depth; ++p;
+        if (depth == 0) { state = kDone; continue; }       // not reachable: the payload starts with '['
+        if (depth == 1) { ++n_top; all_numeric = false; }
+        state = kAfterValue;
+        continue;
+      }
+      if (c != '"') return kJsonInvalid;
+      p = json_string(t, p + 1, e);
+      if (p < 0) return kJsonInvalid;
+      state = kColon;
+      continue;
+    }
+    if (state == kColon) {
+      if (c != ':') return kJsonInvalid;
+      ++p;
+      state = kValue;
+      continue;
+    }
+  }
+  if (p != e) return kJsonInvalid;                          // "Extra data"
+  *n_elems = n_top;
+  *numeric = all_numeric;
+  return kJsonList;
+}
+
+// ------------------------------------------------------------------------------------------
+// One rollout.
+// ------------------------------------------------------------------------------------------
+struct Caps { int P, C, Bc, Tb; };
+struct RolloutOut {            // pointers to THIS rollout's rows (o3v_rewards_soa layout)
+  int32_t* flags; double* ans_seg; double* ans_box; int32_t* n_times; double* think_times;
+  int32_t* n_claims; double* claim_t; int32_t* claim_nbox; uint32_t* claim_valid; double* claim_box;
+  int32_t* n_tboxes; uint32_t* tbox_valid; double* think_box;
+};
+struct Maxima { int times, claims, claim_boxes, think_boxes; };
+
+#if defined(__CUDA_ARCH__)
+#define O3V_LANE0 ((threadIdx.x & 31) == 0)
+#else
+#define O3V_LANE0 true
+#endif
+
+constexpr int kFlagThink = 1, kFlagAnswer = 2, kFlagAnsSeg = 4, kFlagAnsBox = 8;
+constexpr int kTaskVisual = 0, kTaskTemporal = 1, kTaskTemporalMcq = 2;
+
+// `<box>(\[.*?\])</box>` without DOTALL at or after p inside [.., lim): on success the payload is
+// [*bs, *be) (brackets included) and the return value is the end of the match; -1 if no match.
+O3V_HD int64_t next_box(const uint8_t* t, int64_t p, int64_t lim, int64_t* bs, int64_t* be) {
+  constexpr Lit kOpen = make_lit("<box>["), kClose = make_lit("</box>");
+  for (;;) {
+    p = find_lit(t, p, lim, kOpen);
+    if (p < 0) return -1;
+    for (int64_t i = p + 6; i < lim; ++i) {
+      const uint8_t c = t[i];
+      if (c == '\n') break;                                // '.' does not cross a newline
+      if (c == ']' && lit_at(t, i + 1, lim, kClose)) {
+        *bs = p + 5;
+        *be = i + 1;
+        return i + 7;
+      }
+    }
+    ++p;                                                   // the regex retries one character later
+  }
+}
+
+O3V_HD void parse_rollout(const uint8_t* t, int64_t beg, int64_t end, int task, const Caps& cap,
+                          const RolloutOut& o, Maxima* mx) {
+  constexpr Lit kThinkO = make_lit("<think>"), kThinkC = make_lit("</think>"), kAnsO = make_lit("<answer>"),
+                kAnsC = make_lit("</answer>"), kT = make_lit("<t>"), kTEnd = make_lit("</t>s"),
+                kTo = make_lit("</t>s to <t>"), kObj = make_lit("<obj>"), kObjBox = make_lit("</obj><box>["),
+                kBoxAt = make_lit("]</box>at<t>");
+  int flags = 0;
+  // think / answer spans: leftmost open tag, first close tag after it (lazy `.*?`, DOTALL)
+  int64_t ts = find_lit(t, beg, end, kThinkO), te = -1;
+  if (ts >= 0) { ts += 7; te = find_lit(t, ts, end, kThinkC); }
+  const bool has_think = te >= 0;
+  int64_t as = find_lit(t, beg, end, kAnsO), ae = -1;
+  if (as >= 0) { as += 8; ae = find_lit(t, as, end, kAnsC); }
+  const bool has_answer = ae >= 0;
+  if (has_think) flags |= kFlagThink;
+  if (has_answer) flags |= kFlagAnswer;
+
+  // ---- answer "<t>a</t>s to <t>b</t>s" (:119, temporal tasks)
+  if ((task == kTaskTemporal || task == kTaskTemporalMcq) && has_answer) {
+    int64_t p = as;
+    while ((p = find_lit(t, p, ae, kT)) >= 0) {
+      const int64_t a0 = p + 3, a1 = scan_simple_decimal(t, a0, ae);
+      if (a1 >= 0 && lit_at(t, a1, ae, kTo)) {
+        const int64_t b0 = a1 + 12, b1 = scan_simple_decimal(t, b0, ae);
+        if (b1 >= 0 && lit_at(t, b1, ae, kTEnd)) {
+          flags |= kFlagAnsSeg;
+          const double a = dec_to_double(t, a0, a1, 0), b = dec_to_double(t, b0, b1, 0);
+          if (O3V_LANE0) { o.ans_seg[0] = a; o.ans_seg[1] = b; }
+          break;
+        }
+      }
+      ++p;
+    }
+  }
+
+  // ---- every "<t>x</t>s" inside <think> (:405-412, :447-449); one bad float() empties the list
+  int n_times = 0;
+  if (has_think) {
+    bool all_ok = true;
+    int64_t p = ts;
+    while ((p = find_lit(t, p, te, kT)) >= 0) {
+      bool ok;
+      const int64_t x0 = p + 3, x1 = scan_digits_dots(t, x0, te, &ok);
+      if (x1 > x0 && lit_at(t, x1, te, kTEnd)) {
+        if (!ok) all_ok = false;
+        else if (all_ok) {
+          const double v = dec_to_double(t, x0, x1, 0);
+          if (n_times < cap.P && O3V_LANE0) o.think_times[n_times] = v;
+        }
+        ++n_times;
+        p = x1 + 5;
+      } else {
+        ++p;
+      }
+    }
+    if (!all_ok) n_times = 0;
+  }
+
+  int n_tboxes = 0, n_claims = 0, max_cb = 0;
+  uint32_t tvalid = 0;
+  if (task == kTaskVisual) {
+    // ---- first <box> of the answer (:211-223)
+    if (has_answer) {
+      int64_t bs, be;
+      if (next_box(t, as, ae, &bs, &be) >= 0) {
+        int n; bool numeric; double v[4];
+        if (json_box(t, bs, be, &n, &numeric, v) == kJsonList && n == 4 && numeric) {
+          flags |= kFlagAnsBox;
+          if (O3V_LANE0) { o.ans_box[0] = v[0]; o.ans_box[1] = v[1]; o.ans_box[2] = v[2]; o.ans_box[3] = v[3]; }
+        }
+      }
+    }
+    // ---- every <box> inside <think> (:505-511); payloads that are not JSON are skipped
+    if (has_think) {
+      int64_t p = ts, bs, be;
+      while ((p = next_box(t, p, te, &bs, &be)) >= 0) {
+        int n; bool numeric; double v[4];
+        if (json_box(t, bs, be, &n, &numeric, v) != kJsonList) continue;
+        if (n == 4 && numeric && n_tboxes < 32) {
+          tvalid |= 1u << n_tboxes;
+          if (n_tboxes < cap.Tb && O3V_LANE0) {
+            double* dst = o.think_box + 4 * n_tboxes;
+            dst[0] = v[0]; dst[1] = v[1]; dst[2] = v[2]; dst[3] = v[3];
+          }
+        }
+        ++n_tboxes;
+      }
+    }
+  } else if (has_think) {
+    // ---- claims (:308-335): <obj>(.*?)</obj>((?:<box>\[.*?\]</box>)+)at<t>(.*?)</t>s, DOTALL
+    int64_t p = ts;
+    for (;;) {
+      p = find_lit(t, p, te, kObj);
+      if (p < 0) break;
+      const int64_t q = find_lit(t, p + 5, te, kObjBox);
+      if (q < 0) break;
+      const int64_t e = find_lit(t, q + 12, te, kBoxAt);
+      if (e < 0) break;
+      const int64_t z = find_lit(t, e + 12, te, kTEnd);
+      if (z < 0) break;
+      p = z + 5;
+      int64_t fs = e + 12, fe = z;
+      strip_space(t, &fs, &fe, true);
+      double tv;
+      if (!python_float(t, fs, fe, &tv)) continue;          // ValueError -> claim dropped (:332)
+      // boxes: re.findall(r'\[.*?\]', group 2) without DOTALL, group 2 = [q + 6, e + 7)
+      const int64_t g0 = q + 6, g1 = e + 7;
+      int nb = 0;
+      uint32_t valid = 0;
+      bool json_ok = true;
+      double* cbox = o.claim_box + (int64_t)(n_claims < cap.C ? n_claims : 0) * cap.Bc * 4;
+      for (int64_t i = g0; i < g1 && json_ok;) {
+        if (t[i] != '[') { ++i; continue; }
+        int64_t j = i + 1;
+        while (j < g1 && t[j] != ']' && t[j] != '\n') ++j;
+        if (j >= g1) break;
+        if (t[j] == '\n') { i = j + 1; continue; }
+        int n; bool numeric; double v[4];
+        if (json_box(t, i, j + 1, &n, &numeric, v) != kJsonList) { json_ok = false; break; }
+        if (n == 4 && numeric && nb < 32) {
+          valid |= 1u << nb;
+          if (n_claims < cap.C && nb < cap.Bc && O3V_LANE0) {
+            double* dst = cbox + 4 * nb;
+            dst[0] = v[0]; dst[1] = v[1]; dst[2] = v[2]; dst[3] = v[3];
+          }
+        }
+        ++nb;
+        i = j + 1;
+      }
+      if (!json_ok) continue;                               // JSONDecodeError -> claim dropped
+      if (n_claims < cap.C && O3V_LANE0) {
+        o.claim_t[n_claims] = tv;
+        o.claim_nbox[n_claims] = nb;
+        o.claim_valid[n_claims] = valid;
+      }
+      if (nb > max_cb) max_cb = nb;
+      ++n_claims;
+    }
+  }
+
+  if (O3V_LANE0) {
+    *o.flags = flags;
+    *o.n_times = n_times;
+    *o.n_claims = n_claims;
+    *o.n_tboxes = n_tboxes;
+    *o.tbox_valid = tvalid;
+  }
+  mx->times = n_times;
+  mx->claims = n_claims;
+  mx->claim_boxes = max_cb;
+  mx->think_boxes = n_tboxes;
+}
+
+}  // namespace scan
+}  // namespace o3v

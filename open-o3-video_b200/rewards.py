@@ -1,13 +1,16 @@
-"""Spatio-temporal rewards: text parsing in Python, numerics on the GPU (K4).
+"""Spatio-temporal rewards: completion text scanned on the GPU (K6), numerics on the GPU (K4).
 
 Drop-in for the numeric reward callables of the reference
 (src/r1-v/src/open_r1/reward_func.py): same names, same `f(completions, **kwargs) ->
-list[float]` signature (grpo_trainer.py:655), same task gating.  The regex / json / ast
-extraction is string work and stays in Python exactly as the reference does it (cited per
-function); everything after parsing -- temporal IoU, in-segment ratio, adaptive temporal
-proximity, temporal gating + bbox IoU, visual-QA IoUs -- runs in one CUDA launch over a
-struct-of-arrays batch (include/o3v.h `o3v_rewards_soa`).  `ans_acc_reward` and
-`format_reward` are pure string rewards and are not part of this path.
+list[float]` signature (grpo_trainer.py:655), same task gating.  The completions are shipped to
+the device as UTF-8 bytes and `o3v_parse_completions` (K6) extracts what the reference's regex /
+json / float() calls extract, bit for bit; the ground-truth side of the kwargs (a few numbers per
+prompt, already structured) is packed on the host exactly as the reference reads it (cited per
+function); temporal IoU, in-segment ratio, adaptive temporal proximity, temporal gating + bbox
+IoU and the visual-QA IoUs then run in one more launch over the struct-of-arrays batch
+(include/o3v.h `o3v_rewards_soa`, K4).  `parse_rollout` / `pack_rollouts` keep the host-side
+route for callers that already hold parsed rollouts.  `ans_acc_reward` and `format_reward` are
+pure string rewards and are not part of this path.
 """
 import ast
 import ctypes
@@ -53,6 +56,22 @@ def parse_claims(think_content: str):
     return claims
 
 
+def parse_gt_answer(task: str, answer: str):
+    """Ground-truth side of kwargs['answer'] -> (gt_seg, gt_vbox), as the reference reads it."""
+    gt_seg, gt_vbox = [0.0, 0.0], None
+    if task in ("temporal QA", "temporal QA (MCQ)"):
+        gt = answer.split("\n")[1] if task == "temporal QA (MCQ)" else answer       # :116, :146
+        gt_seg = [float(x) for x in ast.literal_eval(gt)]                           # :118, :147, :409
+    if task == "visual QA":
+        mg = re.search(r"<box>(\[.*?\])</box>", "<answer>%s</answer>" % answer)      # :204, :493
+        if mg:
+            try:
+                gt_vbox = json.loads(mg.group(1))                                   # :216, :498
+            except Exception:
+                gt_vbox = None
+    return gt_seg, gt_vbox
+
+
 def parse_rollout(content: str, task: str, answer: str, key_frames=None, key_items=None, image_size=None,
                   image_size_refine=None, step_percent: float = 0.0) -> dict:
     """One completion + its reward kwargs -> the parsed structure the kernels consume."""
@@ -65,9 +84,8 @@ def parse_rollout(content: str, task: str, answer: str, key_frames=None, key_ite
     m = re.search(r"<answer>\s*(.*?)\s*</answer>", content, re.DOTALL)              # :91 extract_answer
     output_ans = m.group(1).strip() if m else ""
     think = think_match.group(1) if think_match else ""
+    r["gt_seg"], r["gt_vbox"] = parse_gt_answer(task, answer)
     if task in ("temporal QA", "temporal QA (MCQ)"):
-        gt = answer.split("\n")[1] if task == "temporal QA (MCQ)" else answer       # :116, :146
-        r["gt_seg"] = [float(x) for x in ast.literal_eval(gt)]
         mm = re.search(r"<t>(\d+\.?\d*)</t>s to <t>(\d+\.?\d*)</t>s", output_ans)   # :119
         if mm:
             r["ans_seg"] = [float(mm.group(1)), float(mm.group(2))]
@@ -78,12 +96,6 @@ def parse_rollout(content: str, task: str, answer: str, key_frames=None, key_ite
             r["think_times"] = []
     if task == "visual QA":
         pat = r"<box>(\[.*?\])</box>"
-        mg = re.search(pat, "<answer>%s</answer>" % answer)                         # :204, :493
-        if mg:
-            try:
-                r["gt_vbox"] = json.loads(mg.group(1))
-            except Exception:
-                r["gt_vbox"] = None
         mp = re.search(pat, output_ans)                                             # :212
         if mp:
             try:
@@ -101,6 +113,42 @@ def parse_rollout(content: str, task: str, answer: str, key_frames=None, key_ite
 
 
 # ----------------------------------------------------------------------------- packing
+def pack_gt(gts: Sequence[dict]):
+    """Per-prompt ground truth (dicts with task, step_percent, gt_seg, gt_vbox, key_frames, key_items,
+    image_size, image_size_refine) -> the per-prompt arrays of o3v_rewards_soa, plus dims K, O, Gb."""
+    Q = len(gts)
+    K = max([len(g["key_frames"]) for g in gts] + [1])
+    O = max([len(g["key_items"].get(str(f["idx"]), {})) for g in gts for f in g["key_frames"]] + [1])
+    Gb = max([len(bx) for g in gts for f in g["key_frames"]
+              for bx in g["key_items"].get(str(f["idx"]), {}).values()] + [1])
+    a = dict(
+        task=np.zeros(Q, np.int32), step_percent=np.zeros(Q), gt_flags=np.zeros(Q, np.int32), gt_seg=np.zeros((Q, 2)),
+        gt_vbox=np.zeros((Q, 4)), image_size=np.ones((Q, 2)), image_refine=np.ones((Q, 2)),
+        n_kf=np.zeros(Q, np.int32), kf_time=np.zeros((Q, K)), n_obj=np.zeros((Q, K), np.int32),
+        n_gtbox=np.zeros((Q, K, O), np.int32), gt_box=np.zeros((Q, K, O, Gb, 4)))
+    for q, g in enumerate(gts):
+        if g["task"] not in TASK_IDS:
+            raise ValueError("Unknown task: %s" % g["task"])            # data_loader.py:33
+        a["task"][q] = TASK_IDS[g["task"]]
+        a["step_percent"][q] = g["step_percent"]
+        a["gt_seg"][q] = g["gt_seg"]
+        if g["gt_vbox"] is not None:
+            a["gt_flags"][q] = GF_VBOX
+            a["gt_vbox"][q] = g["gt_vbox"]
+        a["image_size"][q] = g["image_size"]
+        a["image_refine"][q] = g["image_size_refine"]
+        a["n_kf"][q] = len(g["key_frames"])
+        for k, fr in enumerate(g["key_frames"]):
+            a["kf_time"][q, k] = fr["time"]
+            objs = g["key_items"].get(str(fr["idx"]), {})
+            a["n_obj"][q, k] = len(objs)
+            for o, boxes in enumerate(objs.values()):
+                a["n_gtbox"][q, k, o] = len(boxes)
+                for gi, box in enumerate(boxes):
+                    a["gt_box"][q, k, o, gi] = box
+    return a, dict(K=K, O=O, Gb=Gb)
+
+
 def pack_rollouts(rollouts: Sequence[dict], G: int = 1):
     """Parsed rollouts (GT identical within each block of G) -> dict of numpy arrays in the
     o3v_rewards_soa layout, plus the dims."""
@@ -114,20 +162,13 @@ def pack_rollouts(rollouts: Sequence[dict], G: int = 1):
     if Bc > 32 or Tb > 32:
         raise ValueError("more than 32 boxes per claim / think block")
     gts = [rollouts[q * G] for q in range(Q)]
-    K = max([len(g["key_frames"]) for g in gts] + [1])
-    O = max([len(g["key_items"].get(str(f["idx"]), {})) for g in gts for f in g["key_frames"]] + [1])
-    Gb = max([len(bx) for g in gts for f in g["key_frames"]
-              for bx in g["key_items"].get(str(f["idx"]), {}).values()] + [1])
+    gt_arrays, gt_dims = pack_gt(gts)
     a = dict(
         flags=np.zeros(R, np.int32), ans_seg=np.zeros((R, 2)), ans_box=np.zeros((R, 4)),
         n_times=np.zeros(R, np.int32), think_times=np.zeros((R, P)), n_claims=np.zeros(R, np.int32),
         claim_t=np.zeros((R, C)), claim_nbox=np.zeros((R, C), np.int32), claim_valid=np.zeros((R, C), np.uint32),
         claim_box=np.zeros((R, C, Bc, 4)), n_tboxes=np.zeros(R, np.int32), tbox_valid=np.zeros(R, np.uint32),
-        think_box=np.zeros((R, Tb, 4)),
-        task=np.zeros(Q, np.int32), step_percent=np.zeros(Q), gt_flags=np.zeros(Q, np.int32), gt_seg=np.zeros((Q, 2)),
-        gt_vbox=np.zeros((Q, 4)), image_size=np.ones((Q, 2)), image_refine=np.ones((Q, 2)),
-        n_kf=np.zeros(Q, np.int32), kf_time=np.zeros((Q, K)), n_obj=np.zeros((Q, K), np.int32),
-        n_gtbox=np.zeros((Q, K, O), np.int32), gt_box=np.zeros((Q, K, O, Gb, 4)))
+        think_box=np.zeros((R, Tb, 4)))
     for i, r in enumerate(rollouts):
         f = (RF_HAS_THINK if r["has_think"] else 0) | (RF_HAS_ANSWER if r["has_answer"] else 0)
         if r["ans_seg"] is not None:
@@ -153,27 +194,8 @@ def pack_rollouts(rollouts: Sequence[dict], G: int = 1):
             if _box_ok(box):
                 a["tbox_valid"][i] |= np.uint32(1 << b)
                 a["think_box"][i, b] = box
-    for q, g in enumerate(gts):
-        if g["task"] not in TASK_IDS:
-            raise ValueError("Unknown task: %s" % g["task"])            # data_loader.py:33
-        a["task"][q] = TASK_IDS[g["task"]]
-        a["step_percent"][q] = g["step_percent"]
-        a["gt_seg"][q] = g["gt_seg"]
-        if g["gt_vbox"] is not None:
-            a["gt_flags"][q] = GF_VBOX
-            a["gt_vbox"][q] = g["gt_vbox"]
-        a["image_size"][q] = g["image_size"]
-        a["image_refine"][q] = g["image_size_refine"]
-        a["n_kf"][q] = len(g["key_frames"])
-        for k, fr in enumerate(g["key_frames"]):
-            a["kf_time"][q, k] = fr["time"]
-            objs = g["key_items"].get(str(fr["idx"]), {})
-            a["n_obj"][q, k] = len(objs)
-            for o, boxes in enumerate(objs.values()):
-                a["n_gtbox"][q, k, o] = len(boxes)
-                for gi, box in enumerate(boxes):
-                    a["gt_box"][q, k, o, gi] = box
-    dims = dict(R=R, G=G, P=P, C=C, Bc=Bc, Tb=Tb, K=K, O=O, Gb=Gb)
+    a.update(gt_arrays)
+    dims = dict(R=R, G=G, P=P, C=C, Bc=Bc, Tb=Tb, **gt_dims)
     return a, dims
 
 
@@ -217,6 +239,91 @@ def rewards_from_rollouts(rollouts: Sequence[dict], G: int = 1, device="cuda") -
     return grounded_rewards_device(to_device(arrays, device), dims)
 
 
+# ----------------------------------------------------------------------------- K6: text scanned on the device
+ROLLOUT_ROWS = (("flags", torch.int32, ()), ("ans_seg", torch.float64, (2,)), ("ans_box", torch.float64, (4,)),
+                ("n_times", torch.int32, ()), ("think_times", torch.float64, ("P",)), ("n_claims", torch.int32, ()),
+                ("claim_t", torch.float64, ("C",)), ("claim_nbox", torch.int32, ("C",)),
+                ("claim_valid", torch.int32, ("C",)), ("claim_box", torch.float64, ("C", "Bc", 4)),
+                ("n_tboxes", torch.int32, ()), ("tbox_valid", torch.int32, ()), ("think_box", torch.float64, ("Tb", 4)))
+DEFAULT_CAPS = dict(P=16, C=16, Bc=4, Tb=8)
+
+
+def encode_completions(contents: Sequence[str]):
+    """list[str] -> (pinned uint8 tensor padded as o3v_parse_args.text requires, pinned int64 offsets [R+1])."""
+    blobs = [c.encode("utf-8", "surrogatepass") for c in contents]
+    offsets = torch.zeros(len(blobs) + 1, dtype=torch.int64)
+    if blobs:
+        offsets[1:] = torch.cumsum(torch.tensor([len(b) for b in blobs], dtype=torch.int64), 0)
+    total = int(offsets[-1])
+    text = torch.zeros((total + 15) // 16 * 16 + 16, dtype=torch.uint8)
+    if total:
+        text[:total] = torch.frombuffer(bytearray(b"".join(blobs)), dtype=torch.uint8)
+    if torch.cuda.is_available():
+        text, offsets = text.pin_memory(), offsets.pin_memory()
+    return text, offsets
+
+
+def parse_completions_device(text: torch.Tensor, offsets: torch.Tensor, task: torch.Tensor, G: int = 1,
+                             caps: Optional[dict] = None, sync: bool = True):
+    """K6 launch: UTF-8 bytes on the device -> (rollout-side arrays of o3v_rewards_soa, dims P/C/Bc/Tb).
+
+    text uint8 (padded, see include/o3v.h), offsets int64 [R+1], task int32 [R/G], all CUDA tensors.
+    With sync=True the overflow report is read back and the launch is repeated with larger rows
+    when some rollout had more timestamps / claims / boxes than the capacities; with sync=False the
+    caller gets the report tensor under key "overflow" and checks it itself."""
+    if not (text.is_cuda and offsets.is_cuda and task.is_cuda):
+        raise RuntimeError("open-o3-video_b200 ops take CUDA tensors only (no CPU fallback)")
+    lib = _lib.load()
+    R = offsets.numel() - 1
+    caps = dict(DEFAULT_CAPS if caps is None else caps)
+    dev = text.device
+    with torch.cuda.device(dev):
+        ws = torch.empty(max(2, lib.o3v_parse_workspace_bytes() // 8), dtype=torch.int64, device=dev)
+        while True:
+            out = {"overflow": torch.empty(4, dtype=torch.int32, device=dev)}
+            for name, dt, shape in ROLLOUT_ROWS:
+                out[name] = torch.empty((R,) + tuple(caps[d] if isinstance(d, str) else d for d in shape),
+                                        dtype=dt, device=dev)
+            a = _lib.ParseArgs()
+            a.R, a.G = R, G
+            for k in ("P", "C", "Bc", "Tb"):
+                setattr(a, k, caps[k])
+            a.text, a.offsets, a.task = text.data_ptr(), offsets.data_ptr(), task.data_ptr()
+            for name in out:
+                setattr(a, name, out[name].data_ptr())
+            _lib.call("o3v_parse_completions", 1, lib.o3v_parse_completions, ctypes.byref(a),
+                      ctypes.c_void_p(ws.data_ptr()), ctypes.c_size_t(ws.numel() * 8),
+                      ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+            if not sync:
+                break
+            over = out["overflow"].tolist()
+            if not any(over):
+                break
+            if over[2] > 32 or over[3] > 32:
+                raise ValueError("more than 32 boxes per claim / think block")    # as pack_rollouts
+            for k, v in zip(("P", "C", "Bc", "Tb"), over):
+                if v:
+                    caps[k] = min(32, v) if k in ("Bc", "Tb") else v
+    return out, caps
+
+
+def rewards_from_text(contents: Sequence[str], gts: Sequence[dict], G: int = 1, device="cuda",
+                      caps: Optional[dict] = None) -> torch.Tensor:
+    """Completion strings + per-prompt ground truth (see pack_gt) -> [R, 5] float64 on the device:
+    K6 (scan) then K4 (numerics), two launches."""
+    R = len(contents)
+    if R == 0:
+        return torch.empty(0, 5, dtype=torch.float64, device=device)
+    assert R == len(gts) * G
+    gt_arrays, gt_dims = pack_gt(gts)
+    text, offsets = encode_completions(contents)
+    dev_gt = to_device(gt_arrays, device)
+    rows, caps = parse_completions_device(text.to(device, non_blocking=True), offsets.to(device, non_blocking=True),
+                                          dev_gt["task"], G, caps)
+    rows.update(dev_gt)
+    return grounded_rewards_device(rows, dict(R=R, G=G, **caps, **gt_dims))
+
+
 # ----------------------------------------------------------------------------- reference-named callables
 _cache = {"key": None, "val": None}
 
@@ -233,10 +340,14 @@ def grounded_rewards(completions, **kwargs) -> np.ndarray:
     if _cache["key"] == key:
         return _cache["val"]
     get = lambda name, i: (kwargs[name][i] if name in kwargs and kwargs[name] is not None else None)
-    rollouts = [parse_rollout(c, task, get("answer", i) or "", get("key_frames", i), get("key_items", i),
-                              get("image_size", i), get("image_size_refine", i), step)
-                for i, c in enumerate(contents)]
-    val = rewards_from_rollouts(rollouts, 1).cpu().numpy()
+    gts = []
+    for i in range(len(contents)):
+        gt_seg, gt_vbox = parse_gt_answer(task, get("answer", i) or "")
+        gts.append(dict(task=task, step_percent=step, gt_seg=gt_seg, gt_vbox=gt_vbox,
+                        key_frames=get("key_frames", i) or [], key_items=get("key_items", i) or {},
+                        image_size=get("image_size", i) or (1, 1),
+                        image_size_refine=get("image_size_refine", i) or (1, 1)))
+    val = rewards_from_text(contents, gts, 1).cpu().numpy()
     _cache["key"], _cache["val"] = key, val
     return val
 

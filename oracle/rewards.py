@@ -191,7 +191,11 @@ def thk_spatial(r):
             for obj in objects.keys():
                 claim_boxes = bboxes
                 gt_boxes = objects[obj]
-                if not isinstance(claim_boxes[0], list):                   # :579-586
+                try:
+                    is_claim_originally_multiple = isinstance(claim_boxes[0], list)   # :579
+                except Exception:                                          # :580-582 (no boxes survived findall)
+                    continue
+                if not is_claim_originally_multiple:                       # :584-585
                     claim_boxes = [claim_boxes]
                 lst = []
                 for gt_box in gt_boxes:

@@ -6,6 +6,8 @@ Outputs (committed):
     logps_small.npz      reference _get_per_token_logps (grpo_trainer.py:371-384) on seeded inputs
     rewards_small.json   reference reward_func.py functions on rendered synthetic rollouts
     rewards_kat.json     the known-answer cases of SURVEY.md Appendix B, re-run here
+    parse_cases.json     reference reward callables on seeded completion TEXT (well-formed and malformed):
+                         pins the text extraction (regex / json / float) end to end
 Inputs are regenerated from the seed by the tests (oracle/synth.py); only outputs
 (and, for rewards, the small structured inputs) are stored.
 """
@@ -107,7 +109,30 @@ def gen_vstar():
     print("vstar_small.json", arr.shape, "means", arr.mean(0).round(4).tolist())
 
 
+def gen_parse():
+    """Reference reward callables on (completion text, kwargs) cases from oracle/parse.text_cases, and the
+    reference's own claim parser on think blocks."""
+    import random
+    import warnings
+    from oracle import parse as op
+    warnings.simplefilter("ignore")
+    rf = ref_import.load_reward_func()
+    n, seed = 1200, synth.SEED + 60
+    cases = op.text_cases(n, seed)
+    ref = op.reference_rewards_from_text(rf, cases)
+    rng = random.Random(seed + 1)
+    thinks = [op.synth_completion(rng, "temporal-spatial free-form QA", True) for _ in range(400)]
+    claims = [[[c["timestamp"], c["bboxes"]] for c in rf.parse_temporal_spatial_reasoning_process(t)] for t in thinks]
+    with open(os.path.join(HERE, "parse_cases.json"), "w") as f:
+        json.dump(dict(seed=seed, n=n, names=list(orw.REWARD_NAMES),
+                       expected=[[repr(float(x)) for x in row] for row in ref],
+                       claims_seed=seed + 1, claims_n=400, claims=[repr(c) for c in claims]), f)
+    print("parse_cases.json", ref.shape, "nonzero per column", (ref != 0).sum(0),
+          "claims", sum(len(c) for c in claims))
+
+
 if __name__ == "__main__":
+    gen_parse()
     gen_logps()
     gen_rewards()
     gen_vstar()

@@ -1,0 +1,75 @@
+// TEST FIXTURE, not a product path: compiles csrc/scan_core.cuh (the K6 scanner, host + device
+// code) with g++ so that the CPU test-suite can fuzz the scanner's logic against Python's
+// re / json / float on the build box, where there is no GPU.  The package never loads this
+// library; the product path is the CUDA kernel in csrc/parse.cu (lib/libo3v.so).
+#include <stdint.h>
+#include <string.h>
+
+#include "../../open-o3-video_b200/csrc/scan_core.cuh"
+
+using namespace o3v::scan;
+
+extern "C" {
+
+// float(str.strip()) on bytes [0, n): 1 = ok
+int scan_host_python_float(const uint8_t* s, int64_t n, int strip_mode, double* out) {
+  int64_t a = 0, b = n;
+  strip_space(s, &a, &b, strip_mode != 0);
+  return python_float(s, a, b, out) ? 1 : 0;
+}
+
+double scan_host_dec(const uint8_t* s, int64_t n, int64_t exp10) { return dec_to_double(s, 0, n, exp10); }
+double scan_host_big(const uint8_t* s, int64_t n, int64_t exp10) { return big_to_double(s, 0, n, exp10); }
+
+int scan_host_json_box(const uint8_t* s, int64_t n, int* n_elems, int* numeric, double* out4) {
+  bool num = false;
+  int ne = 0;
+  double v[4] = {0, 0, 0, 0};
+  const int rc = json_box(s, 0, n, &ne, &num, v);
+  *n_elems = ne;
+  *numeric = num ? 1 : 0;
+  memcpy(out4, v, sizeof(v));
+  return rc;
+}
+
+int64_t scan_host_find(const uint8_t* s, int64_t from, int64_t end, const char* lit) {
+  Lit l{0, 0, (int)strlen(lit)};
+  for (int i = 0; i < l.n; ++i) {
+    if (i < 8) l.lo |= (uint64_t)(uint8_t)lit[i] << (8 * i);
+    else l.hi |= (uint64_t)(uint8_t)lit[i] << (8 * (i - 8));
+  }
+  return find_lit(s, from, end, l);
+}
+
+// same argument block as o3v_parse_args, host pointers
+struct Args {
+  int64_t R, G;
+  int32_t P, C, Bc, Tb;
+  const uint8_t* text; const int64_t* offsets; const int32_t* task;
+  int32_t* flags; double* ans_seg; double* ans_box; int32_t* n_times; double* think_times; int32_t* n_claims;
+  double* claim_t; int32_t* claim_nbox; uint32_t* claim_valid; double* claim_box; int32_t* n_tboxes;
+  uint32_t* tbox_valid; double* think_box; int32_t* overflow;
+};
+
+int scan_host_parse(const Args* ap) {
+  const Args& a = *ap;
+  for (int i = 0; i < 4; ++i) a.overflow[i] = 0;
+  for (int64_t r = 0; r < a.R; ++r) {
+    Caps cap{a.P, a.C, a.Bc, a.Tb};
+    RolloutOut o;
+    o.flags = a.flags + r; o.ans_seg = a.ans_seg + r * 2; o.ans_box = a.ans_box + r * 4;
+    o.n_times = a.n_times + r; o.think_times = a.think_times + r * a.P; o.n_claims = a.n_claims + r;
+    o.claim_t = a.claim_t + r * a.C; o.claim_nbox = a.claim_nbox + r * a.C; o.claim_valid = a.claim_valid + r * a.C;
+    o.claim_box = a.claim_box + r * (int64_t)a.C * a.Bc * 4; o.n_tboxes = a.n_tboxes + r;
+    o.tbox_valid = a.tbox_valid + r; o.think_box = a.think_box + r * (int64_t)a.Tb * 4;
+    Maxima mx;
+    parse_rollout(a.text, a.offsets[r], a.offsets[r + 1], a.task[r / a.G], cap, o, &mx);
+    if (mx.times > a.P && mx.times > a.overflow[0]) a.overflow[0] = mx.times;
+    if (mx.claims > a.C && mx.claims > a.overflow[1]) a.overflow[1] = mx.claims;
+    if (mx.claim_boxes > a.Bc && mx.claim_boxes > a.overflow[2]) a.overflow[2] = mx.claim_boxes;
+    if (mx.think_boxes > a.Tb && mx.think_boxes > a.overflow[3]) a.overflow[3] = mx.think_boxes;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,130 @@
+"""GPU parity of K6 (o3v_parse_completions, csrc/parse.cu) through the C ABI: bit-exact against the oracle
+(oracle/parse.py = the reference's own re / json / float calls) and, end to end with K4, against the golden
+rewards the live reference produced from the same completion text."""
+import json
+import os
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import parse as op
+from oracle import rewards as orw
+
+import scan_host
+from test_parse_cpu import EDGE_TEXTS
+
+pytestmark = pytest.mark.gpu
+
+
+def _device_parse(texts, tasks, G=1, caps=None, sync=True):
+    from open_o3_video_b200 import rewards
+    text, offsets = rewards.encode_completions(texts)
+    task = torch.tensor([rewards.TASK_IDS[t] for t in tasks[::G]], dtype=torch.int32).cuda()
+    rows, caps = rewards.parse_completions_device(text.cuda(), offsets.cuda(), task, G, caps, sync)
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in rows.items()}, caps
+
+
+def _check(texts, tasks, G=1, caps=None):
+    got, caps = _device_parse(texts, tasks, G, caps)
+    exp = op.pack([op.parse_text(t, k) for t, k in zip(texts, tasks)], caps["P"], caps["C"], caps["Bc"], caps["Tb"])
+    bad = scan_host.mismatches(got, exp, op.used_mask(exp))
+    assert not bad, [(r, k, texts[r][:100]) for r, k in sorted(bad)[:5]]
+    return got, exp, caps
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_parse_bit_exact_on_wild_text(seed):
+    texts, tasks = op.synth_batch(8000, seed)
+    got, exp, caps = _check(texts, tasks)
+    assert (exp["n_claims"] > 0).sum() > 400 and (exp["n_times"] > 0).sum() > 1500
+
+
+@pytest.mark.parametrize("task", op.TASKS)
+def test_parse_edge_cases(task):
+    _check(EDGE_TEXTS, [task] * len(EDGE_TEXTS))
+
+
+def test_parse_alignment_and_long_text():
+    texts = []
+    for pad in list(range(0, 40)) + [495, 496, 505, 511, 512, 513, 1023, 1024, 1030, 70000]:
+        texts.append("p" * pad + "<think>" + "q" * (pad % 7) + "<t>%d.5</t>s" % pad + "</think>" + "r" * pad
+                     + "<answer>From <t>1</t>s to <t>%d</t>s</answer>" % pad)
+    got, exp, _ = _check(texts, ["temporal QA"] * len(texts))
+    assert (got["n_times"] == 1).all()
+
+
+def test_parse_overflow_relaunch_and_report():
+    texts, tasks = op.synth_batch(2000, 9)
+    # sync=False: one launch, rows truncated at the capacities, true counts and the overflow report
+    small = dict(P=2, C=1, Bc=1, Tb=1)
+    got, _ = _device_parse(texts, tasks, caps=small, sync=False)
+    exp = op.pack([op.parse_text(t, k) for t, k in zip(texts, tasks)], 2, 1, 1, 1)
+    assert not scan_host.mismatches({k: got[k] for k in exp}, exp, op.used_mask(exp))
+    assert got["overflow"][0] == exp["n_times"].max() and got["overflow"][1] == exp["n_claims"].max()
+    # sync=True grows the rows until everything fits
+    got, exp, caps = _check(texts, tasks, caps=small)
+    assert caps["P"] >= exp["n_times"].max() and caps["C"] >= exp["n_claims"].max()
+
+
+def test_parse_empty_and_ragged():
+    from open_o3_video_b200 import rewards
+    got, _ = _device_parse([], [])
+    assert got["flags"].shape == (0,)
+    got, exp, _ = _check(["", "", "<think></think>", ""], ["visual QA"] * 4)
+    assert got["flags"].tolist() == [0, 0, 1, 0]
+    with pytest.raises(RuntimeError):
+        rewards.parse_completions_device(torch.zeros(16, dtype=torch.uint8), torch.zeros(1, dtype=torch.int64),
+                                         torch.zeros(1, dtype=torch.int32))
+
+
+def test_parse_c4_scale_properties():
+    """65 536 rollouts (BASELINE config 4 scale): oracle on a subset, permutation equivariance on the rest."""
+    base, tasks = op.synth_batch(4096, 33, wild=False)
+    reps = 16
+    texts, tk = base * reps, tasks * reps
+    got, caps = _device_parse(texts, tk)
+    exp = op.pack([op.parse_text(t, k) for t, k in zip(base, tasks)], caps["P"], caps["C"], caps["Bc"], caps["Tb"])
+    m = op.used_mask(exp)
+    for rep in (0, 7, 15):
+        sl = {k: got[k][rep * 4096:(rep + 1) * 4096] for k in exp}
+        assert not scan_host.mismatches(sl, exp, m)
+    perm = np.random.RandomState(0).permutation(len(texts))
+    got_p, _ = _device_parse([texts[i] for i in perm], [tk[i] for i in perm], caps=caps)
+    for k in ("flags", "n_times", "n_claims", "n_tboxes"):
+        assert np.array_equal(got_p[k], got[k][perm])
+
+
+def test_text_to_rewards_matches_golden_reference(golden_dir):
+    """K6 + K4 through the reference-named callables == the live reference's rewards on the same text."""
+    from open_o3_video_b200 import rewards
+    g = json.load(open(os.path.join(golden_dir, "parse_cases.json")))
+    cases = op.text_cases(g["n"], g["seed"])
+    exp = np.array([[float(x) for x in row] for row in g["expected"]])
+    got = np.zeros_like(exp)
+    fns = [rewards.reward_funcs_registry[n] for n in g["names"]]
+    for i, (text, kw) in enumerate(cases[:300]):              # one rollout per call, as the golden was made
+        completions = [[{"role": "assistant", "content": text}]]
+        kwargs = {k: [v] for k, v in kw.items()}
+        for j, fn in enumerate(fns):
+            got[i, j] = fn(prompts=None, completions=completions, **kwargs)[0]
+    np.testing.assert_allclose(got[:300], exp[:300], rtol=0, atol=1e-6)     # north_star: rewards within 1e-6
+    assert np.array_equal(got[:300, [0, 1, 2, 4]], exp[:300, [0, 1, 2, 4]])  # IoU / ratio columns are exact
+    # batched: all cases of one task in a single call (GT differs per rollout, G = 1)
+    from collections import defaultdict
+    by_task = defaultdict(list)
+    for i, (text, kw) in enumerate(cases):
+        by_task[(kw["task"], kw["step_percent"])].append(i)
+    for (task, step), idx in by_task.items():
+        contents = [cases[i][0] for i in idx]
+        gts = []
+        for i in idx:
+            kw = cases[i][1]
+            seg, vbox = rewards.parse_gt_answer(task, kw["answer"])
+            gts.append(dict(task=task, step_percent=step, gt_seg=seg, gt_vbox=vbox, key_frames=kw["key_frames"],
+                            key_items=kw["key_items"], image_size=kw["image_size"],
+                            image_size_refine=kw["image_size_refine"]))
+        out = rewards.rewards_from_text(contents, gts, 1).cpu().numpy()
+        np.testing.assert_allclose(out, exp[idx], rtol=0, atol=1e-6)

@@ -56,6 +56,27 @@ out = torch.empty(dims["R"], 5, dtype=torch.float64, device=dev)
 nbytes = rewards.soa_bytes(arrays) + out.numel() * 8
 line("K4 grounded rewards c4 (65536 x 16, %.0f B/rollout)" % (nbytes / dims["R"]), nbytes,
      lambda: rewards.grounded_rewards_device(dev_arrays, dims, out))
+# K6 at the same scale: the 65536 rollouts rendered to completion text, scanned on the device
+import time  # noqa: E402
+from oracle import parse as oparse, rewards as orw  # noqa: E402
+texts = [orw.render(r)[0] for r in ro]
+text, offsets = rewards.encode_completions(texts)
+d_text, d_off = text.to(dev), offsets.to(dev)
+d_task = dev_arrays["task"]
+rows, caps = rewards.parse_completions_device(d_text, d_off, d_task, 8)
+n_text = int(offsets[-1])
+written = int(dims["R"] * 20 + (rows["n_times"].sum() * 8 + rows["n_claims"].sum() * 16).item()
+              + (rows["claim_nbox"] * (torch.arange(caps["C"], device=dev)[None, :] < rows["n_claims"][:, None])).sum().item() * 32)
+line("K6 parse completions c4 (65536 rollouts, %.0f B text/rollout, rows P=%d C=%d Bc=%d)" %
+     (n_text / dims["R"], caps["P"], caps["C"], caps["Bc"]), n_text + written,
+     lambda: rewards.parse_completions_device(d_text, d_off, d_task, 8, caps, sync=False))
+t0 = time.perf_counter()
+for tx, r in zip(texts[:4096], ro[:4096]):
+    oparse.parse_text(tx, r["task"])
+dt = time.perf_counter() - t0
+print(json.dumps(dict(kernel="K6 cpu baseline: reference regex/json/float path (oracle port, 1 core)",
+                      sample="4096 of the 65536 rollouts", rollouts_per_s=4096 / dt,
+                      text_mb_per_s=sum(len(t) for t in texts[:4096]) / dt / 1e6)), flush=True)
 # dlogits / merge at the bench chunk
 T, V = 8192, 152064
 z = torch.randn(T, V, device=dev, generator=g, dtype=torch.bfloat16)
