@@ -269,7 +269,6 @@ int o3v_vstar_scores(const o3v_vstar_soa* soa, double* out, void* stream);
  *            largest count that did not fit (0 = everything fitted; the caller re-runs with
  *            larger rows).  overflow = (think times, claims, boxes per claim, think boxes).
  *   outputs  rows are written only up to the counts (no zero fill).
- * workspace: o3v_parse_workspace_bytes() bytes, 8-byte aligned (work ticket).
  * ---------------------------------------------------------------------------------- */
 typedef struct o3v_parse_args {
   int64_t R;
@@ -294,8 +293,7 @@ typedef struct o3v_parse_args {
   int32_t* overflow;     /* [4] */
 } o3v_parse_args;
 
-size_t o3v_parse_workspace_bytes(void);
-int o3v_parse_completions(const o3v_parse_args* args, void* workspace, size_t workspace_bytes, void* stream);
+int o3v_parse_completions(const o3v_parse_args* args, void* stream);
 
 #ifdef __cplusplus
 }

@@ -14,10 +14,10 @@
 // Python's float() and json.loads produce) and box payloads through a JSON recogniser that accepts
 // what CPython's C scanner accepts.
 //
-// Everything here is `O3V_HD` (host + device).  The device build runs one WARP per rollout:
-// literal searches are warp-cooperative (16 bytes per lane, 512 bytes per step); the short
-// sequential pieces (number tokens, box payloads) are executed redundantly by all lanes on
-// broadcast loads, and lane 0 stores.  The host build of this same header exists only so that
+// Everything here is `O3V_HD` (host + device).  The device build runs one THREAD per rollout (the
+// batch supplies the parallelism: 65 536 rollouts at BASELINE config 4): literal searches step 16
+// bytes at a time with byte-SIMD compares, the short sequential pieces (number tokens, box
+// payloads) walk bytes that the search already pulled into L1.  The host build of this same header exists only so that
 // tests can fuzz the logic against Python on the CPU box (tests/hostbuild/); the product path is
 // the kernel in parse.cu.
 #pragma once
@@ -103,38 +103,48 @@ O3V_HD bool lit_at(const uint8_t* t, int64_t p, int64_t end, const Lit& l) {
 }
 
 // First p in [from, end - n] with t[p .. p+n) == literal, else -1.
-// Device: called by all 32 lanes of a warp with identical arguments; `t` is the 16-byte aligned
-// base of the whole text buffer (positions are absolute), padded to a multiple of 16 bytes.
+// Device: `t` is the 16-byte aligned base of the whole text buffer (positions are absolute) and the
+// buffer is padded to a multiple of 16 bytes; a thread compares 16 positions per step against the
+// first two bytes of the needle with byte-SIMD ops and verifies the rare survivors.
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ uint32_t eq_mask16(const uint4& v, uint32_t c4) {   // bit i: byte i == c
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  uint32_t m = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    m |= ((((__vcmpeq4(w[i], c4) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << (4 * i);
+  return m;
+}
+#endif
 O3V_HD int64_t find_lit(const uint8_t* t, int64_t from, int64_t end, const Lit& l) {
   const int64_t last = end - l.n;
   if (from < 0) return -1;
   if (from > last) return -1;
 #if defined(__CUDA_ARCH__)
-  const int lane = threadIdx.x & 31;
-  const uint32_t c0 = (uint32_t)(l.lo & 0xff) * 0x01010101u;
-  for (int64_t base = from & ~(int64_t)15; base <= last; base += 512) {
-    const int64_t p0 = base + lane * 16;
-    uint32_t best = 0xffffffffu;
-    if (p0 <= last) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(t + p0));
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-      uint32_t m = 0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t eq = __vcmpeq4(w[i], c0);   // 0xff per equal byte
-        m |= (((eq >> 7) & 1u) | ((eq >> 14) & 2u) | ((eq >> 21) & 4u) | ((eq >> 28) & 8u)) << (4 * i);
-      }
+  const uint32_t c0 = (uint32_t)(l.lo & 0xff) * 0x01010101u, c1 = (uint32_t)((l.lo >> 8) & 0xff) * 0x01010101u;
+  int64_t base = from & ~(int64_t)15;
+  uint4 v = *reinterpret_cast<const uint4*>(t + base);
+  uint32_t keep = 0xffffu << (int)(from - base);             // drop positions before `from`
+  for (;;) {
+    uint32_t m = eq_mask16(v, c0) & keep;
+    const bool more = base + 16 <= last;
+    uint4 nx = v;
+    if (more || (m != 0 && base + 16 < end)) nx = *reinterpret_cast<const uint4*>(t + base + 16);
+    if (m != 0) {
+      if (l.n > 1) m &= (eq_mask16(v, c1) | (eq_mask16(nx, c1) << 16)) >> 1;
       while (m) {
         const int j = __ffs(m) - 1;
         m &= m - 1;
-        const int64_t p = p0 + j;
-        if (p >= from && p <= last && lit_at(t, p, end, l)) { best = (uint32_t)(p - base); break; }
+        const int64_t p = base + j;
+        if (p > last) break;
+        if (lit_at(t, p, end, l)) return p;
       }
     }
-    best = __reduce_min_sync(0xffffffffu, best);
-    if (best != 0xffffffffu) return base + best;
+    if (!more) return -1;
+    base += 16;
+    v = nx;
+    keep = 0xffffu;
   }
-  return -1;
 #else
   const uint8_t c0 = lit_byte(l, 0);
   for (int64_t p = from; p <= last; ++p)
@@ -724,11 +734,7 @@ struct RolloutOut {            // pointers to THIS rollout's rows (o3v_rewards_s
 };
 struct Maxima { int times, claims, claim_boxes, think_boxes; };
 
-#if defined(__CUDA_ARCH__)
-#define O3V_LANE0 ((threadIdx.x & 31) == 0)
-#else
 #define O3V_LANE0 true
-#endif
 
 constexpr int kFlagThink = 1, kFlagAnswer = 2, kFlagAnsSeg = 4, kFlagAnsBox = 8;
 constexpr int kTaskVisual = 0, kTaskTemporal = 1, kTaskTemporalMcq = 2;
