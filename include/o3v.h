@@ -264,11 +264,14 @@ int o3v_vstar_scores(const o3v_vstar_soa* soa, double* out, void* stream);
  *            must be readable up to the next multiple of 16 bytes past offsets[R]
  *   offsets  [R + 1] int64 byte offsets (offsets[0] = 0 is not required)
  *   task     [Q = R / G] O3V_TASK_* of each prompt (kwargs['task'][0] of its batch)
- *   P, C, Bc, Tb  capacities of the output rows (as in o3v_rewards_soa).  Counts are always the
- *            TRUE counts; entries beyond a capacity are dropped and overflow[i] reports the
- *            largest count that did not fit (0 = everything fitted; the caller re-runs with
- *            larger rows).  overflow = (think times, claims, boxes per claim, think boxes).
- *   outputs  rows are written only up to the counts (no zero fill).
+ *   P, C, Bc, Tb  capacities (>= 1) of the output rows (as in o3v_rewards_soa).  If a rollout holds
+ *            more candidates than a capacity, overflow[i] reports a count that fits (0 = everything
+ *            fitted) and that rollout's rows / counts are incomplete: re-run with larger rows.
+ *            overflow = (think times, claims, boxes per claim, think boxes).
+ *   outputs  rows are written only up to the counts (no zero fill); slots past a count may hold
+ *            scratch values.
+ * workspace: o3v_parse_workspace_bytes(R) bytes, 8-byte aligned (per-rollout records passed between
+ * the three launches: span ends, candidate counts).
  * ---------------------------------------------------------------------------------- */
 typedef struct o3v_parse_args {
   int64_t R;
@@ -293,7 +296,8 @@ typedef struct o3v_parse_args {
   int32_t* overflow;     /* [4] */
 } o3v_parse_args;
 
-int o3v_parse_completions(const o3v_parse_args* args, void* stream);
+size_t o3v_parse_workspace_bytes(int64_t R);
+int o3v_parse_completions(const o3v_parse_args* args, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,25 +1,24 @@
 // K6: completion text -> rollout side of o3v_rewards_soa, on the GPU.
 //
-// One thread per rollout over UTF-8 bytes that are already in HBM; see scan_core.cuh for the
-// scanner and for the reference lines it replaces.  HBM-bound byte work: the text is read once
-// from DRAM (every later touch of a span hits L1), outputs are written only up to the counts
-// found.  The lanes of a warp walk 32 different completions, so loads are per-lane 16-byte
-// vectors out of 32 different cache lines; the lines stay in L1 until their thread has consumed
-// them (a few hundred bytes of window per thread).
+// Three launches over UTF-8 bytes that are already in HBM (scan_core.cuh has the scanner and the
+// reference lines it replaces):
+//   A  parse_scan_kernel     one warp per rollout: warp-cooperative literal searches resolve the
+//                            <think>/<answer> spans and the regex match chains -> candidate ranges
+//   B  parse_convert_kernel  one thread per candidate: decimal -> binary64, JSON box payloads
+//   C  parse_finish_kernel   one thread per rollout: drop rejected candidates, compact, counts
+// HBM-bound byte work in principle (the text is read once from DRAM in A; B re-reads the few
+// bytes of each candidate out of L2); in practice bound by dependent byte loads of the sequential
+// number / JSON routines, which is why those run one candidate per THREAD instead of per warp.
 #include "common.cuh"
 #include "scan_core.cuh"
 
 namespace o3v {
 
-constexpr int kParseThreads = 128;
+constexpr int kScanWarps = 8;        // phase A: rollouts per CTA
+constexpr int kConvertThreads = 128; // phase B
+constexpr int kFinishThreads = 128;  // phase C
 
-__global__ void __launch_bounds__(kParseThreads, 4)
-parse_kernel(const o3v_parse_args a) {
-  const int64_t r = (int64_t)blockIdx.x * kParseThreads + threadIdx.x;
-  if (r >= a.R) return;
-  const int64_t beg = a.offsets[r], end = a.offsets[r + 1];
-  const int task = a.task[r / a.G];
-  scan::Caps cap{a.P, a.C, a.Bc, a.Tb};
+__device__ __forceinline__ scan::RolloutOut rows_of(const o3v_parse_args& a, int64_t r) {
   scan::RolloutOut o;
   o.flags = a.flags + r;
   o.ans_seg = a.ans_seg + r * 2;
@@ -34,37 +33,76 @@ parse_kernel(const o3v_parse_args a) {
   o.n_tboxes = a.n_tboxes + r;
   o.tbox_valid = a.tbox_valid + r;
   o.think_box = a.think_box + r * (int64_t)a.Tb * 4;
-  scan::Maxima mx;
-  scan::parse_rollout(a.text, beg, end, task, cap, o, &mx);
-  // rare: only counts that did not fit are published
-  if (mx.times > a.P) atomicMax(a.overflow + 0, mx.times);
-  if (mx.claims > a.C) atomicMax(a.overflow + 1, mx.claims);
-  if (mx.claim_boxes > a.Bc) atomicMax(a.overflow + 2, mx.claim_boxes);
-  if (mx.think_boxes > a.Tb) atomicMax(a.overflow + 3, mx.think_boxes);
+  return o;
+}
+
+__global__ void __launch_bounds__(kScanWarps * 32, 4)
+parse_scan_kernel(const o3v_parse_args a, scan::Scratch* __restrict__ scratch) {
+  const int64_t r = (int64_t)blockIdx.x * kScanWarps + (threadIdx.x >> 5);
+  if (r >= a.R) return;                      // whole warp leaves together
+  const scan::Caps cap{a.P, a.C, a.Bc, a.Tb};
+  scan::scan_rollout(a.text, a.offsets[r], a.offsets[r + 1], a.task[r / a.G], cap, rows_of(a, r), scratch + r);
+}
+
+__global__ void __launch_bounds__(kConvertThreads, 4)
+parse_convert_kernel(const o3v_parse_args a, scan::Scratch* __restrict__ scratch) {
+  const scan::Caps cap{a.P, a.C, a.Bc, a.Tb};
+  const int per = scan::items_per_rollout(cap);
+  const int64_t idx = (int64_t)blockIdx.x * kConvertThreads + threadIdx.x;
+  const int64_t r = idx / per;
+  if (r >= a.R) return;
+  scan::convert_item(a.text, (int)(idx - r * per), cap, rows_of(a, r), scratch + r);
+}
+
+__global__ void __launch_bounds__(kFinishThreads)
+parse_finish_kernel(const o3v_parse_args a, const scan::Scratch* __restrict__ scratch) {
+  const int64_t r = (int64_t)blockIdx.x * kFinishThreads + threadIdx.x;
+  if (r >= a.R) return;
+  const scan::Caps cap{a.P, a.C, a.Bc, a.Tb};
+  int over[4];
+  scan::finish_rollout(cap, rows_of(a, r), scratch + r, over);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)                // rare: only counts that did not fit are published
+    if (over[i]) atomicMax(a.overflow + i, over[i]);
 }
 
 }  // namespace o3v
 
-extern "C" int o3v_parse_completions(const o3v_parse_args* args, void* stream) {
+extern "C" size_t o3v_parse_workspace_bytes(int64_t R) {
+  return (size_t)(R > 0 ? R : 0) * sizeof(o3v::scan::Scratch);
+}
+
+extern "C" int o3v_parse_completions(const o3v_parse_args* args, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+  static_assert(sizeof(o3v::scan::Scratch) == 40, "scratch record layout");
   if (!args) return O3V_ERR_INVALID_ARG;
   const o3v_parse_args& a = *args;
   if (a.R < 0 || a.G <= 0 || (a.R % a.G) != 0) return O3V_ERR_INVALID_ARG;
-  if (a.P < 0 || a.C < 0 || a.Bc < 0 || a.Bc > 32 || a.Tb < 0 || a.Tb > 32) return O3V_ERR_INVALID_ARG;
+  if (a.P < 1 || a.C < 1 || a.Bc < 1 || a.Bc > 32 || a.Tb < 1 || a.Tb > 32) return O3V_ERR_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
   if (a.R == 0) {
-    if (a.overflow) O3V_CUDA_TRY(cudaMemsetAsync(a.overflow, 0, 4 * sizeof(int32_t), (cudaStream_t)stream));
+    if (a.overflow) O3V_CUDA_TRY(cudaMemsetAsync(a.overflow, 0, 4 * sizeof(int32_t), st));
     return O3V_OK;
   }
   if (!a.text || !a.offsets || !a.task || !a.flags || !a.ans_seg || !a.ans_box || !a.n_times || !a.think_times ||
       !a.n_claims || !a.claim_t || !a.claim_nbox || !a.claim_valid || !a.claim_box || !a.n_tboxes ||
       !a.tbox_valid || !a.think_box || !a.overflow)
     return O3V_ERR_INVALID_ARG;
-  if ((uintptr_t)a.text & 15u) return O3V_ERR_ALIGNMENT;
+  if (((uintptr_t)a.text & 15u) || ((uintptr_t)workspace & 7u)) return O3V_ERR_ALIGNMENT;
+  if (!workspace || workspace_bytes < o3v_parse_workspace_bytes(a.R)) return O3V_ERR_WORKSPACE;
   int rc = o3v::check_device();
   if (rc) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
+  auto* scratch = reinterpret_cast<o3v::scan::Scratch*>(workspace);
   O3V_CUDA_TRY(cudaMemsetAsync(a.overflow, 0, 4 * sizeof(int32_t), st));
-  const unsigned grid = (unsigned)((a.R + o3v::kParseThreads - 1) / o3v::kParseThreads);
-  o3v::parse_kernel<<<grid, o3v::kParseThreads, 0, st>>>(a);
+  const unsigned grid_a = (unsigned)((a.R + o3v::kScanWarps - 1) / o3v::kScanWarps);
+  o3v::parse_scan_kernel<<<grid_a, o3v::kScanWarps * 32, 0, st>>>(a, scratch);
+  O3V_LAUNCH_CHECK();
+  const int64_t items = a.R * (int64_t)(a.P + a.C + a.Tb + 2);
+  const unsigned grid_b = (unsigned)((items + o3v::kConvertThreads - 1) / o3v::kConvertThreads);
+  o3v::parse_convert_kernel<<<grid_b, o3v::kConvertThreads, 0, st>>>(a, scratch);
+  O3V_LAUNCH_CHECK();
+  const unsigned grid_c = (unsigned)((a.R + o3v::kFinishThreads - 1) / o3v::kFinishThreads);
+  o3v::parse_finish_kernel<<<grid_c, o3v::kFinishThreads, 0, st>>>(a, scratch);
   O3V_LAUNCH_CHECK();
   return O3V_OK;
 }

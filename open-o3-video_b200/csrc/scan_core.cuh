@@ -14,12 +14,16 @@
 // Python's float() and json.loads produce) and box payloads through a JSON recogniser that accepts
 // what CPython's C scanner accepts.
 //
-// Everything here is `O3V_HD` (host + device).  The device build runs one THREAD per rollout (the
-// batch supplies the parallelism: 65 536 rollouts at BASELINE config 4): literal searches step 16
-// bytes at a time with byte-SIMD compares, the short sequential pieces (number tokens, box
-// payloads) walk bytes that the search already pulled into L1.  The host build of this same header exists only so that
-// tests can fuzz the logic against Python on the CPU box (tests/hostbuild/); the product path is
-// the kernel in parse.cu.
+// Everything here is `O3V_HD` (host + device).  The device build (parse.cu) runs three phases so
+// that no phase leaves SIMT lanes idle behind divergent nested loops:
+//   A  scan_rollout   one WARP per rollout: warp-cooperative literal searches (16 bytes per lane,
+//                     512 bytes per step) resolve the spans and the regex match chains and record
+//                     CANDIDATES as byte ranges (packed into the output rows themselves);
+//   B  convert_item   one THREAD per candidate: the sequential number / JSON routines, every lane
+//                     of a warp running the same routine on its own range;
+//   C  finish_rollout one thread per rollout: drops rejected candidates, compacts, final counts.
+// The host build of this same header (tests/hostbuild/) runs A, B, C in plain loops so that the
+// CPU tests can fuzz the logic against Python; the product path is the CUDA build.
 #pragma once
 #include <stdint.h>
 
@@ -103,48 +107,36 @@ O3V_HD bool lit_at(const uint8_t* t, int64_t p, int64_t end, const Lit& l) {
 }
 
 // First p in [from, end - n] with t[p .. p+n) == literal, else -1.
-// Device: `t` is the 16-byte aligned base of the whole text buffer (positions are absolute) and the
-// buffer is padded to a multiple of 16 bytes; a thread compares 16 positions per step against the
-// first two bytes of the needle with byte-SIMD ops and verifies the rare survivors.
-#if defined(__CUDA_ARCH__)
-__device__ __forceinline__ uint32_t eq_mask16(const uint4& v, uint32_t c4) {   // bit i: byte i == c
-  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-  uint32_t m = 0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-    m |= ((((__vcmpeq4(w[i], c4) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << (4 * i);
-  return m;
-}
-#endif
+// Device: called by all 32 lanes of a warp with identical arguments (phase A); `t` is the 16-byte
+// aligned base of the whole text buffer (positions are absolute), padded to a multiple of 16 bytes.
 O3V_HD int64_t find_lit(const uint8_t* t, int64_t from, int64_t end, const Lit& l) {
   const int64_t last = end - l.n;
   if (from < 0) return -1;
   if (from > last) return -1;
 #if defined(__CUDA_ARCH__)
-  const uint32_t c0 = (uint32_t)(l.lo & 0xff) * 0x01010101u, c1 = (uint32_t)((l.lo >> 8) & 0xff) * 0x01010101u;
-  int64_t base = from & ~(int64_t)15;
-  uint4 v = *reinterpret_cast<const uint4*>(t + base);
-  uint32_t keep = 0xffffu << (int)(from - base);             // drop positions before `from`
-  for (;;) {
-    uint32_t m = eq_mask16(v, c0) & keep;
-    const bool more = base + 16 <= last;
-    uint4 nx = v;
-    if (more || (m != 0 && base + 16 < end)) nx = *reinterpret_cast<const uint4*>(t + base + 16);
-    if (m != 0) {
-      if (l.n > 1) m &= (eq_mask16(v, c1) | (eq_mask16(nx, c1) << 16)) >> 1;
+  const int lane = threadIdx.x & 31;
+  const uint32_t c0 = (uint32_t)(l.lo & 0xff) * 0x01010101u;
+  for (int64_t base = from & ~(int64_t)15; base <= last; base += 512) {
+    const int64_t p0 = base + lane * 16;
+    uint32_t best = 0xffffffffu;
+    if (p0 <= last) {
+      const uint4 v = *reinterpret_cast<const uint4*>(t + p0);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      uint32_t m = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)   // bit j: byte j of the 16 equals the needle's first byte
+        m |= ((((__vcmpeq4(w[i], c0) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << (4 * i);
       while (m) {
         const int j = __ffs(m) - 1;
         m &= m - 1;
-        const int64_t p = base + j;
-        if (p > last) break;
-        if (lit_at(t, p, end, l)) return p;
+        const int64_t p = p0 + j;
+        if (p >= from && p <= last && lit_at(t, p, end, l)) { best = (uint32_t)(p - base); break; }
       }
     }
-    if (!more) return -1;
-    base += 16;
-    v = nx;
-    keep = 0xffffu;
+    best = __reduce_min_sync(0xffffffffu, best);
+    if (best != 0xffffffffu) return base + best;
   }
+  return -1;
 #else
   const uint8_t c0 = lit_byte(l, 0);
   for (int64_t p = from; p <= last; ++p)
@@ -724,7 +716,7 @@ O3V_HD int json_box(const uint8_t* t, int64_t s, int64_t e, int* n_elems, bool* 
 }
 
 // ------------------------------------------------------------------------------------------
-// One rollout.
+// One rollout, in three phases.
 // ------------------------------------------------------------------------------------------
 struct Caps { int P, C, Bc, Tb; };
 struct RolloutOut {            // pointers to THIS rollout's rows (o3v_rewards_soa layout)
@@ -732,35 +724,69 @@ struct RolloutOut {            // pointers to THIS rollout's rows (o3v_rewards_s
   int32_t* n_claims; double* claim_t; int32_t* claim_nbox; uint32_t* claim_valid; double* claim_box;
   int32_t* n_tboxes; uint32_t* tbox_valid; double* think_box;
 };
-struct Maxima { int times, claims, claim_boxes, think_boxes; };
+// Per-rollout scratch between the phases (caller-provided workspace, 40 bytes per rollout).
+struct Scratch {
+  int64_t think_end, answer_end;
+  int32_t time_cands, claim_cands, tbox_cands;
+  uint32_t tbox_kept, tbox_numeric;   // bit j: candidate j is JSON / is a 4-number box
+  int32_t pad_;
+};
 
+#if defined(__CUDA_ARCH__)
+#define O3V_LANE0 ((threadIdx.x & 31) == 0)
+#else
 #define O3V_LANE0 true
+#endif
 
 constexpr int kFlagThink = 1, kFlagAnswer = 2, kFlagAnsSeg = 4, kFlagAnsBox = 8;
 constexpr int kTaskVisual = 0, kTaskTemporal = 1, kTaskTemporalMcq = 2;
 
+// A candidate is a byte range of the text, stored in the double slot its value will occupy:
+// start in the high 40 bits, length in the low 24 (a completion is shorter than 16 MiB).
+constexpr int64_t kMaxRange = (1 << 24) - 1;
+O3V_HD double pack_range(int64_t s, int64_t e) {
+  int64_t n = e - s;
+  if (n > kMaxRange) n = kMaxRange;       // cannot be a number; rejected in phase B
+  return bits_to_double(((uint64_t)s << 24) | (uint64_t)n);
+}
+O3V_HD void unpack_range(double d, int64_t* s, int64_t* e) {
+#if defined(__CUDA_ARCH__)
+  const uint64_t u = (uint64_t)__double_as_longlong(d);
+#else
+  union { double d; uint64_t u; } c;
+  c.d = d;
+  const uint64_t u = c.u;
+#endif
+  *s = (int64_t)(u >> 24);
+  *e = *s + (int64_t)(u & 0xFFFFFF);
+}
+// phase B -> C status of a think-time candidate (real values are >= 0 or +inf)
+constexpr double kTimeNoMatch = -1.0, kTimeBadFloat = -2.0;
+
 // `<box>(\[.*?\])</box>` without DOTALL at or after p inside [.., lim): on success the payload is
 // [*bs, *be) (brackets included) and the return value is the end of the match; -1 if no match.
+// '.' does not cross a newline: a candidate whose first "]</box>" lies behind a newline fails, and so
+// does every candidate before that newline.
 O3V_HD int64_t next_box(const uint8_t* t, int64_t p, int64_t lim, int64_t* bs, int64_t* be) {
-  constexpr Lit kOpen = make_lit("<box>["), kClose = make_lit("</box>");
+  constexpr Lit kOpen = make_lit("<box>["), kClose = make_lit("]</box>"), kNewline = make_lit("\n");
   for (;;) {
     p = find_lit(t, p, lim, kOpen);
     if (p < 0) return -1;
-    for (int64_t i = p + 6; i < lim; ++i) {
-      const uint8_t c = t[i];
-      if (c == '\n') break;                                // '.' does not cross a newline
-      if (c == ']' && lit_at(t, i + 1, lim, kClose)) {
-        *bs = p + 5;
-        *be = i + 1;
-        return i + 7;
-      }
+    const int64_t c = find_lit(t, p + 6, lim, kClose);
+    if (c < 0) return -1;
+    const int64_t nl = find_lit(t, p + 6, c, kNewline);
+    if (nl < 0) {
+      *bs = p + 5;
+      *be = c + 1;
+      return c + 7;
     }
-    ++p;                                                   // the regex retries one character later
+    p = nl + 1;
   }
 }
 
-O3V_HD void parse_rollout(const uint8_t* t, int64_t beg, int64_t end, int task, const Caps& cap,
-                          const RolloutOut& o, Maxima* mx) {
+// ---- phase A: spans and match chains -> candidates (device: warp-uniform, lane 0 stores)
+O3V_HD void scan_rollout(const uint8_t* t, int64_t beg, int64_t end, int task, const Caps& cap,
+                         const RolloutOut& o, Scratch* sc) {
   constexpr Lit kThinkO = make_lit("<think>"), kThinkC = make_lit("</think>"), kAnsO = make_lit("<answer>"),
                 kAnsC = make_lit("</answer>"), kT = make_lit("<t>"), kTEnd = make_lit("</t>s"),
                 kTo = make_lit("</t>s to <t>"), kObj = make_lit("<obj>"), kObjBox = make_lit("</obj><box>["),
@@ -776,7 +802,8 @@ O3V_HD void parse_rollout(const uint8_t* t, int64_t beg, int64_t end, int task, 
   if (has_think) flags |= kFlagThink;
   if (has_answer) flags |= kFlagAnswer;
 
-  // ---- answer "<t>a</t>s to <t>b</t>s" (:119, temporal tasks)
+  // ---- answer "<t>a</t>s to <t>b</t>s" (:119, temporal tasks): the first <t> at which the whole
+  // pattern matches; the two number ranges are converted in phase B
   if ((task == kTaskTemporal || task == kTaskTemporalMcq) && has_answer) {
     int64_t p = as;
     while ((p = find_lit(t, p, ae, kT)) >= 0) {
@@ -785,8 +812,7 @@ O3V_HD void parse_rollout(const uint8_t* t, int64_t beg, int64_t end, int task, 
         const int64_t b0 = a1 + 12, b1 = scan_simple_decimal(t, b0, ae);
         if (b1 >= 0 && lit_at(t, b1, ae, kTEnd)) {
           flags |= kFlagAnsSeg;
-          const double a = dec_to_double(t, a0, a1, 0), b = dec_to_double(t, b0, b1, 0);
-          if (O3V_LANE0) { o.ans_seg[0] = a; o.ans_seg[1] = b; }
+          if (O3V_LANE0) { o.ans_seg[0] = pack_range(a0, a1); o.ans_seg[1] = pack_range(b0, b1); }
           break;
         }
       }
@@ -794,61 +820,39 @@ O3V_HD void parse_rollout(const uint8_t* t, int64_t beg, int64_t end, int task, 
     }
   }
 
-  // ---- every "<t>x</t>s" inside <think> (:405-412, :447-449); one bad float() empties the list
-  int n_times = 0;
+  // ---- every "<t>" inside <think> is a candidate for "<t>x</t>s" (:405-412, :447-449); a match
+  // contains no second "<t>", so the candidates of findall's matches are exactly these, in order
+  int n_time = 0, n_tbox = 0, n_claim = 0;
   if (has_think) {
-    bool all_ok = true;
     int64_t p = ts;
     while ((p = find_lit(t, p, te, kT)) >= 0) {
-      bool ok;
-      const int64_t x0 = p + 3, x1 = scan_digits_dots(t, x0, te, &ok);
-      if (x1 > x0 && lit_at(t, x1, te, kTEnd)) {
-        if (!ok) all_ok = false;
-        else if (all_ok) {
-          const double v = dec_to_double(t, x0, x1, 0);
-          if (n_times < cap.P && O3V_LANE0) o.think_times[n_times] = v;
-        }
-        ++n_times;
-        p = x1 + 5;
-      } else {
-        ++p;
-      }
+      if (n_time < cap.P && O3V_LANE0) o.think_times[n_time] = pack_range(p + 3, p + 3);
+      ++n_time;
+      p += 3;
     }
-    if (!all_ok) n_times = 0;
   }
 
-  int n_tboxes = 0, n_claims = 0, max_cb = 0;
-  uint32_t tvalid = 0;
   if (task == kTaskVisual) {
-    // ---- first <box> of the answer (:211-223)
+    // ---- first <box> of the answer (:211-223); flag provisional until phase B has parsed it
     if (has_answer) {
       int64_t bs, be;
       if (next_box(t, as, ae, &bs, &be) >= 0) {
-        int n; bool numeric; double v[4];
-        if (json_box(t, bs, be, &n, &numeric, v) == kJsonList && n == 4 && numeric) {
-          flags |= kFlagAnsBox;
-          if (O3V_LANE0) { o.ans_box[0] = v[0]; o.ans_box[1] = v[1]; o.ans_box[2] = v[2]; o.ans_box[3] = v[3]; }
-        }
+        flags |= kFlagAnsBox;
+        if (O3V_LANE0) o.ans_box[0] = pack_range(bs, be);
       }
     }
-    // ---- every <box> inside <think> (:505-511); payloads that are not JSON are skipped
+    // ---- every <box> inside <think> (:505-511)
     if (has_think) {
       int64_t p = ts, bs, be;
       while ((p = next_box(t, p, te, &bs, &be)) >= 0) {
-        int n; bool numeric; double v[4];
-        if (json_box(t, bs, be, &n, &numeric, v) != kJsonList) continue;
-        if (n == 4 && numeric && n_tboxes < 32) {
-          tvalid |= 1u << n_tboxes;
-          if (n_tboxes < cap.Tb && O3V_LANE0) {
-            double* dst = o.think_box + 4 * n_tboxes;
-            dst[0] = v[0]; dst[1] = v[1]; dst[2] = v[2]; dst[3] = v[3];
-          }
-        }
-        ++n_tboxes;
+        if (n_tbox < cap.Tb && O3V_LANE0) o.think_box[4 * n_tbox] = pack_range(bs, be);
+        ++n_tbox;
       }
     }
   } else if (has_think) {
-    // ---- claims (:308-335): <obj>(.*?)</obj>((?:<box>\[.*?\]</box>)+)at<t>(.*?)</t>s, DOTALL
+    // ---- claims (:308-335): <obj>(.*?)</obj>((?:<box>\[.*?\]</box>)+)at<t>(.*?)</t>s, DOTALL.
+    // Leftmost match at an <obj>: shortest group 1 = first "</obj><box>[" after it; group 2 ends at
+    // the first "]</box>at<t>" after that; group 3 at the first "</t>s" (DESIGN.md section 8).
     int64_t p = ts;
     for (;;) {
       p = find_lit(t, p, te, kObj);
@@ -860,56 +864,177 @@ O3V_HD void parse_rollout(const uint8_t* t, int64_t beg, int64_t end, int task, 
       const int64_t z = find_lit(t, e + 12, te, kTEnd);
       if (z < 0) break;
       p = z + 5;
-      int64_t fs = e + 12, fe = z;
-      strip_space(t, &fs, &fe, true);
-      double tv;
-      if (!python_float(t, fs, fe, &tv)) continue;          // ValueError -> claim dropped (:332)
-      // boxes: re.findall(r'\[.*?\]', group 2) without DOTALL, group 2 = [q + 6, e + 7)
-      const int64_t g0 = q + 6, g1 = e + 7;
-      int nb = 0;
-      uint32_t valid = 0;
-      bool json_ok = true;
-      double* cbox = o.claim_box + (int64_t)(n_claims < cap.C ? n_claims : 0) * cap.Bc * 4;
-      for (int64_t i = g0; i < g1 && json_ok;) {
-        if (t[i] != '[') { ++i; continue; }
-        int64_t j = i + 1;
-        while (j < g1 && t[j] != ']' && t[j] != '\n') ++j;
-        if (j >= g1) break;
-        if (t[j] == '\n') { i = j + 1; continue; }
-        int n; bool numeric; double v[4];
-        if (json_box(t, i, j + 1, &n, &numeric, v) != kJsonList) { json_ok = false; break; }
-        if (n == 4 && numeric && nb < 32) {
-          valid |= 1u << nb;
-          if (n_claims < cap.C && nb < cap.Bc && O3V_LANE0) {
-            double* dst = cbox + 4 * nb;
-            dst[0] = v[0]; dst[1] = v[1]; dst[2] = v[2]; dst[3] = v[3];
-          }
-        }
-        ++nb;
-        i = j + 1;
+      if (n_claim < cap.C && O3V_LANE0) {
+        o.claim_t[n_claim] = pack_range(e + 12, z);                            // group 3
+        o.claim_box[(int64_t)n_claim * cap.Bc * 4] = pack_range(q + 6, e + 7);  // group 2
       }
-      if (!json_ok) continue;                               // JSONDecodeError -> claim dropped
-      if (n_claims < cap.C && O3V_LANE0) {
-        o.claim_t[n_claims] = tv;
-        o.claim_nbox[n_claims] = nb;
-        o.claim_valid[n_claims] = valid;
-      }
-      if (nb > max_cb) max_cb = nb;
-      ++n_claims;
+      ++n_claim;
     }
   }
 
   if (O3V_LANE0) {
     *o.flags = flags;
-    *o.n_times = n_times;
-    *o.n_claims = n_claims;
-    *o.n_tboxes = n_tboxes;
-    *o.tbox_valid = tvalid;
+    sc->think_end = te;
+    sc->answer_end = ae;
+    sc->time_cands = n_time;
+    sc->claim_cands = n_claim;
+    sc->tbox_cands = n_tbox;
+    sc->tbox_kept = 0;
+    sc->tbox_numeric = 0;
   }
-  mx->times = n_times;
-  mx->claims = n_claims;
-  mx->claim_boxes = max_cb;
-  mx->think_boxes = n_tboxes;
+}
+
+// ---- phase B: one candidate (device: one thread each).  Items of a rollout are numbered
+// [0, P) think times, [P, P+C) claims, [P+C, P+C+Tb) think boxes, then the answer segment and the
+// answer box.
+O3V_HD int items_per_rollout(const Caps& cap) { return cap.P + cap.C + cap.Tb + 2; }
+
+O3V_HD void or_bits(uint32_t* word, uint32_t bits) {
+#if defined(__CUDA_ARCH__)
+  atomicOr(word, bits);
+#else
+  *word |= bits;
+#endif
+}
+
+O3V_HD void convert_item(const uint8_t* t, int item, const Caps& cap, const RolloutOut& o, Scratch* sc) {
+  constexpr Lit kTEnd = make_lit("</t>s");
+  if (item < cap.P) {                                                   // ---- "<t>x</t>s" of <think>
+    if (item >= sc->time_cands) return;
+    int64_t x0, unused;
+    unpack_range(o.think_times[item], &x0, &unused);
+    const int64_t te = sc->think_end;
+    bool ok;
+    const int64_t x1 = scan_digits_dots(t, x0, te, &ok);
+    double v = kTimeNoMatch;
+    if (x1 > x0 && lit_at(t, x1, te, kTEnd)) v = ok ? dec_to_double(t, x0, x1, 0) : kTimeBadFloat;
+    o.think_times[item] = v;
+    return;
+  }
+  item -= cap.P;
+  if (item < cap.C) {                                                   // ---- one claim
+    if (item >= sc->claim_cands) return;
+    int64_t fs, fe, g0, g1;
+    unpack_range(o.claim_t[item], &fs, &fe);
+    double* cbox = o.claim_box + (int64_t)item * cap.Bc * 4;
+    unpack_range(cbox[0], &g0, &g1);
+    const bool too_long = fe - fs >= kMaxRange || g1 - g0 >= kMaxRange;
+    strip_space(t, &fs, &fe, true);
+    double tv;
+    int nb = 0;
+    uint32_t valid = 0;
+    bool keep = !too_long && python_float(t, fs, fe, &tv);               // ValueError -> claim dropped (:332)
+    // boxes: re.findall(r'\[.*?\]', group 2) without DOTALL
+    for (int64_t i = g0; keep && i < g1;) {
+      if (t[i] != '[') { ++i; continue; }
+      int64_t j = i + 1;
+      while (j < g1 && t[j] != ']' && t[j] != '\n') ++j;
+      if (j >= g1) break;
+      if (t[j] == '\n') { i = j + 1; continue; }
+      int n; bool numeric; double v[4];
+      if (json_box(t, i, j + 1, &n, &numeric, v) != kJsonList) { keep = false; break; }   // JSONDecodeError
+      if (n == 4 && numeric && nb < 32) {
+        valid |= 1u << nb;
+        if (nb < cap.Bc) {
+          double* dst = cbox + 4 * nb;
+          dst[0] = v[0]; dst[1] = v[1]; dst[2] = v[2]; dst[3] = v[3];
+        }
+      }
+      ++nb;
+      i = j + 1;
+    }
+    o.claim_nbox[item] = keep ? nb : -1;
+    if (keep) {
+      o.claim_t[item] = tv;
+      o.claim_valid[item] = valid;
+    }
+    return;
+  }
+  item -= cap.C;
+  if (item < cap.Tb) {                                                  // ---- one <box> of <think> (visual QA)
+    if (item >= sc->tbox_cands) return;
+    int64_t bs, be;
+    double* dst = o.think_box + 4 * item;
+    unpack_range(dst[0], &bs, &be);
+    int n; bool numeric; double v[4];
+    if (be - bs >= kMaxRange || json_box(t, bs, be, &n, &numeric, v) != kJsonList) return;   // not JSON: skipped
+    const bool box = n == 4 && numeric;
+    if (box) { dst[0] = v[0]; dst[1] = v[1]; dst[2] = v[2]; dst[3] = v[3]; }
+    or_bits(&sc->tbox_kept, 1u << item);
+    if (box) or_bits(&sc->tbox_numeric, 1u << item);
+    return;
+  }
+  item -= cap.Tb;
+  if (item == 0) {                                                      // ---- the answer's two numbers
+    if (!(*o.flags & kFlagAnsSeg)) return;
+    for (int k = 0; k < 2; ++k) {
+      int64_t s, e;
+      unpack_range(o.ans_seg[k], &s, &e);
+      o.ans_seg[k] = dec_to_double(t, s, e, 0);
+    }
+    return;
+  }
+  if (!(*o.flags & kFlagAnsBox)) return;                                // ---- the answer's first <box>
+  int64_t bs, be;
+  unpack_range(o.ans_box[0], &bs, &be);
+  int n; bool numeric; double v[4];
+  if (be - bs < kMaxRange && json_box(t, bs, be, &n, &numeric, v) == kJsonList && n == 4 && numeric) {
+    o.ans_box[0] = v[0]; o.ans_box[1] = v[1]; o.ans_box[2] = v[2]; o.ans_box[3] = v[3];
+  } else {
+    *o.flags &= ~kFlagAnsBox;
+  }
+}
+
+// ---- phase C: drop rejected candidates, compact, publish the counts.  over[4]: a count that did not
+// fit its capacity (candidates are an upper bound of the matches), else 0.
+O3V_HD void finish_rollout(const Caps& cap, const RolloutOut& o, const Scratch* sc, int over[4]) {
+  over[0] = sc->time_cands > cap.P ? sc->time_cands : 0;
+  over[1] = sc->claim_cands > cap.C ? sc->claim_cands : 0;
+  over[2] = 0;
+  over[3] = sc->tbox_cands > cap.Tb ? sc->tbox_cands : 0;
+  // think times: one bad float() empties the list (:413-415, :450-451)
+  int n = sc->time_cands < cap.P ? sc->time_cands : cap.P, k = 0;
+  bool all_ok = true;
+  for (int i = 0; i < n; ++i) {
+    const double v = o.think_times[i];
+    if (v == kTimeBadFloat) all_ok = false;
+    else if (v != kTimeNoMatch) { if (k != i) o.think_times[k] = v; ++k; }
+  }
+  *o.n_times = all_ok ? k : 0;
+  // claims
+  n = sc->claim_cands < cap.C ? sc->claim_cands : cap.C;
+  k = 0;
+  for (int c = 0; c < n; ++c) {
+    const int nb = o.claim_nbox[c];
+    if (nb < 0) continue;
+    if (nb > cap.Bc && nb > over[2]) over[2] = nb;
+    if (k != c) {
+      o.claim_t[k] = o.claim_t[c];
+      o.claim_nbox[k] = nb;
+      o.claim_valid[k] = o.claim_valid[c];
+      const int m = (nb < cap.Bc ? nb : cap.Bc) * 4;
+      const double* src = o.claim_box + (int64_t)c * cap.Bc * 4;
+      double* dst = o.claim_box + (int64_t)k * cap.Bc * 4;
+      for (int i = 0; i < m; ++i) dst[i] = src[i];
+    }
+    ++k;
+  }
+  *o.n_claims = k;
+  // think boxes
+  n = sc->tbox_cands < cap.Tb ? sc->tbox_cands : cap.Tb;
+  k = 0;
+  uint32_t valid = 0;
+  for (int j = 0; j < n; ++j) {
+    if (!((sc->tbox_kept >> j) & 1u)) continue;
+    if ((sc->tbox_numeric >> j) & 1u) {
+      valid |= 1u << k;
+      if (k != j)
+        for (int i = 0; i < 4; ++i) o.think_box[4 * k + i] = o.think_box[4 * j + i];
+    }
+    ++k;
+  }
+  *o.n_tboxes = k;
+  *o.tbox_valid = valid;
 }
 
 }  // namespace scan

@@ -278,6 +278,7 @@ def parse_completions_device(text: torch.Tensor, offsets: torch.Tensor, task: to
     caps = dict(DEFAULT_CAPS if caps is None else caps)
     dev = text.device
     with torch.cuda.device(dev):
+        ws = torch.empty(max(1, lib.o3v_parse_workspace_bytes(R) // 8), dtype=torch.int64, device=dev)
         while True:
             out = {"overflow": torch.empty(4, dtype=torch.int32, device=dev)}
             for name, dt, shape in ROLLOUT_ROWS:
@@ -290,7 +291,8 @@ def parse_completions_device(text: torch.Tensor, offsets: torch.Tensor, task: to
             a.text, a.offsets, a.task = text.data_ptr(), offsets.data_ptr(), task.data_ptr()
             for name in out:
                 setattr(a, name, out[name].data_ptr())
-            _lib.call("o3v_parse_completions", 1, lib.o3v_parse_completions, ctypes.byref(a),
+            _lib.call("o3v_parse_completions", 3, lib.o3v_parse_completions, ctypes.byref(a),
+                      ctypes.c_void_p(ws.data_ptr()), ctypes.c_size_t(ws.numel() * 8),
                       ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
             if not sync:
                 break

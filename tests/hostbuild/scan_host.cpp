@@ -62,12 +62,13 @@ int scan_host_parse(const Args* ap) {
     o.claim_t = a.claim_t + r * a.C; o.claim_nbox = a.claim_nbox + r * a.C; o.claim_valid = a.claim_valid + r * a.C;
     o.claim_box = a.claim_box + r * (int64_t)a.C * a.Bc * 4; o.n_tboxes = a.n_tboxes + r;
     o.tbox_valid = a.tbox_valid + r; o.think_box = a.think_box + r * (int64_t)a.Tb * 4;
-    Maxima mx;
-    parse_rollout(a.text, a.offsets[r], a.offsets[r + 1], a.task[r / a.G], cap, o, &mx);
-    if (mx.times > a.P && mx.times > a.overflow[0]) a.overflow[0] = mx.times;
-    if (mx.claims > a.C && mx.claims > a.overflow[1]) a.overflow[1] = mx.claims;
-    if (mx.claim_boxes > a.Bc && mx.claim_boxes > a.overflow[2]) a.overflow[2] = mx.claim_boxes;
-    if (mx.think_boxes > a.Tb && mx.think_boxes > a.overflow[3]) a.overflow[3] = mx.think_boxes;
+    Scratch sc;
+    scan_rollout(a.text, a.offsets[r], a.offsets[r + 1], a.task[r / a.G], cap, o, &sc);
+    for (int item = 0; item < items_per_rollout(cap); ++item) convert_item(a.text, item, cap, o, &sc);
+    int over[4];
+    finish_rollout(cap, o, &sc, over);
+    for (int i = 0; i < 4; ++i)
+      if (over[i] > a.overflow[i]) a.overflow[i] = over[i];
   }
   return 0;
 }

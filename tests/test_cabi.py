@@ -55,18 +55,21 @@ def test_argument_validation_without_gpu(lib):
     assert lib.o3v_gspo_fwd_bwd(one, null, one, one, one, 8, 8, 1, 4, 0, 8, 0.04, 0.2, 0.2, 1,
                                 one, null, null, null, null, null, null, one, 8, null) == -4         # workspace
     assert lib.o3v_grounded_rewards(None, null, null) == -1
-    assert lib.o3v_parse_completions(None, null) == -1
+    assert lib.o3v_parse_completions(None, null, 0, null) == -1
     from open_o3_video_b200 import _lib
     a = _lib.ParseArgs()
     a.R, a.G, a.P, a.C, a.Bc, a.Tb = 4, 3, 1, 1, 1, 1                    # R % G
-    assert lib.o3v_parse_completions(ctypes.byref(a), null) == -1
+    assert lib.o3v_parse_completions(ctypes.byref(a), one, 1 << 20, null) == -1
     a.G, a.Bc = 1, 33                                                    # more than 32 boxes per claim
-    assert lib.o3v_parse_completions(ctypes.byref(a), null) == -1
+    assert lib.o3v_parse_completions(ctypes.byref(a), one, 1 << 20, null) == -1
     a.Bc = 1
     for name, _ in _lib.ParseArgs._fields_[6:]:
         setattr(a, name, 16)
     a.text = 24                                                          # text must be 16-byte aligned
-    assert lib.o3v_parse_completions(ctypes.byref(a), null) == -2
+    assert lib.o3v_parse_completions(ctypes.byref(a), one, 1 << 20, null) == -2
+    a.text = 16
+    assert lib.o3v_parse_completions(ctypes.byref(a), one, 8, null) == -4    # workspace
+    assert lib.o3v_parse_workspace_bytes(4) == 4 * 40
     assert lib.o3v_set_tunable(b"nope", 1) == -1
     assert lib.o3v_lmhead_fwd_workspace_bytes(128, 1024, 64) == 4 * 3 * 128 * 4
     assert lib.o3v_gspo_workspace_bytes(8) == (2 * 8 + 4 + 8 * 32 * 4) * 4

@@ -58,15 +58,16 @@ def test_parse_alignment_and_long_text():
 
 def test_parse_overflow_relaunch_and_report():
     texts, tasks = op.synth_batch(2000, 9)
-    # sync=False: one launch, rows truncated at the capacities, true counts and the overflow report
     small = dict(P=2, C=1, Bc=1, Tb=1)
+    # sync=False: one pass; the report names capacities that fit
     got, _ = _device_parse(texts, tasks, caps=small, sync=False)
-    exp = op.pack([op.parse_text(t, k) for t, k in zip(texts, tasks)], 2, 1, 1, 1)
-    assert not scan_host.mismatches({k: got[k] for k in exp}, exp, op.used_mask(exp))
-    assert got["overflow"][0] == exp["n_times"].max() and got["overflow"][1] == exp["n_claims"].max()
-    # sync=True grows the rows until everything fits
+    full = op.pack([op.parse_text(t, k) for t, k in zip(texts, tasks)], 64, 64, 32, 32)
+    ov = got["overflow"]
+    assert ov[0] >= full["n_times"].max() and ov[1] >= full["n_claims"].max() and ov[3] >= full["n_tboxes"].max()
+    # sync=True grows the rows until everything fits, then the result is exact
     got, exp, caps = _check(texts, tasks, caps=small)
     assert caps["P"] >= exp["n_times"].max() and caps["C"] >= exp["n_claims"].max()
+    assert not got["overflow"].any()
 
 
 def test_parse_empty_and_ragged():
