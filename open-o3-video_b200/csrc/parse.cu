@@ -41,17 +41,21 @@ parse_scan_kernel(const o3v_parse_args a, scan::Scratch* __restrict__ scratch) {
   const int64_t r = (int64_t)blockIdx.x * kScanWarps + (threadIdx.x >> 5);
   if (r >= a.R) return;                      // whole warp leaves together
   const scan::Caps cap{a.P, a.C, a.Bc, a.Tb};
-  scan::scan_rollout(a.text, a.offsets[r], a.offsets[r + 1], a.task[r / a.G], cap, rows_of(a, r), scratch + r);
+  scan::scan_rollout(a.text, a.offsets[a.R], a.offsets[r], a.offsets[r + 1], a.task[r / a.G], cap, rows_of(a, r), scratch + r);
 }
 
 __global__ void __launch_bounds__(kConvertThreads, 4)
 parse_convert_kernel(const o3v_parse_args a, scan::Scratch* __restrict__ scratch) {
   const scan::Caps cap{a.P, a.C, a.Bc, a.Tb};
+  // item-major: the 128 threads of a CTA convert the SAME item of 128 consecutive rollouts, so every lane
+  // of a warp runs the same routine (all time candidates k, or all claims c, ...)
   const int per = scan::items_per_rollout(cap);
-  const int64_t idx = (int64_t)blockIdx.x * kConvertThreads + threadIdx.x;
-  const int64_t r = idx / per;
-  if (r >= a.R) return;
-  scan::convert_item(a.text, (int)(idx - r * per), cap, rows_of(a, r), scratch + r);
+  const int64_t tiles = (a.R + kConvertThreads - 1) / kConvertThreads;
+  const int64_t tile = blockIdx.x % tiles;
+  const int item = (int)(blockIdx.x / tiles);
+  const int64_t r = tile * kConvertThreads + threadIdx.x;
+  if (r >= a.R || item >= per) return;
+  scan::convert_item(a.text, item, cap, rows_of(a, r), scratch + r);
 }
 
 __global__ void __launch_bounds__(kFinishThreads)
@@ -97,8 +101,8 @@ extern "C" int o3v_parse_completions(const o3v_parse_args* args, void* workspace
   const unsigned grid_a = (unsigned)((a.R + o3v::kScanWarps - 1) / o3v::kScanWarps);
   o3v::parse_scan_kernel<<<grid_a, o3v::kScanWarps * 32, 0, st>>>(a, scratch);
   O3V_LAUNCH_CHECK();
-  const int64_t items = a.R * (int64_t)(a.P + a.C + a.Tb + 2);
-  const unsigned grid_b = (unsigned)((items + o3v::kConvertThreads - 1) / o3v::kConvertThreads);
+  const int64_t tiles = (a.R + o3v::kConvertThreads - 1) / o3v::kConvertThreads;
+  const unsigned grid_b = (unsigned)(tiles * (a.P + a.C + a.Tb + 2));
   o3v::parse_convert_kernel<<<grid_b, o3v::kConvertThreads, 0, st>>>(a, scratch);
   O3V_LAUNCH_CHECK();
   const unsigned grid_c = (unsigned)((a.R + o3v::kFinishThreads - 1) / o3v::kFinishThreads);

@@ -106,44 +106,142 @@ O3V_HD bool lit_at(const uint8_t* t, int64_t p, int64_t end, const Lit& l) {
   return true;
 }
 
-// First p in [from, end - n] with t[p .. p+n) == literal, else -1.
-// Device: called by all 32 lanes of a warp with identical arguments (phase A); `t` is the 16-byte
-// aligned base of the whole text buffer (positions are absolute), padded to a multiple of 16 bytes.
-O3V_HD int64_t find_lit(const uint8_t* t, int64_t from, int64_t end, const Lit& l) {
-  const int64_t last = end - l.n;
-  if (from < 0) return -1;
-  if (from > last) return -1;
+// The literals the match chains search for.
+enum LitId { kLThinkO = 0, kLThinkC, kLAnsO, kLAnsC, kLT, kLTEnd, kLObj, kLObjBox, kLBoxAt, kLBoxOpen, kLBoxClose,
+             kLNewline, kNumLits };
+template <int ID>
+O3V_CONSTEXPR Lit lit_of() {
+  return ID == kLThinkO ? make_lit("<think>") : ID == kLThinkC ? make_lit("</think>") :
+         ID == kLAnsO ? make_lit("<answer>") : ID == kLAnsC ? make_lit("</answer>") :
+         ID == kLT ? make_lit("<t>") : ID == kLTEnd ? make_lit("</t>s") : ID == kLObj ? make_lit("<obj>") :
+         ID == kLObjBox ? make_lit("</obj><box>[") : ID == kLBoxAt ? make_lit("]</box>at<t>") :
+         ID == kLBoxOpen ? make_lit("<box>[") : ID == kLBoxClose ? make_lit("]</box>") : make_lit("\n");
+}
+
+// find<ID>(from, end): first p in [from, end - n] with t[p .. p+n) == literal ID, else -1.
+//
+// Host: a plain scan.  Device (phase A, called by all 32 lanes of a warp with identical
+// arguments): the warp keeps one 512-byte block of the text classified -- per lane, a 16-bit
+// match mask per literal for its 16 positions -- so that the chains' many searches cost a mask
+// select and one warp reduction each, and every block is loaded and classified once per sweep.
+// `t` is the 16-byte aligned base of the whole text buffer (positions are absolute), `total` its
+// length; the buffer is readable up to the next multiple of 16.
+struct Finder {
+  const uint8_t* t;
+  int64_t total;
 #if defined(__CUDA_ARCH__)
-  const int lane = threadIdx.x & 31;
-  const uint32_t c0 = (uint32_t)(l.lo & 0xff) * 0x01010101u;
-  for (int64_t base = from & ~(int64_t)15; base <= last; base += 512) {
-    const int64_t p0 = base + lane * 16;
-    uint32_t best = 0xffffffffu;
-    if (p0 <= last) {
-      const uint4 v = *reinterpret_cast<const uint4*>(t + p0);
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-      uint32_t m = 0;
+  int64_t base;              // start of the cached block (multiple of 512), -1 = none
+  uint32_t mask[kNumLits / 2];   // two 16-bit match masks per register
+
+  __device__ __forceinline__ void init(const uint8_t* text, int64_t n) { t = text; total = n; base = -1; }
+
+  template <int ID>
+  __device__ __forceinline__ static bool win_is(uint32_t w0, uint32_t w1, uint32_t w2) {
+    constexpr Lit l = lit_of<ID>();
+    constexpr uint32_t a0 = (uint32_t)l.lo, a1 = (uint32_t)(l.lo >> 32), a2 = (uint32_t)l.hi;
+    constexpr uint32_t m0 = l.n >= 4 ? 0xffffffffu : (1u << (8 * l.n)) - 1u;
+    constexpr uint32_t m1 = l.n >= 8 ? 0xffffffffu : l.n <= 4 ? 0u : (1u << (8 * (l.n - 4))) - 1u;
+    constexpr uint32_t m2 = l.n >= 12 ? 0xffffffffu : l.n <= 8 ? 0u : (1u << (8 * (l.n - 8))) - 1u;
+    return (((w0 ^ a0) & m0) | ((w1 ^ a1) & m1) | ((w2 ^ a2) & m2)) == 0;
+  }
+  __device__ __forceinline__ static uint32_t eq16(const uint4& v, uint8_t c) {   // bit i: byte i == c
+    const uint32_t c4 = (uint32_t)c * 0x01010101u;
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t m = 0;
 #pragma unroll
-      for (int i = 0; i < 4; ++i)   // bit j: byte j of the 16 equals the needle's first byte
-        m |= ((((__vcmpeq4(w[i], c0) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << (4 * i);
-      while (m) {
-        const int j = __ffs(m) - 1;
-        m &= m - 1;
-        const int64_t p = p0 + j;
-        if (p >= from && p <= last && lit_at(t, p, end, l)) { best = (uint32_t)(p - base); break; }
+    for (int i = 0; i < 4; ++i)
+      m |= ((((__vcmpeq4(w[i], c4) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << (4 * i);
+    return m;
+  }
+  __device__ __forceinline__ void set(int id, int j) { mask[id >> 1] |= 1u << (j + 16 * (id & 1)); }
+
+  // load and classify the block at `blk`
+  __device__ __forceinline__ void load_block(int64_t blk) {
+    const int lane = threadIdx.x & 31;
+    const int64_t p0 = blk + lane * 16;
+    const int64_t limit = (total + 15) & ~(int64_t)15;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (p0 < limit) v = *reinterpret_cast<const uint4*>(t + p0);
+    // the 16 bytes after mine: the next lane's vector (the last lane fetches its own)
+    uint4 nx;
+    nx.x = __shfl_down_sync(0xffffffffu, v.x, 1); nx.y = __shfl_down_sync(0xffffffffu, v.y, 1);
+    nx.z = __shfl_down_sync(0xffffffffu, v.z, 1); nx.w = __shfl_down_sync(0xffffffffu, v.w, 1);
+    if (lane == 31) {
+      nx = make_uint4(0, 0, 0, 0);
+      if (p0 + 16 < limit) nx = *reinterpret_cast<const uint4*>(t + p0 + 16);
+    }
+#pragma unroll
+    for (int i = 0; i < kNumLits / 2; ++i) mask[i] = 0;
+    const uint32_t w[8] = {v.x, v.y, v.z, v.w, nx.x, nx.y, nx.z, nx.w};
+    uint32_t cand = eq16(v, '<') | eq16(v, ']');
+    mask[kLNewline >> 1] = eq16(v, '\n') << (16 * (kLNewline & 1));
+    while (cand) {
+      const int j = __ffs(cand) - 1;
+      cand &= cand - 1;
+      const int sh = (j & 3) * 8;
+      uint32_t w0, w1, w2;                 // the 12 bytes starting at position j
+      switch (j >> 2) {
+        case 0: w0 = __funnelshift_r(w[0], w[1], sh); w1 = __funnelshift_r(w[1], w[2], sh); w2 = __funnelshift_r(w[2], w[3], sh); break;
+        case 1: w0 = __funnelshift_r(w[1], w[2], sh); w1 = __funnelshift_r(w[2], w[3], sh); w2 = __funnelshift_r(w[3], w[4], sh); break;
+        case 2: w0 = __funnelshift_r(w[2], w[3], sh); w1 = __funnelshift_r(w[3], w[4], sh); w2 = __funnelshift_r(w[4], w[5], sh); break;
+        default: w0 = __funnelshift_r(w[3], w[4], sh); w1 = __funnelshift_r(w[4], w[5], sh); w2 = __funnelshift_r(w[5], w[6], sh); break;
+      }
+      if ((w0 & 0xff) == '<') {
+        if (win_is<kLT>(w0, w1, w2)) set(kLT, j);
+        else if (win_is<kLTEnd>(w0, w1, w2)) set(kLTEnd, j);
+        else if (win_is<kLObj>(w0, w1, w2)) set(kLObj, j);
+        else if (win_is<kLObjBox>(w0, w1, w2)) set(kLObjBox, j);
+        else if (win_is<kLBoxOpen>(w0, w1, w2)) set(kLBoxOpen, j);
+        else if (win_is<kLThinkO>(w0, w1, w2)) set(kLThinkO, j);
+        else if (win_is<kLThinkC>(w0, w1, w2)) set(kLThinkC, j);
+        else if (win_is<kLAnsO>(w0, w1, w2)) set(kLAnsO, j);
+        else if (win_is<kLAnsC>(w0, w1, w2)) set(kLAnsC, j);
+      } else if (win_is<kLBoxClose>(w0, w1, w2)) {
+        set(kLBoxClose, j);
+        if (win_is<kLBoxAt>(w0, w1, w2)) set(kLBoxAt, j);
       }
     }
-    best = __reduce_min_sync(0xffffffffu, best);
-    if (best != 0xffffffffu) return base + best;
+    base = blk;
   }
-  return -1;
+
+  template <int ID>
+  __device__ __forceinline__ int64_t find(int64_t from, int64_t end) {
+    constexpr int n = lit_of<ID>().n;
+    const int64_t last = end - n;
+    if (from < 0 || from > last) return -1;
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+      const int64_t blk = from & ~(int64_t)511;
+      if (blk != base) load_block(blk);
+      const int64_t p0 = blk + lane * 16;
+      uint32_t m = (mask[ID >> 1] >> (16 * (ID & 1))) & 0xffffu;
+      const int64_t lo = from - p0, hi = last - p0;          // keep positions lo..hi of my 16
+      if (lo >= 16 || hi < 0) m = 0;
+      else {
+        if (lo > 0) m &= 0xffffu << (int)lo;
+        if (hi < 15) m &= (2u << (int)hi) - 1u;
+      }
+      uint32_t best = m ? (uint32_t)(lane * 16 + __ffs(m) - 1) : 0xffffffffu;
+      best = __reduce_min_sync(0xffffffffu, best);
+      if (best != 0xffffffffu) return blk + best;
+      from = blk + 512;
+      if (from > last) return -1;
+    }
+  }
 #else
-  const uint8_t c0 = lit_byte(l, 0);
-  for (int64_t p = from; p <= last; ++p)
-    if (t[p] == c0 && lit_at(t, p, end, l)) return p;
-  return -1;
+  void init(const uint8_t* text, int64_t n) { t = text; total = n; }
+  template <int ID>
+  int64_t find(int64_t from, int64_t end) const {
+    constexpr Lit l = lit_of<ID>();
+    const int64_t last = end - l.n;
+    if (from < 0) return -1;
+    const uint8_t c0 = lit_byte(l, 0);
+    for (int64_t p = from; p <= last; ++p)
+      if (t[p] == c0 && lit_at(t, p, end, l)) return p;
+    return -1;
+  }
 #endif
-}
+};
 
 // ------------------------------------------------------------------------------------------
 // UTF-8 helpers.  The text is Python str encoded as UTF-8 (well formed); malformed bytes are
@@ -767,14 +865,13 @@ constexpr double kTimeNoMatch = -1.0, kTimeBadFloat = -2.0;
 // [*bs, *be) (brackets included) and the return value is the end of the match; -1 if no match.
 // '.' does not cross a newline: a candidate whose first "]</box>" lies behind a newline fails, and so
 // does every candidate before that newline.
-O3V_HD int64_t next_box(const uint8_t* t, int64_t p, int64_t lim, int64_t* bs, int64_t* be) {
-  constexpr Lit kOpen = make_lit("<box>["), kClose = make_lit("]</box>"), kNewline = make_lit("\n");
+O3V_HD int64_t next_box(Finder& f, int64_t p, int64_t lim, int64_t* bs, int64_t* be) {
   for (;;) {
-    p = find_lit(t, p, lim, kOpen);
+    p = f.find<kLBoxOpen>(p, lim);
     if (p < 0) return -1;
-    const int64_t c = find_lit(t, p + 6, lim, kClose);
+    const int64_t c = f.find<kLBoxClose>(p + 6, lim);
     if (c < 0) return -1;
-    const int64_t nl = find_lit(t, p + 6, c, kNewline);
+    const int64_t nl = f.find<kLNewline>(p + 6, c);
     if (nl < 0) {
       *bs = p + 5;
       *be = c + 1;
@@ -785,19 +882,18 @@ O3V_HD int64_t next_box(const uint8_t* t, int64_t p, int64_t lim, int64_t* bs, i
 }
 
 // ---- phase A: spans and match chains -> candidates (device: warp-uniform, lane 0 stores)
-O3V_HD void scan_rollout(const uint8_t* t, int64_t beg, int64_t end, int task, const Caps& cap,
+O3V_HD void scan_rollout(const uint8_t* t, int64_t total, int64_t beg, int64_t end, int task, const Caps& cap,
                          const RolloutOut& o, Scratch* sc) {
-  constexpr Lit kThinkO = make_lit("<think>"), kThinkC = make_lit("</think>"), kAnsO = make_lit("<answer>"),
-                kAnsC = make_lit("</answer>"), kT = make_lit("<t>"), kTEnd = make_lit("</t>s"),
-                kTo = make_lit("</t>s to <t>"), kObj = make_lit("<obj>"), kObjBox = make_lit("</obj><box>["),
-                kBoxAt = make_lit("]</box>at<t>");
+  constexpr Lit kTEnd = make_lit("</t>s"), kTo = make_lit("</t>s to <t>");
+  Finder f;
+  f.init(t, total);
   int flags = 0;
   // think / answer spans: leftmost open tag, first close tag after it (lazy `.*?`, DOTALL)
-  int64_t ts = find_lit(t, beg, end, kThinkO), te = -1;
-  if (ts >= 0) { ts += 7; te = find_lit(t, ts, end, kThinkC); }
+  int64_t ts = f.find<kLThinkO>(beg, end), te = -1;
+  if (ts >= 0) { ts += 7; te = f.find<kLThinkC>(ts, end); }
   const bool has_think = te >= 0;
-  int64_t as = find_lit(t, beg, end, kAnsO), ae = -1;
-  if (as >= 0) { as += 8; ae = find_lit(t, as, end, kAnsC); }
+  int64_t as = f.find<kLAnsO>(beg, end), ae = -1;
+  if (as >= 0) { as += 8; ae = f.find<kLAnsC>(as, end); }
   const bool has_answer = ae >= 0;
   if (has_think) flags |= kFlagThink;
   if (has_answer) flags |= kFlagAnswer;
@@ -806,7 +902,7 @@ O3V_HD void scan_rollout(const uint8_t* t, int64_t beg, int64_t end, int task, c
   // pattern matches; the two number ranges are converted in phase B
   if ((task == kTaskTemporal || task == kTaskTemporalMcq) && has_answer) {
     int64_t p = as;
-    while ((p = find_lit(t, p, ae, kT)) >= 0) {
+    while ((p = f.find<kLT>(p, ae)) >= 0) {
       const int64_t a0 = p + 3, a1 = scan_simple_decimal(t, a0, ae);
       if (a1 >= 0 && lit_at(t, a1, ae, kTo)) {
         const int64_t b0 = a1 + 12, b1 = scan_simple_decimal(t, b0, ae);
@@ -825,7 +921,7 @@ O3V_HD void scan_rollout(const uint8_t* t, int64_t beg, int64_t end, int task, c
   int n_time = 0, n_tbox = 0, n_claim = 0;
   if (has_think) {
     int64_t p = ts;
-    while ((p = find_lit(t, p, te, kT)) >= 0) {
+    while ((p = f.find<kLT>(p, te)) >= 0) {
       if (n_time < cap.P && O3V_LANE0) o.think_times[n_time] = pack_range(p + 3, p + 3);
       ++n_time;
       p += 3;
@@ -836,7 +932,7 @@ O3V_HD void scan_rollout(const uint8_t* t, int64_t beg, int64_t end, int task, c
     // ---- first <box> of the answer (:211-223); flag provisional until phase B has parsed it
     if (has_answer) {
       int64_t bs, be;
-      if (next_box(t, as, ae, &bs, &be) >= 0) {
+      if (next_box(f, as, ae, &bs, &be) >= 0) {
         flags |= kFlagAnsBox;
         if (O3V_LANE0) o.ans_box[0] = pack_range(bs, be);
       }
@@ -844,7 +940,7 @@ O3V_HD void scan_rollout(const uint8_t* t, int64_t beg, int64_t end, int task, c
     // ---- every <box> inside <think> (:505-511)
     if (has_think) {
       int64_t p = ts, bs, be;
-      while ((p = next_box(t, p, te, &bs, &be)) >= 0) {
+      while ((p = next_box(f, p, te, &bs, &be)) >= 0) {
         if (n_tbox < cap.Tb && O3V_LANE0) o.think_box[4 * n_tbox] = pack_range(bs, be);
         ++n_tbox;
       }
@@ -855,13 +951,13 @@ O3V_HD void scan_rollout(const uint8_t* t, int64_t beg, int64_t end, int task, c
     // the first "]</box>at<t>" after that; group 3 at the first "</t>s" (DESIGN.md section 8).
     int64_t p = ts;
     for (;;) {
-      p = find_lit(t, p, te, kObj);
+      p = f.find<kLObj>(p, te);
       if (p < 0) break;
-      const int64_t q = find_lit(t, p + 5, te, kObjBox);
+      const int64_t q = f.find<kLObjBox>(p + 5, te);
       if (q < 0) break;
-      const int64_t e = find_lit(t, q + 12, te, kBoxAt);
+      const int64_t e = f.find<kLBoxAt>(q + 12, te);
       if (e < 0) break;
-      const int64_t z = find_lit(t, e + 12, te, kTEnd);
+      const int64_t z = f.find<kLTEnd>(e + 12, te);
       if (z < 0) break;
       p = z + 5;
       if (n_claim < cap.C && O3V_LANE0) {

@@ -32,15 +32,6 @@ int scan_host_json_box(const uint8_t* s, int64_t n, int* n_elems, int* numeric, 
   return rc;
 }
 
-int64_t scan_host_find(const uint8_t* s, int64_t from, int64_t end, const char* lit) {
-  Lit l{0, 0, (int)strlen(lit)};
-  for (int i = 0; i < l.n; ++i) {
-    if (i < 8) l.lo |= (uint64_t)(uint8_t)lit[i] << (8 * i);
-    else l.hi |= (uint64_t)(uint8_t)lit[i] << (8 * (i - 8));
-  }
-  return find_lit(s, from, end, l);
-}
-
 // same argument block as o3v_parse_args, host pointers
 struct Args {
   int64_t R, G;
@@ -63,7 +54,7 @@ int scan_host_parse(const Args* ap) {
     o.claim_box = a.claim_box + r * (int64_t)a.C * a.Bc * 4; o.n_tboxes = a.n_tboxes + r;
     o.tbox_valid = a.tbox_valid + r; o.think_box = a.think_box + r * (int64_t)a.Tb * 4;
     Scratch sc;
-    scan_rollout(a.text, a.offsets[r], a.offsets[r + 1], a.task[r / a.G], cap, o, &sc);
+    scan_rollout(a.text, a.offsets[a.R], a.offsets[r], a.offsets[r + 1], a.task[r / a.G], cap, o, &sc);
     for (int item = 0; item < items_per_rollout(cap); ++item) convert_item(a.text, item, cap, o, &sc);
     int over[4];
     finish_rollout(cap, o, &sc, over);

@@ -35,8 +35,6 @@ def load():
     lib.scan_host_python_float.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
     lib.scan_host_json_box.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int),
                                        ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)]
-    lib.scan_host_find.restype = ctypes.c_int64
-    lib.scan_host_find.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_char_p]
     _lib = lib
     return lib
 
