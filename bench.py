@@ -304,14 +304,15 @@ def run_ours(args):
     v_local = weight.shape[0]
     ach = 2.0 * tok_per_launch * H * v_local / (k1_ms * 1e-3) / 1e12
     shares = {k: sum(v) / args.steps for k, v in durs.items()}
-    traffic = None                                         # DRAM bytes per K1 launch from the committed ncu capture
+    traffic, traffic_detail = None, None                   # DRAM bytes per K1 launch from the committed ncu capture
     tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if world == 1 and os.path.isfile(tpath):
         with open(tpath) as f:
             tj = json.load(f).get("%s:%d" % (args.config, args.chunk_tokens))
         if tj:
-            traffic = dict(bytes=tj["dram_bytes_read"] + tj["dram_bytes_write"], algorithmic_bytes=tj["algorithmic_bytes"],
-                           source="profiles/k1_traffic.json (ncu --set full, same command)")
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            traffic_detail = dict(algorithmic_bytes=tj["algorithmic_bytes"], unit="bytes per launch",
+                                  source="profiles/k1_traffic.json (ncu --set full, same command)")
     line = dict(
         metric=METRIC, value=value, unit="tokens/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=ms_dev, higher_is_better=True, scaling="strong", vs_baseline=None,
@@ -328,7 +329,7 @@ def run_ours(args):
         roofline=dict(bound="tensor", kernel="lmhead_gemm_kernel<EPI_STATS> (K1 + logits store), per token chunk",
                       achieved=ach, peak=pk["sustained"], unit="TFLOP/s", frac=ach / pk["sustained"],
                       frac_of_burst=ach / pk["burst"], peak_source=pk["source"] + " (sustained: kernel timed inside a long step)",
-                      ms_per_launch=k1_ms, traffic=traffic),
+                      ms_per_launch=k1_ms, traffic=traffic, traffic_detail=traffic_detail),
         kernel_ms_per_step=shares,
         e2e=dict(value=T / (ms_e2e * 1e-3), unit="tokens/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                  ms_per_step=ms_e2e),

@@ -204,6 +204,19 @@ struct Finder {
     base = blk;
   }
 
+  // my 16-bit match mask of literal ID in block `blk`, restricted to start positions in [from, last]
+  template <int ID>
+  __device__ __forceinline__ uint32_t block_mask(int64_t blk, int64_t from, int64_t last) {
+    if (blk != base) load_block(blk);
+    const int64_t p0 = blk + (threadIdx.x & 31) * 16;
+    uint32_t m = (mask[ID >> 1] >> (16 * (ID & 1))) & 0xffffu;
+    const int64_t lo = from - p0, hi = last - p0;            // keep positions lo..hi of my 16
+    if (lo >= 16 || hi < 0) return 0;
+    if (lo > 0) m &= 0xffffu << (int)lo;
+    if (hi < 15) m &= (2u << (int)hi) - 1u;
+    return m;
+  }
+
   template <int ID>
   __device__ __forceinline__ int64_t find(int64_t from, int64_t end) {
     constexpr int n = lit_of<ID>().n;
@@ -212,15 +225,7 @@ struct Finder {
     const int lane = threadIdx.x & 31;
     for (;;) {
       const int64_t blk = from & ~(int64_t)511;
-      if (blk != base) load_block(blk);
-      const int64_t p0 = blk + lane * 16;
-      uint32_t m = (mask[ID >> 1] >> (16 * (ID & 1))) & 0xffffu;
-      const int64_t lo = from - p0, hi = last - p0;          // keep positions lo..hi of my 16
-      if (lo >= 16 || hi < 0) m = 0;
-      else {
-        if (lo > 0) m &= 0xffffu << (int)lo;
-        if (hi < 15) m &= (2u << (int)hi) - 1u;
-      }
+      const uint32_t m = block_mask<ID>(blk, from, last);
       uint32_t best = m ? (uint32_t)(lane * 16 + __ffs(m) - 1) : 0xffffffffu;
       best = __reduce_min_sync(0xffffffffu, best);
       if (best != 0xffffffffu) return blk + best;
@@ -481,12 +486,42 @@ O3V_HD_NOINLINE double big_to_double(const uint8_t* t, int64_t ms, int64_t me, i
   return bits_to_double((mant & (((uint64_t)1 << 52) - 1)) | (biased << 52));
 }
 
+// Digit accumulator of the fast path: the scanners feed it while they recognise a number, so the text
+// is walked once; only the slow path re-reads the mantissa range.
+struct DecAcc {
+  uint64_t w;        // first 19 significant digits
+  int nsig;
+  int64_t frac, dropped;   // digits after the point / beyond the 19th
+  bool exact;        // no non-zero digit was dropped
+};
+O3V_HD void acc_init(DecAcc& a) { a.w = 0; a.nsig = 0; a.frac = 0; a.dropped = 0; a.exact = true; }
+O3V_HD void acc_digit(DecAcc& a, int v, bool after_point) {
+  if (after_point) ++a.frac;
+  if (a.nsig == 0 && v == 0) return;          // leading zero
+  if (a.nsig < 19) { a.w = a.w * 10 + (uint64_t)v; ++a.nsig; }
+  else { ++a.dropped; if (v) a.exact = false; }
+}
+// value of the accumulated digits x 10^exp10 (unsigned), correctly rounded; [ms, me) is the mantissa text
+O3V_HD double acc_value(const DecAcc& a, const uint8_t* t, int64_t ms, int64_t me, int64_t exp10) {
+  if (a.nsig == 0) return 0.0;
+  const int64_t e = a.dropped - a.frac + exp10;   // value = w x 10^e when exact
+  if (a.exact && a.w < ((uint64_t)1 << 53)) {
+#if defined(__CUDA_ARCH__)
+    if (e >= 0 && e <= 22) return __dmul_rn((double)a.w, pow10_exact((int)e));
+    if (e < 0 && e >= -22) return __ddiv_rn((double)a.w, pow10_exact((int)-e));
+#else
+    if (e >= 0 && e <= 22) return (double)a.w * pow10_exact((int)e);
+    if (e < 0 && e >= -22) return (double)a.w / pow10_exact((int)-e);
+#endif
+  }
+  return big_to_double(t, ms, me, exp10);
+}
+
 // value of mantissa text [ms, me) x 10^exp10 (unsigned), correctly rounded.
 O3V_HD double dec_to_double(const uint8_t* t, int64_t ms, int64_t me, int64_t exp10) {
-  uint64_t w = 0;
-  int nsig = 0;
-  int64_t frac_digits = 0, dropped = 0;
-  bool seen_point = false, exact = true;
+  DecAcc a;
+  acc_init(a);
+  bool seen_point = false;
   for (int64_t p = ms; p < me;) {
     const uint8_t c = t[p];
     if (c == '.') { seen_point = true; ++p; continue; }
@@ -494,25 +529,9 @@ O3V_HD double dec_to_double(const uint8_t* t, int64_t ms, int64_t me, int64_t ex
     int len = 1;
     const int v = digit_at(t, p, me, &len);
     p += len;
-    if (v < 0) continue;
-    if (seen_point) ++frac_digits;
-    if (nsig == 0 && v == 0) continue;        // leading zero
-    if (nsig < 19) { w = w * 10 + (uint64_t)v; ++nsig; }
-    else { ++dropped; if (v) exact = false; }
+    if (v >= 0) acc_digit(a, v, seen_point);
   }
-  if (nsig == 0) return 0.0;
-  // value = w x 10^(dropped - frac_digits + exp10) when exact
-  const int64_t e = dropped - frac_digits + exp10;
-  if (exact && w < ((uint64_t)1 << 53)) {
-#if defined(__CUDA_ARCH__)
-    if (e >= 0 && e <= 22) return __dmul_rn((double)w, pow10_exact((int)e));
-    if (e < 0 && e >= -22) return __ddiv_rn((double)w, pow10_exact((int)-e));
-#else
-    if (e >= 0 && e <= 22) return (double)w * pow10_exact((int)e);
-    if (e < 0 && e >= -22) return (double)w / pow10_exact((int)-e);
-#endif
-  }
-  return big_to_double(t, ms, me, exp10);
+  return acc_value(a, t, ms, me, exp10);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -520,12 +539,15 @@ O3V_HD double dec_to_double(const uint8_t* t, int64_t ms, int64_t me, int64_t ex
 // ------------------------------------------------------------------------------------------
 // `[\d.]+` at p (reward_func.py:405, :447): returns the end of the run (p if empty); *ok says
 // whether float() accepts it (>= 1 digit, <= 1 dot).
-O3V_HD int64_t scan_digits_dots(const uint8_t* t, int64_t p, int64_t end, bool* ok) {
+O3V_HD int64_t scan_digits_dots(const uint8_t* t, int64_t p, int64_t end, bool* ok, DecAcc* acc) {
   int digits = 0, dots = 0;
+  acc_init(*acc);
   while (p < end) {
     if (t[p] == '.') { ++dots; ++p; continue; }
     int len;
-    if (digit_at(t, p, end, &len) < 0) break;
+    const int v = digit_at(t, p, end, &len);
+    if (v < 0) break;
+    acc_digit(*acc, v, dots > 0);
     ++digits;
     p += len;
   }
@@ -681,13 +703,15 @@ O3V_HD int64_t json_number(const uint8_t* t, int64_t p, int64_t e, double* out) 
   if (p < e && t[p] == '-') { neg = true; ++p; }
   const int64_t ms = p;
   if (p >= e || t[p] < '0' || t[p] > '9') return -1;
+  DecAcc a;
+  acc_init(a);
   if (t[p] == '0') ++p;
-  else while (p < e && t[p] >= '0' && t[p] <= '9') ++p;
+  else
+    for (; p < e && t[p] >= '0' && t[p] <= '9'; ++p) acc_digit(a, t[p] - '0', false);
   bool is_float = false;
   if (p + 1 < e && t[p] == '.' && t[p + 1] >= '0' && t[p + 1] <= '9') {
     is_float = true;
-    ++p;
-    while (p < e && t[p] >= '0' && t[p] <= '9') ++p;
+    for (++p; p < e && t[p] >= '0' && t[p] <= '9'; ++p) acc_digit(a, t[p] - '0', true);
   }
   const int64_t me = p;
   int64_t exp10 = 0;
@@ -704,7 +728,7 @@ O3V_HD int64_t json_number(const uint8_t* t, int64_t p, int64_t e, double* out) 
       p = q;
     }
   }
-  const double v = dec_to_double(t, ms, me, exp10);
+  const double v = acc_value(a, t, ms, me, exp10);
   // an integer literal becomes a Python int: "-0" is int 0 -> +0.0 in np.array(dtype=float)
   *out = (neg && (is_float || v != 0.0)) ? -v : v;
   return p;
@@ -920,12 +944,36 @@ O3V_HD void scan_rollout(const uint8_t* t, int64_t total, int64_t beg, int64_t e
   // contains no second "<t>", so the candidates of findall's matches are exactly these, in order
   int n_time = 0, n_tbox = 0, n_claim = 0;
   if (has_think) {
+#if defined(__CUDA_ARCH__)
+    // all occurrences at once: per 512-byte block every lane owns the matches among its 16 positions; a warp
+    // prefix sum of the match counts gives each lane the candidate index of its first match
+    const int lane = threadIdx.x & 31;
+    const int64_t last = te - 3;
+    for (int64_t blk = ts & ~(int64_t)511; blk <= last; blk += 512) {
+      uint32_t m = f.block_mask<kLT>(blk, ts, last);
+      const int cnt = __popc(m);
+      int pre = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, pre, d);
+        if (lane >= d) pre += v;
+      }
+      int k = n_time + pre - cnt;
+      for (; m; m &= m - 1, ++k)
+        if (k < cap.P) {
+          const int64_t x0 = blk + lane * 16 + (__ffs(m) - 1) + 3;
+          o.think_times[k] = pack_range(x0, x0);
+        }
+      n_time += __shfl_sync(0xffffffffu, pre, 31);
+    }
+#else
     int64_t p = ts;
     while ((p = f.find<kLT>(p, te)) >= 0) {
-      if (n_time < cap.P && O3V_LANE0) o.think_times[n_time] = pack_range(p + 3, p + 3);
+      if (n_time < cap.P) o.think_times[n_time] = pack_range(p + 3, p + 3);
       ++n_time;
       p += 3;
     }
+#endif
   }
 
   if (task == kTaskVisual) {
@@ -1001,9 +1049,10 @@ O3V_HD void convert_item(const uint8_t* t, int item, const Caps& cap, const Roll
     unpack_range(o.think_times[item], &x0, &unused);
     const int64_t te = sc->think_end;
     bool ok;
-    const int64_t x1 = scan_digits_dots(t, x0, te, &ok);
+    DecAcc acc;
+    const int64_t x1 = scan_digits_dots(t, x0, te, &ok, &acc);
     double v = kTimeNoMatch;
-    if (x1 > x0 && lit_at(t, x1, te, kTEnd)) v = ok ? dec_to_double(t, x0, x1, 0) : kTimeBadFloat;
+    if (x1 > x0 && lit_at(t, x1, te, kTEnd)) v = ok ? acc_value(acc, t, x0, x1, 0) : kTimeBadFloat;
     o.think_times[item] = v;
     return;
   }
