@@ -38,10 +38,12 @@ __device__ __forceinline__ scan::RolloutOut rows_of(const o3v_parse_args& a, int
 
 __global__ void __launch_bounds__(kScanWarps * 32, 4)
 parse_scan_kernel(const o3v_parse_args a, scan::Scratch* __restrict__ scratch) {
+  __shared__ uint32_t mask_cache[kScanWarps][scan::Finder::kSmemWords];   // 6 KB per warp
   const int64_t r = (int64_t)blockIdx.x * kScanWarps + (threadIdx.x >> 5);
   if (r >= a.R) return;                      // whole warp leaves together
   const scan::Caps cap{a.P, a.C, a.Bc, a.Tb};
-  scan::scan_rollout(a.text, a.offsets[a.R], a.offsets[r], a.offsets[r + 1], a.task[r / a.G], cap, rows_of(a, r), scratch + r);
+  scan::scan_rollout(a.text, a.offsets[a.R], a.offsets[r], a.offsets[r + 1], a.task[r / a.G], cap, rows_of(a, r), scratch + r,
+                     mask_cache[threadIdx.x >> 5]);
 }
 
 __global__ void __launch_bounds__(kConvertThreads, 4)

@@ -129,11 +129,18 @@ O3V_CONSTEXPR Lit lit_of() {
 struct Finder {
   const uint8_t* t;
   int64_t total;
+  static constexpr int kSmemBlocks = 8;                       // blocks of a rollout whose masks stay in smem
+  static constexpr int kSmemWords = kSmemBlocks * (kNumLits / 2) * 32;   // per warp
 #if defined(__CUDA_ARCH__)
-  int64_t base;              // start of the cached block (multiple of 512), -1 = none
+  int64_t base;              // start of the block classified in registers (multiple of 512), -1 = none
   uint32_t mask[kNumLits / 2];   // two 16-bit match masks per register
+  uint32_t* sm;              // this warp's mask cache: [block][word][lane]
+  int64_t first;             // block 0 of the cache = the rollout's first block
+  uint32_t cached;           // bit b: block b of the rollout is in `sm`
 
-  __device__ __forceinline__ void init(const uint8_t* text, int64_t n) { t = text; total = n; base = -1; }
+  __device__ __forceinline__ void init(const uint8_t* text, int64_t n, int64_t rollout_beg, uint32_t* warp_smem) {
+    t = text; total = n; base = -1; sm = warp_smem; first = rollout_beg & ~(int64_t)511; cached = 0;
+  }
 
   template <int ID>
   __device__ __forceinline__ static bool win_is(uint32_t w0, uint32_t w1, uint32_t w2) {
@@ -187,15 +194,22 @@ struct Finder {
         default: w0 = __funnelshift_r(w[3], w[4], sh); w1 = __funnelshift_r(w[4], w[5], sh); w2 = __funnelshift_r(w[5], w[6], sh); break;
       }
       if ((w0 & 0xff) == '<') {
-        if (win_is<kLT>(w0, w1, w2)) set(kLT, j);
-        else if (win_is<kLTEnd>(w0, w1, w2)) set(kLTEnd, j);
-        else if (win_is<kLObj>(w0, w1, w2)) set(kLObj, j);
-        else if (win_is<kLObjBox>(w0, w1, w2)) set(kLObjBox, j);
-        else if (win_is<kLBoxOpen>(w0, w1, w2)) set(kLBoxOpen, j);
-        else if (win_is<kLThinkO>(w0, w1, w2)) set(kLThinkO, j);
-        else if (win_is<kLThinkC>(w0, w1, w2)) set(kLThinkC, j);
-        else if (win_is<kLAnsO>(w0, w1, w2)) set(kLAnsO, j);
-        else if (win_is<kLAnsC>(w0, w1, w2)) set(kLAnsC, j);
+        switch ((w0 >> 8) & 0xff) {                          // second byte picks the few tags worth testing
+          case '/':
+            if (win_is<kLTEnd>(w0, w1, w2)) set(kLTEnd, j);
+            else if (win_is<kLObjBox>(w0, w1, w2)) set(kLObjBox, j);
+            else if (win_is<kLThinkC>(w0, w1, w2)) set(kLThinkC, j);
+            else if (win_is<kLAnsC>(w0, w1, w2)) set(kLAnsC, j);
+            break;
+          case 't':
+            if (win_is<kLT>(w0, w1, w2)) set(kLT, j);
+            else if (win_is<kLThinkO>(w0, w1, w2)) set(kLThinkO, j);
+            break;
+          case 'o': if (win_is<kLObj>(w0, w1, w2)) set(kLObj, j); break;
+          case 'b': if (win_is<kLBoxOpen>(w0, w1, w2)) set(kLBoxOpen, j); break;
+          case 'a': if (win_is<kLAnsO>(w0, w1, w2)) set(kLAnsO, j); break;
+          default: break;
+        }
       } else if (win_is<kLBoxClose>(w0, w1, w2)) {
         set(kLBoxClose, j);
         if (win_is<kLBoxAt>(w0, w1, w2)) set(kLBoxAt, j);
@@ -207,9 +221,26 @@ struct Finder {
   // my 16-bit match mask of literal ID in block `blk`, restricted to start positions in [from, last]
   template <int ID>
   __device__ __forceinline__ uint32_t block_mask(int64_t blk, int64_t from, int64_t last) {
-    if (blk != base) load_block(blk);
-    const int64_t p0 = blk + (threadIdx.x & 31) * 16;
-    uint32_t m = (mask[ID >> 1] >> (16 * (ID & 1))) & 0xffffu;
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (blk - first) >> 9;
+    uint32_t word;
+    if (b >= 0 && b < kSmemBlocks) {                         // classified once per rollout, then served from smem
+      uint32_t* row = sm + (int)b * (kNumLits / 2) * 32 + lane;
+      if (!((cached >> (int)b) & 1u)) {
+        load_block(blk);
+#pragma unroll
+        for (int i = 0; i < kNumLits / 2; ++i) row[i * 32] = mask[i];
+        cached |= 1u << (int)b;
+        word = mask[ID >> 1];
+      } else {
+        word = row[(ID >> 1) * 32];
+      }
+    } else {
+      if (blk != base) load_block(blk);
+      word = mask[ID >> 1];
+    }
+    const int64_t p0 = blk + lane * 16;
+    uint32_t m = (word >> (16 * (ID & 1))) & 0xffffu;
     const int64_t lo = from - p0, hi = last - p0;            // keep positions lo..hi of my 16
     if (lo >= 16 || hi < 0) return 0;
     if (lo > 0) m &= 0xffffu << (int)lo;
@@ -234,7 +265,7 @@ struct Finder {
     }
   }
 #else
-  void init(const uint8_t* text, int64_t n) { t = text; total = n; }
+  void init(const uint8_t* text, int64_t n, int64_t, uint32_t*) { t = text; total = n; }
   template <int ID>
   int64_t find(int64_t from, int64_t end) const {
     constexpr Lit l = lit_of<ID>();
@@ -907,10 +938,10 @@ O3V_HD int64_t next_box(Finder& f, int64_t p, int64_t lim, int64_t* bs, int64_t*
 
 // ---- phase A: spans and match chains -> candidates (device: warp-uniform, lane 0 stores)
 O3V_HD void scan_rollout(const uint8_t* t, int64_t total, int64_t beg, int64_t end, int task, const Caps& cap,
-                         const RolloutOut& o, Scratch* sc) {
+                         const RolloutOut& o, Scratch* sc, uint32_t* warp_smem) {
   constexpr Lit kTEnd = make_lit("</t>s"), kTo = make_lit("</t>s to <t>");
   Finder f;
-  f.init(t, total);
+  f.init(t, total, beg, warp_smem);
   int flags = 0;
   // think / answer spans: leftmost open tag, first close tag after it (lazy `.*?`, DOTALL)
   int64_t ts = f.find<kLThinkO>(beg, end), te = -1;

@@ -54,7 +54,7 @@ int scan_host_parse(const Args* ap) {
     o.claim_box = a.claim_box + r * (int64_t)a.C * a.Bc * 4; o.n_tboxes = a.n_tboxes + r;
     o.tbox_valid = a.tbox_valid + r; o.think_box = a.think_box + r * (int64_t)a.Tb * 4;
     Scratch sc;
-    scan_rollout(a.text, a.offsets[a.R], a.offsets[r], a.offsets[r + 1], a.task[r / a.G], cap, o, &sc);
+    scan_rollout(a.text, a.offsets[a.R], a.offsets[r], a.offsets[r + 1], a.task[r / a.G], cap, o, &sc, nullptr);
     for (int item = 0; item < items_per_rollout(cap); ++item) convert_item(a.text, item, cap, o, &sc);
     int over[4];
     finish_rollout(cap, o, &sc, over);
