@@ -38,6 +38,33 @@
 #define O3V_HD_NOINLINE inline
 #endif
 
+// A data-dependent loop run by the lanes of a warp on DIFFERENT data: the vote at the top makes the lanes start
+// every iteration together (lanes that are done idle until the last one is), instead of drifting apart until the
+// loop's exit.  The body must leave only through `continue` (no break / return).
+#if defined(__CUDA_ARCH__)
+#define O3V_LOCKSTEP_BEGIN(cond)                            \
+  {                                                         \
+    const unsigned lockstep_mask__ = __activemask();        \
+    for (;;) {                                              \
+      const bool lockstep_go__ = (cond);                    \
+      if (!__any_sync(lockstep_mask__, lockstep_go__)) break; \
+      if (lockstep_go__) {
+#define O3V_LOCKSTEP_END \
+      }                  \
+    }                    \
+  }
+#else
+#define O3V_LOCKSTEP_BEGIN(cond) \
+  {                              \
+    for (;;) {                   \
+      if (!(cond)) break;        \
+      {
+#define O3V_LOCKSTEP_END \
+      }                  \
+    }                    \
+  }
+#endif
+
 namespace o3v {
 namespace scan {
 
@@ -774,12 +801,12 @@ O3V_HD int json_box(const uint8_t* t, int64_t s, int64_t e, int* n_elems, bool* 
   int n_top = 0;
   bool all_numeric = true;
   // states
-  enum { kValueOrClose, kValue, kAfterValue, kKeyOrClose, kKey, kColon, kDone };
+  enum { kValueOrClose, kValue, kAfterValue, kKeyOrClose, kKey, kColon, kDone, kBad };
   int state = kValue;
-  while (true) {
+  // one token per iteration; the lanes of a warp (each on its own payload) start every token together
+  O3V_LOCKSTEP_BEGIN(state < kDone)
     while (p < e && json_ws(t[p])) ++p;
-    if (state == kDone) break;
-    if (p >= e) return kJsonInvalid;
+    if (p >= e) { state = kBad; continue; }
     const uint8_t c = t[p];
     if (state == kValue || state == kValueOrClose) {
       if (state == kValueOrClose && c == ']') {            // empty array
@@ -790,7 +817,7 @@ O3V_HD int json_box(const uint8_t* t, int64_t s, int64_t e, int* n_elems, bool* 
       }
       const bool top_elem = depth == 1;
       if (c == '[' || c == '{') {
-        if (depth >= kJsonMaxDepth) return kJsonInvalid;
+        if (depth >= kJsonMaxDepth) { state = kBad; continue; }
         if (c == '[') is_array |= (uint64_t)1 << depth; else is_array &= ~((uint64_t)1 << depth);
         ++depth; ++p;
         state = c == '[' ? kValueOrClose : kKeyOrClose;
@@ -800,7 +827,7 @@ O3V_HD int json_box(const uint8_t* t, int64_t s, int64_t e, int* n_elems, bool* 
       bool num = false;
       if (c == '"') {
         const int64_t q = json_string(t, p + 1, e);
-        if (q < 0) return kJsonInvalid;
+        if (q < 0) { state = kBad; continue; }
         if (top_elem) {                                      // np.array(dtype=float) calls float(str)
           int64_t fs = p + 1, fe = q - 1;
           bool escaped = false;
@@ -817,7 +844,7 @@ O3V_HD int json_box(const uint8_t* t, int64_t s, int64_t e, int* n_elems, bool* 
       } else if (c == '-' && lit_at(t, p, e, kNegInfinity)) { p += 9; v = bits_to_double(0xFFF0000000000000ull); num = true;
       } else {
         const int64_t q = json_number(t, p, e, &v);
-        if (q < 0) return kJsonInvalid;
+        if (q < 0) { state = kBad; continue; }
         p = q;
         num = true;
       }
@@ -839,7 +866,7 @@ O3V_HD int json_box(const uint8_t* t, int64_t s, int64_t e, int* n_elems, bool* 
         state = kAfterValue;
         continue;
       }
-      return kJsonInvalid;
+      { state = kBad; continue; }
     }
     if (state == kKeyOrClose || state == kKey) {
       if (state == kKeyOrClose && c == '}') {
@@ -849,19 +876,21 @@ O3V_HD int json_box(const uint8_t* t, int64_t s, int64_t e, int* n_elems, bool* 
         state = kAfterValue;
         continue;
       }
-      if (c != '"') return kJsonInvalid;
+      if (c != '"') { state = kBad; continue; }
       p = json_string(t, p + 1, e);
-      if (p < 0) return kJsonInvalid;
+      if (p < 0) { state = kBad; continue; }
       state = kColon;
       continue;
     }
     if (state == kColon) {
-      if (c != ':') return kJsonInvalid;
+      if (c != ':') { state = kBad; continue; }
       ++p;
       state = kValue;
       continue;
     }
-  }
+  O3V_LOCKSTEP_END
+  if (state == kBad) return kJsonInvalid;
+  while (p < e && json_ws(t[p])) ++p;
   if (p != e) return kJsonInvalid;                          // "Extra data"
   *n_elems = n_top;
   *numeric = all_numeric;
@@ -1101,14 +1130,16 @@ O3V_HD void convert_item(const uint8_t* t, int item, const Caps& cap, const Roll
     uint32_t valid = 0;
     bool keep = !too_long && python_float(t, fs, fe, &tv);               // ValueError -> claim dropped (:332)
     // boxes: re.findall(r'\[.*?\]', group 2) without DOTALL
-    for (int64_t i = g0; keep && i < g1;) {
-      if (t[i] != '[') { ++i; continue; }
+    int64_t i = g0;
+    O3V_LOCKSTEP_BEGIN(keep && i < g1)                                  // one box per iteration
+      while (i < g1 && t[i] != '[') ++i;
+      if (i >= g1) continue;
       int64_t j = i + 1;
       while (j < g1 && t[j] != ']' && t[j] != '\n') ++j;
-      if (j >= g1) break;
+      if (j >= g1) { i = g1; continue; }
       if (t[j] == '\n') { i = j + 1; continue; }
       int n; bool numeric; double v[4];
-      if (json_box(t, i, j + 1, &n, &numeric, v) != kJsonList) { keep = false; break; }   // JSONDecodeError
+      if (json_box(t, i, j + 1, &n, &numeric, v) != kJsonList) { keep = false; continue; }   // JSONDecodeError
       if (n == 4 && numeric && nb < 32) {
         valid |= 1u << nb;
         if (nb < cap.Bc) {
@@ -1118,7 +1149,7 @@ O3V_HD void convert_item(const uint8_t* t, int item, const Caps& cap, const Roll
       }
       ++nb;
       i = j + 1;
-    }
+    O3V_LOCKSTEP_END
     o.claim_nbox[item] = keep ? nb : -1;
     if (keep) {
       o.claim_t[item] = tv;
