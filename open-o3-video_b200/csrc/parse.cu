@@ -56,8 +56,12 @@ parse_convert_kernel(const o3v_parse_args a, scan::Scratch* __restrict__ scratch
   const int64_t tile = blockIdx.x % tiles;
   const int item = (int)(blockIdx.x / tiles);
   const int64_t r = tile * kConvertThreads + threadIdx.x;
-  if (r >= a.R || item >= per) return;
-  scan::convert_item(a.text, item, cap, rows_of(a, r), scratch + r);
+  const bool in_range = r < a.R && item < per;
+  const scan::RolloutOut o = rows_of(a, in_range ? r : 0);
+  const bool active = in_range && scan::item_active(item, cap, o, scratch + r);
+  const unsigned lanes = __ballot_sync(0xffffffffu, active);   // the lanes that convert: they stay in lockstep
+  if (!active) return;
+  scan::convert_item(a.text, item, cap, o, scratch + r, lanes);
 }
 
 __global__ void __launch_bounds__(kFinishThreads)

@@ -38,31 +38,39 @@
 #define O3V_HD_NOINLINE inline
 #endif
 
-// A data-dependent loop run by the lanes of a warp on DIFFERENT data: the vote at the top makes the lanes start
-// every iteration together (lanes that are done idle until the last one is), instead of drifting apart until the
-// loop's exit.  The body must leave only through `continue` (no break / return).
+// A data-dependent loop run by the lanes of a warp on DIFFERENT data (phase B).  `lanes` is the set of lanes
+// that run the loop (all of them must reach it); the vote at the top makes them start every iteration together
+// instead of drifting apart until the loop's exit (finished lanes idle until the last one is).  The body must
+// leave only through `continue` (no break / return).  O3V_LOCKSTEP_WHO(p) = the running lanes for which p holds;
+// every running lane must evaluate it (no `continue` before it).
 #if defined(__CUDA_ARCH__)
-#define O3V_LOCKSTEP_BEGIN(cond)                            \
-  {                                                         \
-    const unsigned lockstep_mask__ = __activemask();        \
-    for (;;) {                                              \
-      const bool lockstep_go__ = (cond);                    \
-      if (!__any_sync(lockstep_mask__, lockstep_go__)) break; \
+#define O3V_LOCKSTEP_BEGIN(lanes, cond)                                        \
+  {                                                                            \
+    const unsigned lockstep_all__ = (lanes);                                   \
+    for (;;) {                                                                 \
+      const bool lockstep_go__ = (cond);                                       \
+      const unsigned lockstep_run__ = __ballot_sync(lockstep_all__, lockstep_go__); \
+      if (lockstep_run__ == 0) break;                                          \
       if (lockstep_go__) {
+#define O3V_LOCKSTEP_WHO(pred) __ballot_sync(lockstep_run__, (pred))
 #define O3V_LOCKSTEP_END \
       }                  \
     }                    \
   }
+#define O3V_SYNC_LANES(lanes) __syncwarp(lanes)
 #else
-#define O3V_LOCKSTEP_BEGIN(cond) \
-  {                              \
-    for (;;) {                   \
-      if (!(cond)) break;        \
+#define O3V_LOCKSTEP_BEGIN(lanes, cond) \
+  {                                     \
+    (void)(lanes);                      \
+    for (;;) {                          \
+      if (!(cond)) break;               \
       {
+#define O3V_LOCKSTEP_WHO(pred) ((pred) ? 1u : 0u)
 #define O3V_LOCKSTEP_END \
       }                  \
     }                    \
   }
+#define O3V_SYNC_LANES(lanes) (void)(lanes)
 #endif
 
 namespace o3v {
@@ -792,7 +800,8 @@ O3V_HD int64_t json_number(const uint8_t* t, int64_t p, int64_t e, double* out) 
   return p;
 }
 
-O3V_HD int json_box(const uint8_t* t, int64_t s, int64_t e, int* n_elems, bool* numeric, double out[4]) {
+O3V_HD int json_box(const uint8_t* t, int64_t s, int64_t e, int* n_elems, bool* numeric, double out[4],
+                    unsigned lanes = 0xffffffffu) {
   constexpr Lit kNull = make_lit("null"), kTrue = make_lit("true"), kFalse = make_lit("false"),
                 kNaN = make_lit("NaN"), kInfinity = make_lit("Infinity"), kNegInfinity = make_lit("-Infinity");
   int64_t p = s;
@@ -804,7 +813,7 @@ O3V_HD int json_box(const uint8_t* t, int64_t s, int64_t e, int* n_elems, bool* 
   enum { kValueOrClose, kValue, kAfterValue, kKeyOrClose, kKey, kColon, kDone, kBad };
   int state = kValue;
   // one token per iteration; the lanes of a warp (each on its own payload) start every token together
-  O3V_LOCKSTEP_BEGIN(state < kDone)
+  O3V_LOCKSTEP_BEGIN(lanes, state < kDone)
     while (p < e && json_ws(t[p])) ++p;
     if (p >= e) { state = kBad; continue; }
     const uint8_t c = t[p];
@@ -1101,7 +1110,19 @@ O3V_HD void or_bits(uint32_t* word, uint32_t bits) {
 #endif
 }
 
-O3V_HD void convert_item(const uint8_t* t, int item, const Caps& cap, const RolloutOut& o, Scratch* sc) {
+// does this rollout hold candidate `item`?  (the lanes for which it does run convert_item together)
+O3V_HD bool item_active(int item, const Caps& cap, const RolloutOut& o, const Scratch* sc) {
+  if (item < cap.P) return item < sc->time_cands;
+  item -= cap.P;
+  if (item < cap.C) return item < sc->claim_cands;
+  item -= cap.C;
+  if (item < cap.Tb) return item < sc->tbox_cands;
+  item -= cap.Tb;
+  return (*o.flags & (item == 0 ? kFlagAnsSeg : kFlagAnsBox)) != 0;
+}
+
+O3V_HD void convert_item(const uint8_t* t, int item, const Caps& cap, const RolloutOut& o, Scratch* sc,
+                         unsigned lanes) {
   constexpr Lit kTEnd = make_lit("</t>s");
   if (item < cap.P) {                                                   // ---- "<t>x</t>s" of <think>
     if (item >= sc->time_cands) return;
@@ -1131,24 +1152,31 @@ O3V_HD void convert_item(const uint8_t* t, int item, const Caps& cap, const Roll
     bool keep = !too_long && python_float(t, fs, fe, &tv);               // ValueError -> claim dropped (:332)
     // boxes: re.findall(r'\[.*?\]', group 2) without DOTALL
     int64_t i = g0;
-    O3V_LOCKSTEP_BEGIN(keep && i < g1)                                  // one box per iteration
+    O3V_SYNC_LANES(lanes);
+    O3V_LOCKSTEP_BEGIN(lanes, keep && i < g1)                           // one box per iteration
       while (i < g1 && t[i] != '[') ++i;
-      if (i >= g1) continue;
       int64_t j = i + 1;
-      while (j < g1 && t[j] != ']' && t[j] != '\n') ++j;
-      if (j >= g1) { i = g1; continue; }
-      if (t[j] == '\n') { i = j + 1; continue; }
-      int n; bool numeric; double v[4];
-      if (json_box(t, i, j + 1, &n, &numeric, v) != kJsonList) { keep = false; continue; }   // JSONDecodeError
-      if (n == 4 && numeric && nb < 32) {
-        valid |= 1u << nb;
-        if (nb < cap.Bc) {
-          double* dst = cbox + 4 * nb;
-          dst[0] = v[0]; dst[1] = v[1]; dst[2] = v[2]; dst[3] = v[3];
-        }
+      int found = 0;                                                     // 1: payload [i, j], 2: a newline came first
+      if (i < g1) {
+        while (j < g1 && t[j] != ']' && t[j] != '\n') ++j;
+        found = j >= g1 ? 0 : (t[j] == ']' ? 1 : 2);
       }
-      ++nb;
-      i = j + 1;
+      const unsigned parsers = O3V_LOCKSTEP_WHO(found == 1);
+      if (found == 1) {
+        int n; bool numeric; double v[4];
+        if (json_box(t, i, j + 1, &n, &numeric, v, parsers) != kJsonList) { keep = false; continue; }   // JSONDecodeError
+        if (n == 4 && numeric && nb < 32) {
+          valid |= 1u << nb;
+          if (nb < cap.Bc) {
+            double* dst = cbox + 4 * nb;
+            dst[0] = v[0]; dst[1] = v[1]; dst[2] = v[2]; dst[3] = v[3];
+          }
+        }
+        ++nb;
+        i = j + 1;
+      } else {
+        i = found == 2 ? j + 1 : g1;
+      }
     O3V_LOCKSTEP_END
     o.claim_nbox[item] = keep ? nb : -1;
     if (keep) {
@@ -1164,7 +1192,7 @@ O3V_HD void convert_item(const uint8_t* t, int item, const Caps& cap, const Roll
     double* dst = o.think_box + 4 * item;
     unpack_range(dst[0], &bs, &be);
     int n; bool numeric; double v[4];
-    if (be - bs >= kMaxRange || json_box(t, bs, be, &n, &numeric, v) != kJsonList) return;   // not JSON: skipped
+    if (json_box(t, bs, be - bs >= kMaxRange ? bs : be, &n, &numeric, v, lanes) != kJsonList) return;   // not JSON: skipped
     const bool box = n == 4 && numeric;
     if (box) { dst[0] = v[0]; dst[1] = v[1]; dst[2] = v[2]; dst[3] = v[3]; }
     or_bits(&sc->tbox_kept, 1u << item);
@@ -1185,7 +1213,7 @@ O3V_HD void convert_item(const uint8_t* t, int item, const Caps& cap, const Roll
   int64_t bs, be;
   unpack_range(o.ans_box[0], &bs, &be);
   int n; bool numeric; double v[4];
-  if (be - bs < kMaxRange && json_box(t, bs, be, &n, &numeric, v) == kJsonList && n == 4 && numeric) {
+  if (json_box(t, bs, be - bs >= kMaxRange ? bs : be, &n, &numeric, v, lanes) == kJsonList && n == 4 && numeric) {
     o.ans_box[0] = v[0]; o.ans_box[1] = v[1]; o.ans_box[2] = v[2]; o.ans_box[3] = v[3];
   } else {
     *o.flags &= ~kFlagAnsBox;

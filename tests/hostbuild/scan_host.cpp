@@ -55,7 +55,8 @@ int scan_host_parse(const Args* ap) {
     o.tbox_valid = a.tbox_valid + r; o.think_box = a.think_box + r * (int64_t)a.Tb * 4;
     Scratch sc;
     scan_rollout(a.text, a.offsets[a.R], a.offsets[r], a.offsets[r + 1], a.task[r / a.G], cap, o, &sc, nullptr);
-    for (int item = 0; item < items_per_rollout(cap); ++item) convert_item(a.text, item, cap, o, &sc);
+    for (int item = 0; item < items_per_rollout(cap); ++item)
+      if (item_active(item, cap, o, &sc)) convert_item(a.text, item, cap, o, &sc, 0xffffffffu);
     int over[4];
     finish_rollout(cap, o, &sc, over);
     for (int i = 0; i < 4; ++i)
