@@ -38,12 +38,12 @@ __device__ __forceinline__ scan::RolloutOut rows_of(const o3v_parse_args& a, int
 
 __global__ void __launch_bounds__(kScanWarps * 32, 4)
 parse_scan_kernel(const o3v_parse_args a, scan::Scratch* __restrict__ scratch) {
-  __shared__ uint32_t mask_cache[kScanWarps][scan::Finder::kSmemWords];   // 6 KB per warp
+  extern __shared__ uint32_t mask_cache[];   // kScanWarps x Finder::kSmemWords (6 KB + a 32-entry list per warp)
   const int64_t r = (int64_t)blockIdx.x * kScanWarps + (threadIdx.x >> 5);
   if (r >= a.R) return;                      // whole warp leaves together
   const scan::Caps cap{a.P, a.C, a.Bc, a.Tb};
   scan::scan_rollout(a.text, a.offsets[a.R], a.offsets[r], a.offsets[r + 1], a.task[r / a.G], cap, rows_of(a, r), scratch + r,
-                     mask_cache[threadIdx.x >> 5]);
+                     mask_cache + (threadIdx.x >> 5) * scan::Finder::kSmemWords);
 }
 
 __global__ void __launch_bounds__(kConvertThreads, 4)
@@ -105,7 +105,9 @@ extern "C" int o3v_parse_completions(const o3v_parse_args* args, void* workspace
   auto* scratch = reinterpret_cast<o3v::scan::Scratch*>(workspace);
   O3V_CUDA_TRY(cudaMemsetAsync(a.overflow, 0, 4 * sizeof(int32_t), st));
   const unsigned grid_a = (unsigned)((a.R + o3v::kScanWarps - 1) / o3v::kScanWarps);
-  o3v::parse_scan_kernel<<<grid_a, o3v::kScanWarps * 32, 0, st>>>(a, scratch);
+  const size_t smem_a = (size_t)o3v::kScanWarps * o3v::scan::Finder::kSmemWords * sizeof(uint32_t);
+  O3V_CUDA_TRY(cudaFuncSetAttribute(o3v::parse_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+  o3v::parse_scan_kernel<<<grid_a, o3v::kScanWarps * 32, smem_a, st>>>(a, scratch);
   O3V_LAUNCH_CHECK();
   const int64_t tiles = (a.R + o3v::kConvertThreads - 1) / o3v::kConvertThreads;
   const unsigned grid_b = (unsigned)(tiles * (a.P + a.C + a.Tb + 2));

@@ -165,7 +165,8 @@ struct Finder {
   const uint8_t* t;
   int64_t total;
   static constexpr int kSmemBlocks = 8;                       // blocks of a rollout whose masks stay in smem
-  static constexpr int kSmemWords = kSmemBlocks * (kNumLits / 2) * 32;   // per warp
+  static constexpr int kMaskWords = kSmemBlocks * (kNumLits / 2) * 32;
+  static constexpr int kSmemWords = kMaskWords + 32;           // per warp: mask cache + a 32-entry position list
 #if defined(__CUDA_ARCH__)
   int64_t base;              // start of the block classified in registers (multiple of 512), -1 = none
   uint32_t mask[kNumLits / 2];   // two 16-bit match masks per register
@@ -297,6 +298,26 @@ struct Finder {
       if (best != 0xffffffffu) return blk + best;
       from = blk + 512;
       if (from > last) return -1;
+    }
+  }
+
+  // Per-LANE search in the shared-memory masks (every block of [from, end) must already be cached and
+  // published with __syncwarp): first start position >= from of literal ID, else -1.
+  template <int ID>
+  __device__ __forceinline__ int64_t next_lane(int64_t from, int64_t end) const {
+    const int64_t last = end - lit_of<ID>().n;
+    if (from > last) return -1;
+    uint32_t rel = (uint32_t)(from - first);                  // < kSmemBlocks * 512
+    const uint32_t rel_last = (uint32_t)(last - first);
+    for (;;) {
+      const uint32_t word = sm[(rel >> 9) * (kNumLits / 2) * 32 + (ID >> 1) * 32 + ((rel >> 4) & 31)];
+      const uint32_t m = ((word >> (16 * (ID & 1))) & 0xffffu) & (0xffffu << (rel & 15));
+      if (m) {
+        const uint32_t p = (rel & ~15u) + (uint32_t)(__ffs(m) - 1);
+        return p <= rel_last ? first + p : -1;
+      }
+      rel = (rel & ~15u) + 16;
+      if (rel > rel_last) return -1;
     }
   }
 #else
@@ -1066,6 +1087,61 @@ O3V_HD void scan_rollout(const uint8_t* t, int64_t total, int64_t beg, int64_t e
     // ---- claims (:308-335): <obj>(.*?)</obj>((?:<box>\[.*?\]</box>)+)at<t>(.*?)</t>s, DOTALL.
     // Leftmost match at an <obj>: shortest group 1 = first "</obj><box>[" after it; group 2 ends at
     // the first "]</box>at<t>" after that; group 3 at the first "</t>s" (DESIGN.md section 8).
+#if defined(__CUDA_ARCH__)
+    // Lane-parallel form of the same chain when the span's masks fit the shared-memory cache: all <obj>
+    // occurrences of a block are listed at once, lane i looks up (q, e, z) of occurrence i on its own, and
+    // only the choice "first <obj> at or after the previous match's end" runs serially (on shuffles).
+    bool fast = false;
+    const int lane = threadIdx.x & 31;
+    const int64_t b0 = (ts - f.first) >> 9, b1 = (te - f.first) >> 9;
+    if (b1 < Finder::kSmemBlocks) {
+      fast = true;
+      for (int64_t b = b0; b <= b1; ++b) (void)f.block_mask<kLObj>(f.first + (b << 9), ts, te);
+      __syncwarp();
+      uint32_t* list = f.sm + Finder::kMaskWords;
+      int64_t cur = ts;
+      bool stop = false;
+      for (int64_t b = b0; b <= b1 && !stop; ++b) {
+        const int64_t blk = f.first + (b << 9);
+        uint32_t m = f.block_mask<kLObj>(blk, ts, te - 5);
+        const int cnt = __popc(m);
+        int pre = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, pre, d);
+          if (lane >= d) pre += v;
+        }
+        const int total_objs = __shfl_sync(0xffffffffu, pre, 31);
+        if (total_objs == 0) continue;
+        if (total_objs > 32) { fast = false; break; }          // pathological block: take the sequential chain
+        for (int k = pre - cnt; m; m &= m - 1, ++k) list[k] = (uint32_t)(blk + lane * 16 + (__ffs(m) - 1) - f.first);
+        __syncwarp();
+        int64_t p = -1, q = -1, e = -1, z = -1;
+        if (lane < total_objs) {
+          p = f.first + list[lane];
+          q = f.next_lane<kLObjBox>(p + 5, te);
+          if (q >= 0) e = f.next_lane<kLBoxAt>(q + 12, te);
+          if (e >= 0) z = f.next_lane<kLTEnd>(e + 12, te);
+        }
+        __syncwarp();
+        for (int i = 0; i < total_objs; ++i) {
+          const int64_t pi = __shfl_sync(0xffffffffu, p, i);
+          if (pi < cur) continue;                              // inside the previous match
+          const int64_t zi = __shfl_sync(0xffffffffu, z, i);
+          if (zi < 0) { stop = true; break; }                  // a failed search ends finditer
+          if (lane == i && n_claim < cap.C) {
+            o.claim_t[n_claim] = pack_range(e + 12, z);
+            o.claim_box[(int64_t)n_claim * cap.Bc * 4] = pack_range(q + 6, e + 7);
+          }
+          ++n_claim;
+          cur = zi + 5;
+        }
+      }
+      if (!fast) n_claim = 0;
+    }
+    if (!fast)
+#endif
+    {
     int64_t p = ts;
     for (;;) {
       p = f.find<kLObj>(p, te);
@@ -1082,6 +1158,7 @@ O3V_HD void scan_rollout(const uint8_t* t, int64_t total, int64_t beg, int64_t e
         o.claim_box[(int64_t)n_claim * cap.Bc * 4] = pack_range(q + 6, e + 7);  // group 2
       }
       ++n_claim;
+    }
     }
   }
 
