@@ -56,6 +56,30 @@ def test_parse_alignment_and_long_text():
     assert (got["n_times"] == 1).all()
 
 
+def test_parse_long_completions_cross_the_mask_cache():
+    """Completions longer than the 8 cached 512-byte blocks: padding inserted before / inside / after <think>, so
+    that spans and claim chains start inside the shared-memory cache and end outside it (register-cached blocks,
+    sequential chain) or lie entirely outside."""
+    import random
+    rng = random.Random(3)
+    base, tasks = op.synth_batch(1500, 21)
+    texts = []
+    for t in base:
+        pad = "x" * rng.choice([0, 500, 3000, 3600, 4090, 4100, 6000, 9000])
+        where = rng.random()
+        if where < 0.3:
+            t = pad + t
+        elif where < 0.6:
+            t = t.replace("<think>", "<think>" + pad, 1)
+        elif where < 0.8:
+            i = rng.randrange(len(t) + 1)
+            t = t[:i] + pad + t[i:]
+        else:
+            t = t.replace("</think>", pad + "</think>", 1)
+        texts.append(t)
+    _check(texts, tasks)
+
+
 def test_parse_overflow_relaunch_and_report():
     texts, tasks = op.synth_batch(2000, 9)
     small = dict(P=2, C=1, Bc=1, Tb=1)
