@@ -70,6 +70,24 @@ written = int(dims["R"] * 20 + (rows["n_times"].sum() * 8 + rows["n_claims"].sum
 line("K6 parse completions c4 (65536 rollouts, %.0f B text/rollout, rows P=%d C=%d Bc=%d)" %
      (n_text / dims["R"], caps["P"], caps["C"], caps["Bc"]), n_text + written,
      lambda: rewards.parse_completions_device(d_text, d_off, d_task, 8, caps, sync=False))
+# end to end through the host API: Python strings in, [R, 5] rewards on the host out (UTF-8 encode, H2D, K6, overflow
+# read-back, GT pack, K4, D2H), next to the reference's whole CPU path (regex + numerics) on a sample
+gts = [ro[q * 8] for q in range(len(ro) // 8)]
+rewards.rewards_from_text(texts[:4096], gts[:512], 8, dev)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+e2e_out = rewards.rewards_from_text(texts, gts, 8, dev).cpu()
+dt_e2e = time.perf_counter() - t0
+kws = [orw.render(r)[1] for r in ro[:2048]]
+t0 = time.perf_counter()
+ref_out = [orw.rewards_for_rollout(oparse.rollout_from_text(tx, kw)) for tx, kw in zip(texts[:2048], kws)]
+dt_ref = time.perf_counter() - t0
+assert float((e2e_out[:2048] - torch.tensor(ref_out, dtype=torch.float64)).abs().max()) < 1e-6
+print(json.dumps(dict(kernel="text -> rewards end to end (rewards_from_text: encode + H2D + K6 + K4 + D2H), 65536 rollouts",
+                      seconds=dt_e2e, rollouts_per_s=len(texts) / dt_e2e,
+                      cpu_reference_rollouts_per_s=2048 / dt_ref, cpu_sample="2048 rollouts, oracle port of the whole "
+                      "reward path (regex + numerics), 1 core", speedup_vs_one_core=(len(texts) / dt_e2e) / (2048 / dt_ref))),
+      flush=True)
 t0 = time.perf_counter()
 for tx, r in zip(texts[:4096], ro[:4096]):
     oparse.parse_text(tx, r["task"])
