@@ -115,37 +115,48 @@ def parse_rollout(content: str, task: str, answer: str, key_frames=None, key_ite
 # ----------------------------------------------------------------------------- packing
 def pack_gt(gts: Sequence[dict]):
     """Per-prompt ground truth (dicts with task, step_percent, gt_seg, gt_vbox, key_frames, key_items,
-    image_size, image_size_refine) -> the per-prompt arrays of o3v_rewards_soa, plus dims K, O, Gb."""
+    image_size, image_size_refine) -> the per-prompt arrays of o3v_rewards_soa, plus dims K, O, Gb.
+    Ragged lists are padded in Python and converted with one np.array call per field (element-wise numpy
+    stores cost more than the kernels at BASELINE config 4's 8192 prompts)."""
     Q = len(gts)
-    K = max([len(g["key_frames"]) for g in gts] + [1])
-    O = max([len(g["key_items"].get(str(f["idx"]), {})) for g in gts for f in g["key_frames"]] + [1])
-    Gb = max([len(bx) for g in gts for f in g["key_frames"]
-              for bx in g["key_items"].get(str(f["idx"]), {}).values()] + [1])
-    a = dict(
-        task=np.zeros(Q, np.int32), step_percent=np.zeros(Q), gt_flags=np.zeros(Q, np.int32), gt_seg=np.zeros((Q, 2)),
-        gt_vbox=np.zeros((Q, 4)), image_size=np.ones((Q, 2)), image_refine=np.ones((Q, 2)),
-        n_kf=np.zeros(Q, np.int32), kf_time=np.zeros((Q, K)), n_obj=np.zeros((Q, K), np.int32),
-        n_gtbox=np.zeros((Q, K, O), np.int32), gt_box=np.zeros((Q, K, O, Gb, 4)))
-    for q, g in enumerate(gts):
+    frames = [g["key_frames"] for g in gts]
+    objs = [[list(g["key_items"].get(str(f["idx"]), {}).values()) for f in fr] for g, fr in zip(gts, frames)]
+    K = max([len(fr) for fr in frames] + [1])
+    O = max([len(ob) for fo in objs for ob in fo] + [1])
+    Gb = max([len(bx) for fo in objs for ob in fo for bx in ob] + [1])
+    for g in gts:
         if g["task"] not in TASK_IDS:
             raise ValueError("Unknown task: %s" % g["task"])            # data_loader.py:33
-        a["task"][q] = TASK_IDS[g["task"]]
-        a["step_percent"][q] = g["step_percent"]
-        a["gt_seg"][q] = g["gt_seg"]
-        if g["gt_vbox"] is not None:
-            a["gt_flags"][q] = GF_VBOX
-            a["gt_vbox"][q] = g["gt_vbox"]
-        a["image_size"][q] = g["image_size"]
-        a["image_refine"][q] = g["image_size_refine"]
-        a["n_kf"][q] = len(g["key_frames"])
-        for k, fr in enumerate(g["key_frames"]):
-            a["kf_time"][q, k] = fr["time"]
-            objs = g["key_items"].get(str(fr["idx"]), {})
-            a["n_obj"][q, k] = len(objs)
-            for o, boxes in enumerate(objs.values()):
-                a["n_gtbox"][q, k, o] = len(boxes)
+    zbox = [0.0, 0.0, 0.0, 0.0]
+    # existing entries as flat (index, value) lists, scattered with one fancy assignment per array
+    fq, fk, ft, fn = [], [], [], []                       # per key frame: prompt, slot, time, #objects
+    oq, ok, oo, on = [], [], [], []                       # per object: prompt, frame, slot, #boxes
+    bq, bk, bo, bg, bv = [], [], [], [], []               # per GT box
+    for q, (fr, fo) in enumerate(zip(frames, objs)):
+        for k, (f, ob) in enumerate(zip(fr, fo)):
+            fq.append(q); fk.append(k); ft.append(f["time"]); fn.append(len(ob))
+            for o, boxes in enumerate(ob):
+                oq.append(q); ok.append(k); oo.append(o); on.append(len(boxes))
                 for gi, box in enumerate(boxes):
-                    a["gt_box"][q, k, o, gi] = box
+                    bq.append(q); bk.append(k); bo.append(o); bg.append(gi); bv.append(box)
+    a = dict(
+        task=np.array([TASK_IDS[g["task"]] for g in gts], np.int32).reshape(Q),
+        step_percent=np.array([g["step_percent"] for g in gts], np.float64).reshape(Q),
+        gt_flags=np.array([GF_VBOX if g["gt_vbox"] is not None else 0 for g in gts], np.int32).reshape(Q),
+        gt_seg=np.array([g["gt_seg"] for g in gts], np.float64).reshape(Q, 2),
+        gt_vbox=np.array([g["gt_vbox"] if g["gt_vbox"] is not None else zbox for g in gts], np.float64).reshape(Q, 4),
+        image_size=np.array([g["image_size"] for g in gts], np.float64).reshape(Q, 2),
+        image_refine=np.array([g["image_size_refine"] for g in gts], np.float64).reshape(Q, 2),
+        n_kf=np.array([len(fr) for fr in frames], np.int32).reshape(Q),
+        kf_time=np.zeros((Q, K)), n_obj=np.zeros((Q, K), np.int32), n_gtbox=np.zeros((Q, K, O), np.int32),
+        gt_box=np.zeros((Q, K, O, Gb, 4)))
+    if fq:
+        a["kf_time"][fq, fk] = ft
+        a["n_obj"][fq, fk] = fn
+    if oq:
+        a["n_gtbox"][oq, ok, oo] = on
+    if bq:
+        a["gt_box"][bq, bk, bo, bg] = np.array(bv, np.float64).reshape(len(bv), 4)
     return a, dict(K=K, O=O, Gb=Gb)
 
 
@@ -248,18 +259,40 @@ ROLLOUT_ROWS = (("flags", torch.int32, ()), ("ans_seg", torch.float64, (2,)), ("
 DEFAULT_CAPS = dict(P=16, C=16, Bc=4, Tb=8)
 
 
+_pinned = {}
+
+
+def _pinned_buffer(name: str, nbytes: int) -> torch.Tensor:
+    """A reusable pinned staging buffer (grown geometrically): pinning 50 MB per call costs more than the kernels."""
+    buf = _pinned.get(name)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 16, 2 * (buf.numel() if buf is not None else 0)), dtype=torch.uint8,
+                          pin_memory=torch.cuda.is_available())
+        _pinned[name] = buf
+    return buf
+
+
 def encode_completions(contents: Sequence[str]):
-    """list[str] -> (pinned uint8 tensor padded as o3v_parse_args.text requires, pinned int64 offsets [R+1])."""
-    blobs = [c.encode("utf-8", "surrogatepass") for c in contents]
-    offsets = torch.zeros(len(blobs) + 1, dtype=torch.int64)
-    if blobs:
-        offsets[1:] = torch.cumsum(torch.tensor([len(b) for b in blobs], dtype=torch.int64), 0)
-    total = int(offsets[-1])
-    text = torch.zeros((total + 15) // 16 * 16 + 16, dtype=torch.uint8)
-    if total:
-        text[:total] = torch.frombuffer(bytearray(b"".join(blobs)), dtype=torch.uint8)
-    if torch.cuda.is_available():
-        text, offsets = text.pin_memory(), offsets.pin_memory()
+    """list[str] -> (uint8 tensor padded as o3v_parse_args.text requires, int64 offsets [R+1]), both in pinned
+    host memory when a GPU is present.  The returned text aliases a staging buffer that the next call reuses."""
+    joined = "".join(contents)
+    if joined.isascii():                                    # byte offsets = character offsets
+        blob = joined.encode("ascii")
+        lengths = np.fromiter(map(len, contents), np.int64, len(contents))
+    else:
+        blobs = [c.encode("utf-8", "surrogatepass") for c in contents]
+        blob = b"".join(blobs)
+        lengths = np.fromiter(map(len, blobs), np.int64, len(blobs))
+    total = len(blob)
+    padded = (total + 15) // 16 * 16 + 16
+    text = _pinned_buffer("text", padded)[:padded]
+    tn = text.numpy()
+    tn[:total] = np.frombuffer(blob, np.uint8)
+    tn[total:] = 0
+    offsets = _pinned_buffer("offsets", 8 * (len(contents) + 1))[:8 * (len(contents) + 1)].view(torch.int64)
+    on = offsets.numpy()
+    on[0] = 0
+    np.cumsum(lengths, out=on[1:])
     return text, offsets
 
 
