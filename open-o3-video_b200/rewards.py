@@ -128,17 +128,22 @@ def pack_gt(gts: Sequence[dict]):
         if g["task"] not in TASK_IDS:
             raise ValueError("Unknown task: %s" % g["task"])            # data_loader.py:33
     zbox = [0.0, 0.0, 0.0, 0.0]
-    # existing entries as flat (index, value) lists, scattered with one fancy assignment per array
-    fq, fk, ft, fn = [], [], [], []                       # per key frame: prompt, slot, time, #objects
-    oq, ok, oo, on = [], [], [], []                       # per object: prompt, frame, slot, #boxes
-    bq, bk, bo, bg, bv = [], [], [], [], []               # per GT box
-    for q, (fr, fo) in enumerate(zip(frames, objs)):
-        for k, (f, ob) in enumerate(zip(fr, fo)):
-            fq.append(q); fk.append(k); ft.append(f["time"]); fn.append(len(ob))
-            for o, boxes in enumerate(ob):
-                oq.append(q); ok.append(k); oo.append(o); on.append(len(boxes))
-                for gi, box in enumerate(boxes):
-                    bq.append(q); bk.append(k); bo.append(o); bg.append(gi); bv.append(box)
+    # existing entries as flat lists (comprehensions), their (prompt, frame, object, box) indices from the counts
+    def within(counts):                                   # 0,1,..,c0-1, 0,1,..,c1-1, ...
+        counts = np.asarray(counts, np.int64)
+        starts = np.cumsum(counts) - counts
+        return np.arange(int(counts.sum())) - np.repeat(starts, counts)
+    n_fr = np.array([len(fr) for fr in frames], np.int64)
+    n_ob = np.array([len(ob) for fo in objs for ob in fo], np.int64)              # per frame
+    n_bx = np.array([len(bx) for fo in objs for ob in fo for bx in ob], np.int64)  # per object
+    fq, fk = np.repeat(np.arange(Q), n_fr), within(n_fr)
+    of = np.repeat(np.arange(n_ob.size), n_ob)                                     # object -> frame
+    oq, ok, oo = fq[of], fk[of], within(n_ob)
+    bo_ = np.repeat(np.arange(n_bx.size), n_bx)                                    # box -> object
+    bq, bk, bo, bg = oq[bo_], ok[bo_], oo[bo_], within(n_bx)
+    ft = [f["time"] for fr in frames for f in fr]
+    fn, on = n_ob, n_bx
+    bv = [box for fo in objs for ob in fo for bx in ob for box in bx]
     a = dict(
         task=np.array([TASK_IDS[g["task"]] for g in gts], np.int32).reshape(Q),
         step_percent=np.array([g["step_percent"] for g in gts], np.float64).reshape(Q),
@@ -150,12 +155,12 @@ def pack_gt(gts: Sequence[dict]):
         n_kf=np.array([len(fr) for fr in frames], np.int32).reshape(Q),
         kf_time=np.zeros((Q, K)), n_obj=np.zeros((Q, K), np.int32), n_gtbox=np.zeros((Q, K, O), np.int32),
         gt_box=np.zeros((Q, K, O, Gb, 4)))
-    if fq:
+    if len(ft):
         a["kf_time"][fq, fk] = ft
         a["n_obj"][fq, fk] = fn
-    if oq:
+    if on.size:
         a["n_gtbox"][oq, ok, oo] = on
-    if bq:
+    if len(bv):
         a["gt_box"][bq, bk, bo, bg] = np.array(bv, np.float64).reshape(len(bv), 4)
     return a, dict(K=K, O=O, Gb=Gb)
 
