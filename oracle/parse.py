@@ -292,6 +292,38 @@ def synth_batch(n, seed, tasks=None, wild=True):
     return out, tk
 
 
+_MUT_ALPHABET = list("<>/[]\n tsobjxhinkawer.,0123456789") + [
+    "<t>", "</t>s", "<box>[", "]</box>", "<obj>", "</obj>", "at<t>", "</obj><box>[", "]</box>at<t>", "<think>", "</think>",
+    "<answer>", "</answer>", " to ", "\u2003", "\u0663"]
+
+
+def mutate_batch(n, seed, tasks=None):
+    """synth_batch followed by random character-level edits (insert a tag fragment, delete, duplicate, move or
+    reverse a span): overlapping, nested and truncated tags that the token-level generator never emits."""
+    rng = random.Random(seed)
+    base, tk = synth_batch(n, seed, tasks)
+    out = []
+    for t in base:
+        for _ in range(rng.choice([0, 1, 1, 2, 3, 5, 8])):
+            if not t:
+                break
+            i = rng.randrange(len(t) + 1)
+            r = rng.random()
+            if r < 0.4:
+                t = t[:i] + rng.choice(_MUT_ALPHABET) + t[i:]
+            elif r < 0.7:
+                t = t[:i] + t[min(len(t), i + rng.randint(1, 6)):]
+            elif r < 0.85:
+                j = min(len(t), i + rng.randint(1, 20))
+                t = t[:i] + t[i:j] * 2 + t[j:]
+            else:
+                j = rng.randrange(len(t) + 1)
+                a, b = min(i, j), max(i, j)
+                t = t[:a] + t[b:] + t[a:b] if rng.random() < 0.5 else t[:a] + t[a:b][::-1] + t[b:]
+        out.append(t)
+    return out, tk
+
+
 def encode(texts):
     """list[str] -> (uint8 buffer padded to 16 bytes, int64 offsets [R+1])."""
     blobs = [t.encode("utf-8", "surrogatepass") for t in texts]

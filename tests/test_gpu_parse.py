@@ -42,6 +42,12 @@ def test_parse_bit_exact_on_wild_text(seed):
     assert (exp["n_claims"] > 0).sum() > 400 and (exp["n_times"] > 0).sum() > 1500
 
 
+@pytest.mark.parametrize("seed", [101, 107])
+def test_parse_bit_exact_on_mutated_text(seed):
+    texts, tasks = op.mutate_batch(8000, seed)
+    _check(texts, tasks)
+
+
 @pytest.mark.parametrize("task", op.TASKS)
 def test_parse_edge_cases(task):
     _check(EDGE_TEXTS, [task] * len(EDGE_TEXTS))

@@ -82,6 +82,13 @@ def test_scanner_bit_exact_on_wild_text(seed):
     assert (exp["n_claims"] > 0).sum() > 300 and (exp["n_times"] > 0).sum() > 1000 and (exp["n_tboxes"] > 0).sum() > 100
 
 
+@pytest.mark.parametrize("seed", [101, 102])
+def test_scanner_bit_exact_on_mutated_text(seed):
+    texts, tasks = op.mutate_batch(8000, seed)
+    bad, got, exp, ov = _compare(texts, tasks)
+    assert not bad, [(r, k, texts[r][:120]) for r, k in sorted(bad)[:5]]
+
+
 def test_scanner_capacity_overflow_report():
     """Too-small rows: the report names a capacity that fits, rollouts that fitted are already exact."""
     texts, tasks = op.synth_batch(3000, 9)
