@@ -28,6 +28,16 @@ def auto_chunk_tokens(v_local: int) -> int:
 SAVE_LOGITS_BYTES = 24 << 30
 
 
+_side_streams = {}
+
+
+def _side_stream(dev):
+    key = torch.device(dev).index
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=dev)
+    return _side_streams[key]
+
+
 def _check_head(hidden, weight, targets):
     _need_cuda(hidden, weight, targets)
     if hidden.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
@@ -229,7 +239,7 @@ def fused_logprob_gspo(hidden: torch.Tensor, weight: torch.Tensor, completion_id
                        epsilon_low: float = 0.2, epsilon_high: float = 0.2, gspo: bool = True,
                        old_per_token_logps: Optional[torch.Tensor] = None, *, v_offset: int = 0, group=None,
                        chunk_tokens: int = DEFAULT_CHUNK_TOKENS, need_grad: bool = True,
-                       d_weight_out: Optional[torch.Tensor] = None):
+                       d_weight_out: Optional[torch.Tensor] = None, overlap_dlogits: bool = False):
     """The whole policy-objective step in one call: per-token log-probs, KL, group advantages,
     GSPO loss AND the gradients w.r.t. hidden and lm_head.weight (grpo_trainer.py:612-613,
     635-636, 658-706 + their backward), chunked over whole sequences.
@@ -268,21 +278,58 @@ def fused_logprob_gspo(hidden: torch.Tensor, weight: torch.Tensor, completion_id
     if need_grad:
         d_weight = d_weight_out if d_weight_out is not None else torch.empty(V, H, dtype=torch.float32, device=dev)
     state = {}
+    # Software pipeline over chunks (overlap_dlogits): the HBM-bound dlogits pass of chunk c runs on a side
+    # stream beside the tensor-bound K1 of chunk c+1 (its CTAs use no shared memory and co-reside with the
+    # persistent GEMM CTAs), then the two backward GEMMs of chunk c follow on the main stream.  Needs a second
+    # logits buffer.  Order of work on the device:  F0 | F1 + D0 | B0 | F2 + D1 | B1 | ... | D(n-1) | B(n-1).
+    pipelined = bool(need_grad and overlap_dlogits and n_chunks > 1)
+    zbuf2 = torch.empty_like(zbuf) if pipelined else None
+    main = torch.cuda.current_stream(dev)
+    side = _side_stream(dev) if pipelined else None
+
+    def backward_gemms(ci, s, e, z):
+        bwd_dhidden(z, weight, out=d_hidden[s:e])
+        if peer_dh:
+            group.allreduce_dh_async(s, e - s)                # runs beside the dW GEMM below
+        bwd_dweight(z, hidden2[s:e], d_weight, accumulate=(ci > 0) or (d_weight_out is not None))
+
+    pending = None                                            # chunk whose backward GEMMs are still to be enqueued
     for ci, n0 in enumerate(range(0, N, seqs)):
         n1 = min(N, n0 + seqs)
         s, e = n0 * Tc, n1 * Tc
-        z = zbuf[: e - s] if need_grad else None
+        z = None
+        if need_grad:
+            z = (zbuf2 if (pipelined and (ci & 1)) else zbuf)[: e - s]
         lp, lse = _stats_to_logp(hidden2[s:e], weight, targets[s:e], v_offset, z, group)
         logp[n0:n1] = lp.view(n1 - n0, Tc)
         state, g, _ = gspo_raw(logp[n0:n1], ref[n0:n1], mask[n0:n1], rpf, num_generations, beta, epsilon_low,
                                epsilon_high, gspo, None if old is None else old[n0:n1], want_grad=need_grad,
                                want_kl=False, N_total=N, seq_offset=n0, state=state)
-        if need_grad:
+        if not need_grad:
+            continue
+        if not pipelined:
             dlogits_(z, lse, g.view(-1), targets[s:e], v_offset)
-            bwd_dhidden(z, weight, out=d_hidden[s:e])
-            if peer_dh:
-                group.allreduce_dh_async(s, e - s)            # runs beside the dW GEMM below
-            bwd_dweight(z, hidden2[s:e], d_weight, accumulate=(ci > 0) or (d_weight_out is not None))
+            backward_gemms(ci, s, e, z)
+            continue
+        if pending is not None:                               # B(c-1): its dlogits ran beside this chunk's K1
+            main.wait_event(pending[-1])
+            backward_gemms(*pending[:4])
+        last = ci == n_chunks - 1
+        done = torch.cuda.Event()
+        if last:                                              # nothing left to hide it behind
+            dlogits_(z, lse, g.view(-1), targets[s:e], v_offset)
+            done.record(main)
+        else:
+            ready = torch.cuda.Event()
+            ready.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ready)
+                dlogits_(z, lse, g.view(-1), targets[s:e], v_offset)
+                done.record(side)
+        pending = (ci, s, e, z, lse, g, done)                 # lse / g stay referenced until the side stream is done
+    if pending is not None:
+        main.wait_event(pending[-1])
+        backward_gemms(*pending[:4])
     if need_grad and peer_dh:
         group.wait_allreduce()
     elif need_grad and group is not None:

@@ -68,6 +68,22 @@ def test_fused_step_matches_oracle(N, Tc, G, H, V, chunk, off_policy, cta):
     assert (dH.view(N, Tc, H)[mask == 0] == 0).all()
 
 
+@pytest.mark.parametrize("N,Tc,chunk", [(8, 64, 128), (9, 100, 300), (6, 256, 256)])
+def test_pipelined_dlogits_is_bit_identical(N, Tc, chunk):
+    """overlap_dlogits only reorders launches across streams: every output must be bit-identical."""
+    from open_o3_video_b200 import logprob
+    G = 3 if N == 9 else 2
+    hidden, weight, ids, ref, mask, rpf, old = _inputs(N, Tc, G, 256, 5000, True, seed=5)
+    args = (hidden.cuda().bfloat16(), weight.cuda().bfloat16(), ids.cuda(), ref.cuda(), mask.cuda(), rpf.cuda(), G, 0.04,
+            0.2, 0.2, True, old.cuda())
+    a = logprob.fused_logprob_gspo(*args, chunk_tokens=chunk, overlap_dlogits=False)
+    for _ in range(3):                                        # repeated: buffer reuse across steps and streams
+        b = logprob.fused_logprob_gspo(*args, chunk_tokens=chunk, overlap_dlogits=True)
+    torch.cuda.synchronize()
+    for k in ("loss", "per_token_logps", "advantages", "mean_kl", "d_hidden", "d_weight"):
+        assert torch.equal(a[k], b[k]), k
+
+
 def test_c1_shape_known_answer():
     """BASELINE config 1 / SURVEY Appendix B: 7B head, 1 x 4 x 512 tokens, on-policy,
     ref = logp + 0.1, rewards [0.5, 2.0, 1.25, 3.0], full mask -> loss = 0.000207."""
