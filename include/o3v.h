@@ -49,7 +49,9 @@ int o3v_check_device(void);
  *   "cta_pair"   1 = one CTA per 128-row tile, 2 = cta_group::2 pairs (256-row tiles), all GEMMs;
  *                "cta_pair_fwd" / "cta_pair_bwd" set it for K1 / K2 only (defaults 1 / 2)
  *   "fwd_groups" vocab splits per token block in K1 (0 = auto)
- *   "max_ctas"   cap on the persistent grid (0 = all SMs) */
+ *   "max_ctas"   cap on the persistent grid (0 = all SMs)
+ *   "hint_fwd_a" / "hint_fwd_b" / "hint_fwd_store" / "hint_bwd_a" / "hint_bwd_b"  L2 eviction hint of the TMA
+ *                loads of operand A / B and of the logits store (0 = none, 1 = evict first, 2 = evict last) */
 int o3v_set_tunable(const char* name, int value);
 /* Diagnostic: the tcgen05 GEMM template on an arbitrary problem, D[M,N] (+)= A . B^T with
  * bf16 operands.  a_mn / b_mn = 0: operand stored [rows, K] (K contiguous, "K-major");

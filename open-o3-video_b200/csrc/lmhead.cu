@@ -21,6 +21,8 @@ static int g_dh_mfast = 0;      // K2a item order (0 = n fastest)
 static int g_dw_mfast = 0;      // K2b item order
 static int g_fwd_groups = 0;    // n-groups (vocab splits) per m-block in K1; 0 = auto
 static int g_max_ctas = 0;      // cap on the persistent grid; 0 = all SMs
+// L2 eviction hints (0 none, 1 evict first, 2 evict last): K1 hidden / W loads and logits store, K2 P / other operand
+static int g_hint_fwd_a = 0, g_hint_fwd_b = 0, g_hint_fwd_store = 0, g_hint_bwd_a = 0, g_hint_bwd_b = 0;
 
 // ------------------------------------------------------------------------------------
 // TMA descriptors (driver entry point fetched through the runtime: no libcuda link)
@@ -278,6 +280,11 @@ extern "C" int o3v_set_tunable(const char* name, int value) {
   else if (n == "dw_mfast") g_dw_mfast = value ? 1 : 0;
   else if (n == "fwd_groups") g_fwd_groups = value;
   else if (n == "max_ctas") g_max_ctas = value;
+  else if (n == "hint_fwd_a") g_hint_fwd_a = value;
+  else if (n == "hint_fwd_b") g_hint_fwd_b = value;
+  else if (n == "hint_fwd_store") g_hint_fwd_store = value;
+  else if (n == "hint_bwd_a") g_hint_bwd_a = value;
+  else if (n == "hint_bwd_b") g_hint_bwd_b = value;
   else return O3V_ERR_INVALID_ARG;
   return O3V_OK;
 }
@@ -311,6 +318,7 @@ extern "C" int o3v_lmhead_fwd(const void* hidden, const void* weight, const int6
   if (workspace_bytes < (size_t)p.num_n_groups * 3 * T * sizeof(float)) return O3V_ERR_WORKSPACE;
   p.targets = targets; p.v_offset = v_offset; p.parts = reinterpret_cast<float*>(workspace);
   p.logits = reinterpret_cast<__nv_bfloat16*>(logits); p.ld_logits = ld_logits;
+  p.hint_a = g_hint_fwd_a; p.hint_b = g_hint_fwd_b; p.hint_store = g_hint_fwd_store;
   CUtensorMap tmA, tmB, tmC = {};
   if ((rc = make_tmap_bf16(&tmA, hidden, H, T, H, 128))) return rc;
   if ((rc = make_tmap_bf16(&tmB, weight, H, V, H, 256 / ncta))) return rc;
@@ -401,6 +409,7 @@ extern "C" int o3v_lmhead_bwd_dhidden(const void* dlogits, int64_t ld_dlogits, c
   const bool wide = (ncta == 2 && g_bwd_wide);
   plan_tiles(p, ncta, 1 << 20, wide ? 2 : 1);       // one n-tile per item
   p.out = d_hidden; p.ld_out = H; p.out_fp32 = out_is_fp32 ? 1 : 0; p.m_fast = g_dh_mfast;
+  p.hint_a = g_hint_bwd_a; p.hint_b = g_hint_bwd_b;
   CUtensorMap tmA, tmB;
   if ((rc = make_tmap_bf16(&tmA, dlogits, V, T, ld_dlogits, 128))) return rc;   // A = P, K-major (K = V)
   if ((rc = make_tmap_bf16(&tmB, weight, H, V, H, 64))) return rc;              // B = W, MN-major (N = H contiguous)
@@ -426,6 +435,7 @@ extern "C" int o3v_lmhead_bwd_dweight(const void* dlogits, int64_t ld_dlogits, c
   const bool wide = (ncta == 2 && g_bwd_wide);
   plan_tiles(p, ncta, 1 << 20, wide ? 2 : 1);
   p.out = d_weight; p.ld_out = H; p.out_fp32 = 1; p.accumulate = accumulate ? 1 : 0; p.m_fast = g_dw_mfast;
+  p.hint_a = g_hint_bwd_a; p.hint_b = g_hint_bwd_b;
   CUtensorMap tmA, tmB;
   if ((rc = make_tmap_bf16(&tmA, dlogits, V, T, ld_dlogits, 64))) return rc;    // A = P^T, MN-major (M = V contiguous)
   if ((rc = make_tmap_bf16(&tmB, hidden, H, T, H, 64))) return rc;              // B = hidden, MN-major

@@ -51,6 +51,8 @@ struct GemmParams {
   int64_t ld_out;
   int32_t out_fp32;
   int32_t accumulate;
+  // L2 eviction hints of the TMA traffic (0 = none, 1 = evict first, 2 = evict last)
+  int32_t hint_a, hint_b, hint_store;
 };
 
 // kAcc = 1: 256-column tiles, the two TMEM accumulator stages double-buffer the epilogue.
@@ -187,8 +189,14 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               else ptx::mbar_arrive_cluster(&full[stage], 0);
             }
             auto load = [&](void* dst, const CUtensorMap* tm, int c0, int c1) {
-              if constexpr (kNCta == 1) ptx::tma_load_2d(dst, tm, &full[stage], c0, c1);
-              else ptx::tma_load_2d_2sm(dst, tm, &full[stage], c0, c1);
+              const int hint = (tm == &tmA) ? p.hint_a : p.hint_b;
+              if (hint == 0) {
+                if constexpr (kNCta == 1) ptx::tma_load_2d(dst, tm, &full[stage], c0, c1);
+                else ptx::tma_load_2d_2sm(dst, tm, &full[stage], c0, c1);
+              } else {
+                if constexpr (kNCta == 1) ptx::tma_load_2d_hint(dst, tm, &full[stage], c0, c1, ptx::l2_policy(hint));
+                else ptx::tma_load_2d_2sm_hint(dst, tm, &full[stage], c0, c1, ptx::l2_policy(hint));
+              }
             };
             if constexpr (!kAMN) {
               load(sa, &tmA, k0, m0);                                   // [128 rows][64 k] K-major
@@ -327,7 +335,9 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 __syncwarp();
                 if (lane == 0) {
                   const int32_t r0 = (int32_t)((int64_t)m_blk * S::UMMA_M + (int64_t)rank * BM + q * 32);
-                  ptx::tma_store_2d(&tmC, stg_warp + sbuf * 4096u, (int32_t)(n0 + cbase - 32), r0);
+                  if (p.hint_store == 0) ptx::tma_store_2d(&tmC, stg_warp + sbuf * 4096u, (int32_t)(n0 + cbase - 32), r0);
+                  else ptx::tma_store_2d_hint(&tmC, stg_warp + sbuf * 4096u, (int32_t)(n0 + cbase - 32), r0,
+                                              ptx::l2_policy(p.hint_store));
                   ptx::bulk_commit();
                 }
                 sbuf ^= 1u;
