@@ -320,8 +320,10 @@ def run_ours(args):
         dtype="bf16", data="synthetic",
         config=dict(workload="%s: %s head (H=%d, V=%d), %d prompts x G=%d x %d completion tokens = %d tokens/step, "
                              "fused logprob+GSPO fwd+bwd" % (args.config, cfg["head"], H, V, cfg["prompts"], G, Tc, T),
-                    parallelism="vocab-sharded x%d (%s exchange of softmax triples, NCCL all-reduce of dHidden)"
-                                % (world, "fused NVLink peer-memory" if args.exchange == "peer" else "NCCL all-gather")
+                    parallelism="vocab-sharded x%d (%s exchange of softmax triples, %s of dHidden)"
+                                % (world, "fused NVLink peer-memory" if args.exchange == "peer" else "NCCL all-gather",
+                                   "one-shot P2P all-reduce beside the dW GEMM"
+                                   if (args.exchange == "peer" and args.overlap_allreduce) else "NCCL all-reduce")
                     if world > 1 else "single GPU", chunk_tokens=args.chunk_tokens,
                     cache="inputs (%.1f GB) and per-chunk logits are far larger than the 126 MB L2; no flush needed"
                           % ((hidden.numel() * 2 + weight.numel() * 2) / 1e9), loss=loss),
