@@ -15,6 +15,8 @@ Public API (mirrors the reference, src/r1-v/src/open_r1/):
   logprob.fused_logprob_gspo                   the whole step, chunked fwd+bwd in one call
   rewards.<reference reward names>             reward_func.py
   trainer.O3VB200TrainerMixin                  drop-in _get_per_token_logps / hot compute_loss
-  sharded.*                                    vocab-parallel multi-GPU (NCCL)
+  sharded.*                                    vocab-parallel multi-GPU (NCCL / peer memory)
+  ops (torch.ops.o3v.*)                        the same launches as registered operators (schema, fake
+                                               kernels, autograd) for torch.compile / torch.export
 """
 __version__ = "0.1.0"
