@@ -272,8 +272,8 @@ int o3v_vstar_scores(const o3v_vstar_soa* soa, double* out, void* stream);
  *            overflow = (think times, claims, boxes per claim, think boxes).
  *   outputs  rows are written only up to the counts (no zero fill); slots past a count may hold
  *            scratch values.
- * workspace: o3v_parse_workspace_bytes(R) bytes, 8-byte aligned (per-rollout records passed between
- * the three launches: span ends, candidate counts).
+ * workspace: o3v_parse_workspace_bytes(R, P, C, Tb) bytes, 8-byte aligned (per-rollout records passed between
+ * the three launches: span ends, candidate counts; and the dense work lists of the conversion launch).
  * ---------------------------------------------------------------------------------- */
 typedef struct o3v_parse_args {
   int64_t R;
@@ -298,7 +298,7 @@ typedef struct o3v_parse_args {
   int32_t* overflow;     /* [4] */
 } o3v_parse_args;
 
-size_t o3v_parse_workspace_bytes(int64_t R);
+size_t o3v_parse_workspace_bytes(int64_t R, int32_t P, int32_t C, int32_t Tb);
 int o3v_parse_completions(const o3v_parse_args* args, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus

@@ -67,7 +67,7 @@ SIGNATURES = {
                                  c_void_p, c_size_t, c_void_p]),
     "o3v_grounded_rewards": (c_int, [ctypes.POINTER(RewardsSoA), c_void_p, c_void_p]),
     "o3v_vstar_scores": (c_int, [ctypes.POINTER(VstarSoA), c_void_p, c_void_p]),
-    "o3v_parse_workspace_bytes": (c_size_t, [c_int64]),
+    "o3v_parse_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32, c_int32]),
     "o3v_parse_completions": (c_int, [ctypes.POINTER(ParseArgs), c_void_p, c_size_t, c_void_p]),
 }
 

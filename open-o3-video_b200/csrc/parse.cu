@@ -36,32 +36,81 @@ __device__ __forceinline__ scan::RolloutOut rows_of(const o3v_parse_args& a, int
   return o;
 }
 
+// Work lists between A and B: A appends every candidate of the three list-like item types to a dense
+// list (one atomicAdd per rollout and type reserves the range), so that B's warps are full however
+// unevenly the candidates are spread over the rollouts.  Entry = rollout * capacity + slot.
+struct WorkLists {
+  unsigned int* count;    // [4]: claims, think times, think boxes, (unused)
+  uint32_t* claims;       // [R * C]
+  uint32_t* times;        // [R * P]
+  uint32_t* tboxes;       // [R * Tb]
+};
+__host__ __device__ inline size_t lists_offset(int64_t R) {
+  return ((size_t)R * sizeof(scan::Scratch) + 15) & ~(size_t)15;
+}
+__host__ __device__ inline WorkLists work_lists(void* workspace, const o3v_parse_args& a) {
+  char* base = reinterpret_cast<char*>(workspace) + lists_offset(a.R);
+  WorkLists w;
+  w.count = reinterpret_cast<unsigned int*>(base);
+  w.claims = reinterpret_cast<uint32_t*>(base + 16);
+  w.times = w.claims + (size_t)a.R * a.C;
+  w.tboxes = w.times + (size_t)a.R * a.P;
+  return w;
+}
+
+__device__ __forceinline__ void append_range(unsigned int* counter, uint32_t* list, uint32_t first_entry, int n) {
+  const int lane = threadIdx.x & 31;
+  unsigned int base = 0;
+  if (lane == 0 && n > 0) base = atomicAdd(counter, (unsigned int)n);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  for (int k = lane; k < n; k += 32) list[base + k] = first_entry + (uint32_t)k;
+}
+
 __global__ void __launch_bounds__(kScanWarps * 32, 4)
-parse_scan_kernel(const o3v_parse_args a, scan::Scratch* __restrict__ scratch) {
+parse_scan_kernel(const o3v_parse_args a, scan::Scratch* __restrict__ scratch, const WorkLists w) {
   extern __shared__ uint32_t mask_cache[];   // kScanWarps x Finder::kSmemWords (6 KB + a 32-entry list per warp)
   const int64_t r = (int64_t)blockIdx.x * kScanWarps + (threadIdx.x >> 5);
   if (r >= a.R) return;                      // whole warp leaves together
   const scan::Caps cap{a.P, a.C, a.Bc, a.Tb};
-  scan::scan_rollout(a.text, a.offsets[a.R], a.offsets[r], a.offsets[r + 1], a.task[r / a.G], cap, rows_of(a, r), scratch + r,
+  scan::Scratch* sc = scratch + r;
+  scan::scan_rollout(a.text, a.offsets[a.R], a.offsets[r], a.offsets[r + 1], a.task[r / a.G], cap, rows_of(a, r), sc,
                      mask_cache + (threadIdx.x >> 5) * scan::Finder::kSmemWords);
+  __syncwarp();                              // lane 0 wrote the counts
+  append_range(w.count + 0, w.claims, (uint32_t)(r * a.C), min(sc->claim_cands, a.C));
+  append_range(w.count + 1, w.times, (uint32_t)(r * a.P), min(sc->time_cands, a.P));
+  append_range(w.count + 2, w.tboxes, (uint32_t)(r * a.Tb), min(sc->tbox_cands, a.Tb));
 }
 
+// B: CTA ranges [claims | think times | think boxes | answers]; within a range thread i converts list entry i
+// (answers: rollout i / 2, segment or box), so all lanes of a warp run the same routine on dense work.
 __global__ void __launch_bounds__(kConvertThreads, 4)
-parse_convert_kernel(const o3v_parse_args a, scan::Scratch* __restrict__ scratch) {
+parse_convert_kernel(const o3v_parse_args a, scan::Scratch* __restrict__ scratch, const WorkLists w,
+                     unsigned nb_claims, unsigned nb_times, unsigned nb_tboxes) {
   const scan::Caps cap{a.P, a.C, a.Bc, a.Tb};
-  // item-major: the 128 threads of a CTA convert the SAME item of 128 consecutive rollouts, so every lane
-  // of a warp runs the same routine (all time candidates k, or all claims c, ...)
-  const int per = scan::items_per_rollout(cap);
-  const int64_t tiles = (a.R + kConvertThreads - 1) / kConvertThreads;
-  const int64_t tile = blockIdx.x % tiles;
-  const int item = (int)(blockIdx.x / tiles);
-  const int64_t r = tile * kConvertThreads + threadIdx.x;
-  const bool in_range = r < a.R && item < per;
-  const scan::RolloutOut o = rows_of(a, in_range ? r : 0);
-  const bool active = in_range && scan::item_active(item, cap, o, scratch + r);
+  unsigned b = blockIdx.x;
+  int64_t r = 0;
+  int item = 0;
+  bool active = false;
+  if (b < nb_claims) {
+    const int64_t i = (int64_t)b * kConvertThreads + threadIdx.x;
+    if (i < (int64_t)w.count[0]) { const uint32_t e = w.claims[i]; r = e / (uint32_t)a.C; item = a.P + (int)(e % (uint32_t)a.C); active = true; }
+  } else if ((b -= nb_claims) < nb_times) {
+    const int64_t i = (int64_t)b * kConvertThreads + threadIdx.x;
+    if (i < (int64_t)w.count[1]) { const uint32_t e = w.times[i]; r = e / (uint32_t)a.P; item = (int)(e % (uint32_t)a.P); active = true; }
+  } else if ((b -= nb_times) < nb_tboxes) {
+    const int64_t i = (int64_t)b * kConvertThreads + threadIdx.x;
+    if (i < (int64_t)w.count[2]) { const uint32_t e = w.tboxes[i]; r = e / (uint32_t)a.Tb; item = a.P + a.C + (int)(e % (uint32_t)a.Tb); active = true; }
+  } else {
+    b -= nb_tboxes;                                                     // answers: a CTA range of segments, then one of boxes
+    const unsigned nb_rollouts = (unsigned)((a.R + kConvertThreads - 1) / kConvertThreads);
+    const int which = b >= nb_rollouts ? 1 : 0;                         // (a warp never mixes item types: its lanes share
+    r = (int64_t)(b - which * nb_rollouts) * kConvertThreads + threadIdx.x;   //  lockstep loops)
+    item = a.P + a.C + a.Tb + which;
+    active = r < a.R && scan::item_active(item, cap, rows_of(a, r), scratch + r);
+  }
   const unsigned lanes = __ballot_sync(0xffffffffu, active);   // the lanes that convert: they stay in lockstep
   if (!active) return;
-  scan::convert_item(a.text, item, cap, o, scratch + r, lanes);
+  scan::convert_item(a.text, item, cap, rows_of(a, r), scratch + r, lanes);
 }
 
 __global__ void __launch_bounds__(kFinishThreads)
@@ -78,8 +127,9 @@ parse_finish_kernel(const o3v_parse_args a, const scan::Scratch* __restrict__ sc
 
 }  // namespace o3v
 
-extern "C" size_t o3v_parse_workspace_bytes(int64_t R) {
-  return (size_t)(R > 0 ? R : 0) * sizeof(o3v::scan::Scratch);
+extern "C" size_t o3v_parse_workspace_bytes(int64_t R, int32_t P, int32_t C, int32_t Tb) {
+  if (R <= 0 || P < 0 || C < 0 || Tb < 0) return 0;
+  return o3v::lists_offset(R) + 16 + (size_t)R * ((size_t)P + C + Tb) * sizeof(uint32_t);
 }
 
 extern "C" int o3v_parse_completions(const o3v_parse_args* args, void* workspace, size_t workspace_bytes,
@@ -99,7 +149,9 @@ extern "C" int o3v_parse_completions(const o3v_parse_args* args, void* workspace
       !a.tbox_valid || !a.think_box || !a.overflow)
     return O3V_ERR_INVALID_ARG;
   if (((uintptr_t)a.text & 15u) || ((uintptr_t)workspace & 7u)) return O3V_ERR_ALIGNMENT;
-  if (!workspace || workspace_bytes < o3v_parse_workspace_bytes(a.R)) return O3V_ERR_WORKSPACE;
+  if (!workspace || workspace_bytes < o3v_parse_workspace_bytes(a.R, a.P, a.C, a.Tb)) return O3V_ERR_WORKSPACE;
+  const int64_t cap_max = a.P > a.C ? (a.P > a.Tb ? a.P : a.Tb) : (a.C > a.Tb ? a.C : a.Tb);
+  if (a.R * cap_max >= ((int64_t)1 << 32)) return O3V_ERR_SHAPE;            // work-list entries are 32-bit
   int rc = o3v::check_device();
   if (rc) return rc;
   auto* scratch = reinterpret_cast<o3v::scan::Scratch*>(workspace);
@@ -107,11 +159,14 @@ extern "C" int o3v_parse_completions(const o3v_parse_args* args, void* workspace
   const unsigned grid_a = (unsigned)((a.R + o3v::kScanWarps - 1) / o3v::kScanWarps);
   const size_t smem_a = (size_t)o3v::kScanWarps * o3v::scan::Finder::kSmemWords * sizeof(uint32_t);
   O3V_CUDA_TRY(cudaFuncSetAttribute(o3v::parse_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
-  o3v::parse_scan_kernel<<<grid_a, o3v::kScanWarps * 32, smem_a, st>>>(a, scratch);
+  const o3v::WorkLists lists = o3v::work_lists(workspace, a);
+  O3V_CUDA_TRY(cudaMemsetAsync(lists.count, 0, 16, st));
+  o3v::parse_scan_kernel<<<grid_a, o3v::kScanWarps * 32, smem_a, st>>>(a, scratch, lists);
   O3V_LAUNCH_CHECK();
-  const int64_t tiles = (a.R + o3v::kConvertThreads - 1) / o3v::kConvertThreads;
-  const unsigned grid_b = (unsigned)(tiles * (a.P + a.C + a.Tb + 2));
-  o3v::parse_convert_kernel<<<grid_b, o3v::kConvertThreads, 0, st>>>(a, scratch);
+  auto blocks = [](int64_t n) { return (unsigned)((n + o3v::kConvertThreads - 1) / o3v::kConvertThreads); };
+  const unsigned nb_claims = blocks(a.R * a.C), nb_times = blocks(a.R * a.P), nb_tboxes = blocks(a.R * a.Tb);
+  const unsigned grid_b = nb_claims + nb_times + nb_tboxes + 2 * blocks(a.R);
+  o3v::parse_convert_kernel<<<grid_b, o3v::kConvertThreads, 0, st>>>(a, scratch, lists, nb_claims, nb_times, nb_tboxes);
   O3V_LAUNCH_CHECK();
   const unsigned grid_c = (unsigned)((a.R + o3v::kFinishThreads - 1) / o3v::kFinishThreads);
   o3v::parse_finish_kernel<<<grid_c, o3v::kFinishThreads, 0, st>>>(a, scratch);

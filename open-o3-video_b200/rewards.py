@@ -316,8 +316,9 @@ def parse_completions_device(text: torch.Tensor, offsets: torch.Tensor, task: to
     caps = dict(DEFAULT_CAPS if caps is None else caps)
     dev = text.device
     with torch.cuda.device(dev):
-        ws = torch.empty(max(1, lib.o3v_parse_workspace_bytes(R) // 8), dtype=torch.int64, device=dev)
         while True:
+            ws = torch.empty(max(1, (lib.o3v_parse_workspace_bytes(R, caps["P"], caps["C"], caps["Tb"]) + 7) // 8),
+                             dtype=torch.int64, device=dev)
             out = {"overflow": torch.empty(4, dtype=torch.int32, device=dev)}
             for name, dt, shape in ROLLOUT_ROWS:
                 out[name] = torch.empty((R,) + tuple(caps[d] if isinstance(d, str) else d for d in shape),
