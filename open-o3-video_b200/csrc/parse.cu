@@ -58,12 +58,18 @@ __host__ __device__ inline WorkLists work_lists(void* workspace, const o3v_parse
   return w;
 }
 
-__device__ __forceinline__ void append_range(unsigned int* counter, uint32_t* list, uint32_t first_entry, int n) {
+// lanes 0..2 reserve the three ranges with one atomicAdd each (in flight together), then all lanes fill them
+__device__ __forceinline__ void append_candidates(const WorkLists& w, const o3v_parse_args& a, int64_t r,
+                                                  int n_claims, int n_times, int n_tboxes) {
   const int lane = threadIdx.x & 31;
+  const int mine = lane == 0 ? n_claims : lane == 1 ? n_times : lane == 2 ? n_tboxes : 0;
   unsigned int base = 0;
-  if (lane == 0 && n > 0) base = atomicAdd(counter, (unsigned int)n);
-  base = __shfl_sync(0xffffffffu, base, 0);
-  for (int k = lane; k < n; k += 32) list[base + k] = first_entry + (uint32_t)k;
+  if (mine > 0) base = atomicAdd(w.count + lane, (unsigned int)mine);
+  const unsigned int b0 = __shfl_sync(0xffffffffu, base, 0), b1 = __shfl_sync(0xffffffffu, base, 1),
+                     b2 = __shfl_sync(0xffffffffu, base, 2);
+  for (int k = lane; k < n_claims; k += 32) w.claims[b0 + k] = (uint32_t)(r * a.C) + (uint32_t)k;
+  for (int k = lane; k < n_times; k += 32) w.times[b1 + k] = (uint32_t)(r * a.P) + (uint32_t)k;
+  for (int k = lane; k < n_tboxes; k += 32) w.tboxes[b2 + k] = (uint32_t)(r * a.Tb) + (uint32_t)k;
 }
 
 __global__ void __launch_bounds__(kScanWarps * 32, 4)
@@ -76,9 +82,7 @@ parse_scan_kernel(const o3v_parse_args a, scan::Scratch* __restrict__ scratch, c
   scan::scan_rollout(a.text, a.offsets[a.R], a.offsets[r], a.offsets[r + 1], a.task[r / a.G], cap, rows_of(a, r), sc,
                      mask_cache + (threadIdx.x >> 5) * scan::Finder::kSmemWords);
   __syncwarp();                              // lane 0 wrote the counts
-  append_range(w.count + 0, w.claims, (uint32_t)(r * a.C), min(sc->claim_cands, a.C));
-  append_range(w.count + 1, w.times, (uint32_t)(r * a.P), min(sc->time_cands, a.P));
-  append_range(w.count + 2, w.tboxes, (uint32_t)(r * a.Tb), min(sc->tbox_cands, a.Tb));
+  append_candidates(w, a, r, min(sc->claim_cands, a.C), min(sc->time_cands, a.P), min(sc->tbox_cands, a.Tb));
 }
 
 // B: CTA ranges [claims | think times | think boxes | answers]; within a range thread i converts list entry i
