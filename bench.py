@@ -251,13 +251,46 @@ def run_ours(args):
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
     even = (N % world == 0)
+    # Gather of the per-rank slices.  "p2p": the staging buffers live in symmetric (peer-mapped) memory and every
+    # rank PUSHES its slice into all peers' buffers with copy-engine transfers over NVLink, so no SM is taken from
+    # the persistent GEMM kernels of the step that is running; "nccl": all-gather kernels (fallback).
+    gather, peer_views, handles = "nccl" if world > 1 else "none", None, None
+    if world > 1 and args.e2e_gather == "p2p":
+        try:
+            import torch.distributed._symmetric_memory as symm
+            st2, peer_views, handles = [], [], []
+            for _slot in range(2):
+                bufs, views, hs = [], [], []
+                for t in full:
+                    b = symm.empty(tuple(t.shape), dtype=t.dtype, device=dev)
+                    h = symm.rendezvous(b, pg)
+                    bufs.append(b)
+                    hs.append(h)
+                    views.append([h.get_buffer(r_, tuple(t.shape), t.dtype) for r_ in range(world)])
+                st2.append(bufs)
+                peer_views.append(views)
+                handles.append(hs)
+            staging, gather = st2, "p2p"
+        except Exception as exc:                              # keep the bench alive on a box without P2P
+            if rank == 0:
+                print("e2e gather: symmetric memory unavailable (%s), using NCCL all-gather" % exc, file=sys.stderr)
+            peer_views = handles = None
 
     def prefetch(slot):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[slot])          # the step that last used this slot is done
+            if gather == "p2p":
+                # every peer must be done with this slot as well before anyone overwrites it
+                handles[slot][0].barrier(channel=4 + slot)
             for d, h in zip(staging[slot], host):
                 d[seq_lo:seq_hi].copy_(h, non_blocking=True)
-            if world > 1:
+            if gather == "p2p":
+                for ti, d in enumerate(staging[slot]):
+                    for r_ in range(world):
+                        if r_ != rank:
+                            peer_views[slot][ti][r_][seq_lo:seq_hi].copy_(d[seq_lo:seq_hi], non_blocking=True)
+                handles[slot][0].barrier(channel=6 + slot)  # all pushes into my buffers have landed
+            elif world > 1:
                 for d in staging[slot]:
                     if even:
                         dist.all_gather_into_tensor(d, d[seq_lo:seq_hi], group=pg)
@@ -335,7 +368,7 @@ def run_ours(args):
                       ms_per_launch=k1_ms, traffic=traffic, traffic_detail=traffic_detail),
         kernel_ms_per_step=shares,
         e2e=dict(value=T / (ms_e2e * 1e-3), unit="tokens/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
-                 ms_per_step=ms_e2e),
+                 ms_per_step=ms_e2e, gather=gather),
         gpu_launches=launches, clocks=clocks)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"], _ = cpu_reference(1, 0, cfg)
@@ -347,6 +380,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--e2e-gather", choices=("p2p", "nccl"), default="p2p",
+                    help="N > 1, end-to-end arm: how the per-rank input slices reach every rank")
     ap.add_argument("--overlap-dlogits", type=int, default=0,
                     help="1: run the dlogits pass of chunk c on a side stream beside K1 of chunk c+1")
     ap.add_argument("--steps", type=int, default=5)
