@@ -219,12 +219,51 @@ def soa_bytes(arrays) -> int:
     return int(sum(v.nbytes for v in arrays.values()))
 
 
+_pinned = {}
+_pinned_busy = {}
+
+
+def _pinned_buffer(name: str, nbytes: int) -> torch.Tensor:
+    """A reusable pinned staging buffer (grown geometrically): pinning per call costs more than the kernels.
+    Waits for the H2D copy that last read the buffer (see `_staged`)."""
+    ev = _pinned_busy.pop(name, None)
+    if ev is not None:
+        ev.synchronize()
+    buf = _pinned.get(name)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 16, 2 * (buf.numel() if buf is not None else 0)), dtype=torch.uint8,
+                          pin_memory=torch.cuda.is_available())
+        _pinned[name] = buf
+    return buf
+
+
+def _staged(name: str):
+    """Call after enqueueing an H2D copy out of staging buffer `name` on the current stream."""
+    ev = torch.cuda.Event()
+    ev.record()
+    _pinned_busy[name] = ev
+
+
 def to_device(arrays, device):
-    """Host SoA -> device tensors (one H2D copy per array from pinned memory)."""
+    """Host SoA -> device tensors: the arrays are packed back to back (16-byte aligned) into one pinned
+    staging buffer and cross PCIe in ONE copy; the result tensors are views of the device copy."""
+    items = [(k, np.ascontiguousarray(v)) for k, v in arrays.items()]
+    offs, total = [], 0
+    for _, v in items:
+        offs.append(total)
+        total += (v.nbytes + 15) // 16 * 16
+    total = max(total, 16)
+    stage = _pinned_buffer("soa", total)[:total]
+    sn = stage.numpy()
+    for (k, v), o in zip(items, offs):
+        sn[o:o + v.nbytes] = v.reshape(-1).view(np.uint8)
+    with torch.cuda.device(device):
+        dev = stage.to(device, non_blocking=True)
+        _staged("soa")
     out = {}
-    for k, v in arrays.items():
-        t = torch.from_numpy(np.ascontiguousarray(v).view(np.int32) if v.dtype == np.uint32 else np.ascontiguousarray(v))
-        out[k] = t.pin_memory().to(device, non_blocking=True)
+    for (k, v), o in zip(items, offs):
+        dt = torch.int32 if v.dtype == np.uint32 else torch.from_numpy(np.empty(0, v.dtype)).dtype
+        out[k] = dev[o:o + v.nbytes].view(dt).view(v.shape)
     return out
 
 
@@ -262,19 +301,6 @@ ROLLOUT_ROWS = (("flags", torch.int32, ()), ("ans_seg", torch.float64, (2,)), ("
                 ("claim_valid", torch.int32, ("C",)), ("claim_box", torch.float64, ("C", "Bc", 4)),
                 ("n_tboxes", torch.int32, ()), ("tbox_valid", torch.int32, ()), ("think_box", torch.float64, ("Tb", 4)))
 DEFAULT_CAPS = dict(P=16, C=16, Bc=4, Tb=8)
-
-
-_pinned = {}
-
-
-def _pinned_buffer(name: str, nbytes: int) -> torch.Tensor:
-    """A reusable pinned staging buffer (grown geometrically): pinning 50 MB per call costs more than the kernels."""
-    buf = _pinned.get(name)
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(nbytes, 1 << 16, 2 * (buf.numel() if buf is not None else 0)), dtype=torch.uint8,
-                          pin_memory=torch.cuda.is_available())
-        _pinned[name] = buf
-    return buf
 
 
 def encode_completions(contents: Sequence[str]):
@@ -357,8 +383,11 @@ def rewards_from_text(contents: Sequence[str], gts: Sequence[dict], G: int = 1, 
     gt_arrays, gt_dims = pack_gt(gts)
     text, offsets = encode_completions(contents)
     dev_gt = to_device(gt_arrays, device)
-    rows, caps = parse_completions_device(text.to(device, non_blocking=True), offsets.to(device, non_blocking=True),
-                                          dev_gt["task"], G, caps)
+    with torch.cuda.device(device):
+        d_text, d_off = text.to(device, non_blocking=True), offsets.to(device, non_blocking=True)
+        _staged("text")
+        _staged("offsets")
+    rows, caps = parse_completions_device(d_text, d_off, dev_gt["task"], G, caps)
     rows.update(dev_gt)
     return grounded_rewards_device(rows, dict(R=R, G=G, **caps, **gt_dims))
 
@@ -372,10 +401,14 @@ def grounded_rewards(completions, **kwargs) -> np.ndarray:
     contents = [c[0]["content"] for c in completions]
     task = kwargs["task"][0]                                   # the reference reads element 0 for the batch
     step = kwargs["step_percent"][0] if "step_percent" in kwargs else 0.0
-    # the trainer calls every reward callable with the same batch (grpo_trainer.py:646-656): compute the
-    # five columns once per batch.  The key holds the VALUES that reach the kernel, not object identities.
-    key = (tuple(contents), task, step, repr(kwargs.get("answer")), repr(kwargs.get("key_frames")),
-           repr(kwargs.get("key_items")), repr(kwargs.get("image_size")), repr(kwargs.get("image_size_refine")))
+    # the trainer calls every reward callable with the same batch (grpo_trainer.py:646-656): compute the five
+    # columns once per batch.  The key holds the completion texts and answers by VALUE (immutable strings) and the
+    # structured ground truth by identity and length: building a value snapshot of the nested key frames / items for
+    # every one of the five calls cost more than the whole GPU path at training batch sizes.
+    ident = lambda name: (id(kwargs.get(name)), len(kwargs[name]) if kwargs.get(name) is not None else -1)
+    ans = kwargs.get("answer")
+    key = (tuple(contents), task, step, tuple(ans) if ans is not None else None, ident("key_frames"), ident("key_items"),
+           ident("image_size"), ident("image_size_refine"))
     if _cache["key"] == key:
         return _cache["val"]
     get = lambda name, i: (kwargs[name][i] if name in kwargs and kwargs[name] is not None else None)
