@@ -396,6 +396,30 @@ def rewards_from_text(contents: Sequence[str], gts: Sequence[dict], G: int = 1, 
 _cache = {"key": None, "val": None}
 
 
+_GT_KEYS = ("answer", "key_frames", "key_items", "image_size", "image_size_refine")
+
+
+def _shared_gt_group(kwargs, R: int) -> int:
+    """Rollouts per prompt when the batch repeats each prompt's ground truth G times in a row, as the trainer
+    builds it (`reward_kwargs[key].extend([example[key]] * num_generations)`, grpo_trainer.py:651-653): the
+    repeats are the SAME objects, so identity (or equal answer strings) is enough to find G.  1 if the batch has
+    no such structure.  The ground truth is then parsed and packed once per prompt."""
+    cols = [kwargs[k] for k in _GT_KEYS if kwargs.get(k) is not None]
+    if R < 2 or not cols:
+        return 1
+    same = lambda i: all(c[i] is c[i - 1] or (isinstance(c[i], str) and c[i] == c[i - 1]) for c in cols)
+    G = 1
+    while G < R and same(G):
+        G += 1
+    if G == 1 or R % G:
+        return 1
+    for i in range(G, R):
+        if (i % G != 0) != same(i):                           # every block: G identical, then a change
+            if i % G != 0:
+                return 1
+    return G
+
+
 def grounded_rewards(completions, **kwargs) -> np.ndarray:
     """All five numeric rewards for a batch: [len(completions), 5] float64 (host)."""
     contents = [c[0]["content"] for c in completions]
@@ -412,14 +436,16 @@ def grounded_rewards(completions, **kwargs) -> np.ndarray:
     if _cache["key"] == key:
         return _cache["val"]
     get = lambda name, i: (kwargs[name][i] if name in kwargs and kwargs[name] is not None else None)
+    R = len(contents)
+    G = _shared_gt_group(kwargs, R)
     gts = []
-    for i in range(len(contents)):
+    for i in range(0, R, G):
         gt_seg, gt_vbox = parse_gt_answer(task, get("answer", i) or "")
         gts.append(dict(task=task, step_percent=step, gt_seg=gt_seg, gt_vbox=gt_vbox,
                         key_frames=get("key_frames", i) or [], key_items=get("key_items", i) or {},
                         image_size=get("image_size", i) or (1, 1),
                         image_size_refine=get("image_size_refine", i) or (1, 1)))
-    val = rewards_from_text(contents, gts, 1).cpu().numpy()
+    val = rewards_from_text(contents, gts, G).cpu().numpy()
     _cache["key"], _cache["val"] = key, val
     return val
 

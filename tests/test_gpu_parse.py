@@ -159,3 +159,30 @@ def test_text_to_rewards_matches_golden_reference(golden_dir):
                             image_size_refine=kw["image_size_refine"]))
         out = rewards.rewards_from_text(contents, gts, 1).cpu().numpy()
         np.testing.assert_allclose(out, exp[idx], rtol=0, atol=1e-6)
+
+
+def test_reward_callables_share_ground_truth_within_a_group():
+    """The trainer repeats each prompt's kwargs G times (same objects): the ground truth is packed once per prompt
+    and the result equals the per-rollout oracle."""
+    from open_o3_video_b200 import rewards
+    import warnings
+    G = 4
+    for task in ("temporal-spatial free-form QA", "visual QA", "temporal QA (MCQ)"):
+        cases = [c for c in op.text_cases(900, 31) if c[1]["task"] == task]
+        prompts = cases[:6]
+        texts, kws = [], []
+        for q, (_, kw) in enumerate(prompts):
+            for g in range(G):
+                texts.append(cases[6 + q * G + g][0])          # a different completion for every rollout
+                kws.append(kw)                                 # the SAME ground-truth objects G times
+        completions = [[{"role": "assistant", "content": t}] for t in texts]
+        kwargs = {k: [kw[k] for kw in kws] for k in kws[0]}
+        kwargs["step_percent"] = [kws[0]["step_percent"]] * len(kws)
+        assert rewards._shared_gt_group(kwargs, len(texts)) == G
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = np.array([orw.rewards_for_rollout(op.rollout_from_text(t, dict(kw, step_percent=kws[0]["step_percent"])))
+                             for t, kw in zip(texts, kws)])
+        got = np.array([rewards.reward_funcs_registry[n](prompts=None, completions=completions, **kwargs)
+                        for n in rewards.REWARD_NAMES]).T
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-6)
