@@ -15,7 +15,9 @@ from oracle import parse as oparse, rewards as orw  # noqa: E402
 
 warnings.simplefilter("ignore")
 for task in ("temporal-spatial free-form QA", "visual QA", "temporal QA"):
-    cases = [c for c in oparse.text_cases(600, 77) if c[1]["task"] == task][:64]
+    pool = [c for c in oparse.text_cases(900, 77) if c[1]["task"] == task]
+    # the trainer's layout: 8 prompts x G = 8 rollouts, each prompt's kwargs repeated G times (same objects)
+    cases = [(pool[8 + q * 8 + g][0], pool[q][1]) for q in range(8) for g in range(8)]
     kw0 = cases[0][1]
     completions = [[{"role": "assistant", "content": t}] for t, _ in cases]
     kwargs = {k: [kw[k] for _, kw in cases] for k in kw0}
