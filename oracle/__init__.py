@@ -24,6 +24,11 @@ Modules
               (grpo_trainer.py:590-596, 635-636, 658, 675-681, 691-706, 711, 737)
   rewards.py  numeric cores of the temporal / spatial rewards
               (reward_func.py:86-181, 184-236, 337-605)
+  parse.py    completion text -> parsed rollout (the reference's regex / json / float extraction,
+              reward_func.py:91-93, 119-126, 211-223, 308-335, 394-412, 437-449, 481-511) and the
+              seeded text generators / mutators that the K6 tests use
+  vstar.py    V-STAR scorer numerics (eval/test/eval_vstar.py:90-178)
+  sft.py      SFT causal-LM cross-entropy (sft_multi_task.py:402-409)
   synth.py    seeded synthetic input generators shared by tests and bench
   ref_import.py  stub loader for the real reference (this container only)
 """
