@@ -343,12 +343,18 @@ def parse_completions_device(text: torch.Tensor, offsets: torch.Tensor, task: to
     dev = text.device
     with torch.cuda.device(dev):
         while True:
-            ws = torch.empty(max(1, (lib.o3v_parse_workspace_bytes(R, caps["P"], caps["C"], caps["Tb"]) + 7) // 8),
-                             dtype=torch.int64, device=dev)
-            out = {"overflow": torch.empty(4, dtype=torch.int32, device=dev)}
-            for name, dt, shape in ROLLOUT_ROWS:
-                out[name] = torch.empty((R,) + tuple(caps[d] if isinstance(d, str) else d for d in shape),
-                                        dtype=dt, device=dev)
+            # one allocation for the workspace, the overflow report and every output row (views, 16-byte aligned)
+            shapes = [("overflow", torch.int32, (4,))] + [
+                (name, dt, (R,) + tuple(caps[d] if isinstance(d, str) else d for d in shape)) for name, dt, shape in ROLLOUT_ROWS]
+            ws_bytes = (lib.o3v_parse_workspace_bytes(R, caps["P"], caps["C"], caps["Tb"]) + 15) // 16 * 16
+            sizes = [(int(np.prod(sh)) * (8 if dt == torch.float64 else 4) + 15) // 16 * 16 for _, dt, sh in shapes]
+            slab = torch.empty(max(16, ws_bytes + sum(sizes)), dtype=torch.uint8, device=dev)
+            ws = slab[:max(ws_bytes, 8)].view(torch.int64)
+            out, o = {}, ws_bytes
+            for (name, dt, sh), nb in zip(shapes, sizes):
+                n = int(np.prod(sh)) * (8 if dt == torch.float64 else 4)
+                out[name] = slab[o:o + n].view(dt).view(sh)
+                o += nb
             a = _lib.ParseArgs()
             a.R, a.G = R, G
             for k in ("P", "C", "Bc", "Tb"):
@@ -373,12 +379,16 @@ def parse_completions_device(text: torch.Tensor, offsets: torch.Tensor, task: to
 
 
 def rewards_from_text(contents: Sequence[str], gts: Sequence[dict], G: int = 1, device="cuda",
-                      caps: Optional[dict] = None) -> torch.Tensor:
-    """Completion strings + per-prompt ground truth (see pack_gt) -> [R, 5] float64 on the device:
-    K6 (scan) then K4 (numerics), two launches."""
+                      caps: Optional[dict] = None, to_host: bool = False):
+    """Completion strings + per-prompt ground truth (see pack_gt) -> [R, 5] float64: K6 (scan, three launches)
+    then K4 (numerics).  Device tensor, or (to_host=True) a numpy array.
+
+    K4 is launched right behind K6 without waiting for the overflow report; the report and the rewards come back
+    in one synchronisation and the pair is repeated with larger rows only if something did not fit."""
     R = len(contents)
     if R == 0:
-        return torch.empty(0, 5, dtype=torch.float64, device=device)
+        out = torch.empty(0, 5, dtype=torch.float64, device=device)
+        return out.cpu().numpy() if to_host else out
     assert R == len(gts) * G
     gt_arrays, gt_dims = pack_gt(gts)
     text, offsets = encode_completions(contents)
@@ -387,9 +397,27 @@ def rewards_from_text(contents: Sequence[str], gts: Sequence[dict], G: int = 1, 
         d_text, d_off = text.to(device, non_blocking=True), offsets.to(device, non_blocking=True)
         _staged("text")
         _staged("offsets")
-    rows, caps = parse_completions_device(d_text, d_off, dev_gt["task"], G, caps)
-    rows.update(dev_gt)
-    return grounded_rewards_device(rows, dict(R=R, G=G, **caps, **gt_dims))
+        caps = dict(DEFAULT_CAPS if caps is None else caps)
+        while True:
+            rows, caps = parse_completions_device(d_text, d_off, dev_gt["task"], G, caps, sync=False)
+            over_dev = rows.pop("overflow")
+            rows.update(dev_gt)
+            out = grounded_rewards_device(rows, dict(R=R, G=G, **caps, **gt_dims))
+            host = _pinned_buffer("result", R * 40 + 16)
+            h_out = host[:R * 40].view(torch.float64).view(R, 5)
+            h_over = host[R * 40:R * 40 + 16].view(torch.int32)
+            h_out.copy_(out, non_blocking=True)
+            h_over.copy_(over_dev, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            over = h_over.tolist()
+            if not any(over):
+                break
+            if over[2] > 32 or over[3] > 32:
+                raise ValueError("more than 32 boxes per claim / think block")    # as pack_rollouts
+            for k, v in zip(("P", "C", "Bc", "Tb"), over):
+                if v:
+                    caps[k] = min(32, v) if k in ("Bc", "Tb") else v
+    return h_out.numpy().copy() if to_host else out
 
 
 # ----------------------------------------------------------------------------- reference-named callables
@@ -445,7 +473,7 @@ def grounded_rewards(completions, **kwargs) -> np.ndarray:
                         key_frames=get("key_frames", i) or [], key_items=get("key_items", i) or {},
                         image_size=get("image_size", i) or (1, 1),
                         image_size_refine=get("image_size_refine", i) or (1, 1)))
-    val = rewards_from_text(contents, gts, G).cpu().numpy()
+    val = rewards_from_text(contents, gts, G, to_host=True)
     _cache["key"], _cache["val"] = key, val
     return val
 
