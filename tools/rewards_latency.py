@@ -14,8 +14,13 @@ from open_o3_video_b200 import rewards  # noqa: E402
 from oracle import parse as oparse, rewards as orw  # noqa: E402
 
 warnings.simplefilter("ignore")
-for task in ("temporal-spatial free-form QA", "visual QA", "temporal QA"):
+FILLER = "The person then walks across the room and picks up the object on the table. "
+for task, pad in (("temporal-spatial free-form QA", 0), ("visual QA", 0), ("temporal QA", 0),
+                  ("temporal-spatial free-form QA", 8000), ("temporal-spatial free-form QA", 64000)):
     pool = [c for c in oparse.text_cases(900, 77) if c[1]["task"] == task]
+    if pad:     # realistic completion lengths (2048 tokens ~ 8 KB): prose between the grounded claims
+        pool = [(t.replace(" then ", " " + FILLER * (pad // len(FILLER) // max(1, t.count(" then "))) + " then "), kw)
+                for t, kw in pool]
     # the trainer's layout: 8 prompts x G = 8 rollouts, each prompt's kwargs repeated G times (same objects)
     cases = [(pool[8 + q * 8 + g][0], pool[q][1]) for q in range(8) for g in range(8)]
     kw0 = cases[0][1]
