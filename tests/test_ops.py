@@ -87,3 +87,25 @@ def test_ops_match_the_wrappers_and_pass_opcheck():
     b = torch.ops.o3v.policy_step(hid, w, ids, cu(d["ref"]), m2, cu(d["rewards_per_func"]), None, G, 0.04, 0.2, 0.2, True, 100)
     for x, k in zip(b, ("loss", "per_token_logps", "advantages", "mean_kl", "d_hidden", "d_weight")):
         assert torch.equal(x, a[k]), k
+
+
+@pytest.mark.gpu
+def test_ops_trace_under_torch_compile_without_graph_breaks():
+    """fullgraph=True: dynamo + AOT autograd must trace through the registered operators (fake kernels, autograd
+    formula) with no graph break; results equal eager."""
+    from open_o3_video_b200 import ops
+    T, H, V = 128, 128, 2000
+    hidden, weight, targets = synth.head_inputs(T, H, V, seed=11)
+    h0, w, t = hidden.cuda().bfloat16(), weight.cuda().bfloat16(), targets.cuda()
+
+    def head(h, w, t):
+        lp, lse, _ = torch.ops.o3v.lmhead_logprob(h * 1.0, w, t, 0, True)
+        return (lp * 2.0).sum()
+
+    ha = h0.clone().requires_grad_(True)
+    eager = head(ha, w, t)
+    eager.backward()
+    hb = h0.clone().requires_grad_(True)
+    compiled = torch.compile(head, fullgraph=True, backend="aot_eager")(hb, w, t)
+    compiled.backward()
+    assert torch.equal(eager, compiled) and torch.equal(ha.grad, hb.grad)
