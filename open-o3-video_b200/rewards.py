@@ -493,5 +493,8 @@ for _j, _n in enumerate(REWARD_NAMES):
     globals()[_n].__name__ = _n          # `reward_func.__name__` names the metric (grpo_trainer.py:718)
     globals()[_n].__doc__ = "B200 drop-in for reward_func.%s (numeric core on the GPU)." % _n
 
-# name -> callable, the numeric subset of grpo.py:58-66's reward_funcs_registry
-reward_funcs_registry = {n: globals()[n] for n in REWARD_NAMES}
+# The numeric subset of the reference's registry under ITS keys (grpo.py:58-66: "ans_tiou": ans_tiou_reward, ...), so
+# that `reward_funcs_registry.update(open_o3_video_b200.rewards.reward_funcs_registry)` swaps exactly those entries
+# ("ans_acc" and "format" stay the reference's string rewards).  The function names are accepted as keys too.
+reward_funcs_registry = {n[:-len("_reward")]: globals()[n] for n in REWARD_NAMES}
+reward_funcs_registry.update({n: globals()[n] for n in REWARD_NAMES})

@@ -102,3 +102,15 @@ def test_ops_refuse_cpu_tensors():
     with pytest.raises(RuntimeError, match="CUDA tensors only"):
         logprob.fused_logprob(torch.zeros(4, 64, dtype=torch.bfloat16), torch.zeros(8, 64, dtype=torch.bfloat16),
                               torch.zeros(4, dtype=torch.int64))
+
+
+def test_reward_registry_uses_the_reference_keys():
+    """grpo.py:58-66 registers the callables under short keys; `.update()` with ours must replace exactly the
+    numeric ones and keep `__name__` (the metric name, grpo_trainer.py:718)."""
+    from open_o3_video_b200 import rewards
+    ref_keys = {"ans_tiou", "ans_viou", "thk_temporal_point", "thk_temporal_segment", "thk_spatial"}
+    assert ref_keys <= set(rewards.reward_funcs_registry)
+    for k in ref_keys:
+        f = rewards.reward_funcs_registry[k]
+        assert f.__name__ == k + "_reward" and rewards.reward_funcs_registry[k + "_reward"] is f
+    assert "ans_acc" not in rewards.reward_funcs_registry and "format" not in rewards.reward_funcs_registry
