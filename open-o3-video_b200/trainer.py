@@ -8,8 +8,8 @@ Usage (the only change a user of the reference makes):
 
 `_get_per_token_logps(self, model, input_ids, **kwargs)` keeps the reference signature and
 return contract ([B, L-1] log-probs of input_ids[:, 1:], grpo_trainer.py:371-384) but calls the
-backbone for the final hidden states and runs the fused lm_head/log-softmax/gather kernel
-instead of materialising `model(...).logits`.  `compute_policy_loss` is the numeric block of
+model with `lm_head` tapped (so the final hidden states come back instead of `[B, L, V]` logits) and
+runs the fused lm_head/log-softmax/gather kernel on them.  `compute_policy_loss` is the numeric block of
 compute_loss (:635-636, 658, 675-681, 691-706) plus its metrics (:711-738) in one launch.
 Everything else in compute_loss (vision prep, generate, decode, reward callables) is the
 reference's own code and is untouched.
@@ -30,18 +30,41 @@ def _unwrap(model):
     return model
 
 
-def final_hidden_states(model, input_ids, **kwargs) -> torch.Tensor:
-    """Backbone forward without the lm_head: `model.model(...)`.last_hidden_state ([B, L, H]).
+class _HeadTap(torch.nn.Module):
+    """Stands in for `lm_head` during one forward: remembers the hidden states it is handed and returns a
+    zero-width logits tensor, so that nothing of size [B, L, V] is ever computed."""
 
-    transformers' Qwen2_5_VLForConditionalGeneration / Qwen3VLForConditionalGeneration compute
-    `logits = self.lm_head(self.model(...)[0])`; we stop one layer earlier."""
+    def __init__(self):
+        super().__init__()
+        self.hidden = None
+
+    def forward(self, hidden_states):
+        self.hidden = hidden_states
+        return hidden_states[..., :0]
+
+
+def final_hidden_states(model, input_ids, **kwargs) -> torch.Tensor:
+    """The hidden states `lm_head` would be applied to ([B, L, H]), without the head.
+
+    The reference calls `model(input_ids, **kwargs).logits` with the vision kwargs (`pixel_values_videos`,
+    `video_grid_thw`, grpo_trainer.py:375, :603-611).  Where the vision tower is merged differs between
+    transformers versions (inside `ForConditionalGeneration.forward` at the commit the reference pins, inside
+    `.model` in later releases), so the full forward is run unchanged with `lm_head` swapped for a tap that records
+    its input; this works for every causal-LM class that ends in `self.lm_head(hidden_states)`."""
     m = _unwrap(model)
-    backbone = getattr(m, "model", None)
-    if backbone is None:
-        raise RuntimeError("O3VB200TrainerMixin needs a model with a `.model` backbone and an `lm_head` "
-                           "(got %s); there is no logits-materialising fallback" % type(m).__name__)
-    out = backbone(input_ids=input_ids, **kwargs)
-    return out.last_hidden_state if hasattr(out, "last_hidden_state") else out[0]
+    head = getattr(m, "lm_head", None)
+    if head is None:
+        raise RuntimeError("O3VB200TrainerMixin needs a model with an `lm_head` (got %s); there is no "
+                           "logits-materialising fallback" % type(m).__name__)
+    tap = _HeadTap()
+    m.lm_head = tap
+    try:
+        model(input_ids, **kwargs)
+    finally:
+        m.lm_head = head
+    if tap.hidden is None:
+        raise RuntimeError("%s.forward never called lm_head" % type(m).__name__)
+    return tap.hidden
 
 
 def lm_head_weight(model) -> torch.Tensor:

@@ -119,23 +119,32 @@ def test_trainer_mixin_keeps_reference_contract():
     ids = torch.randint(0, V, (B, L), generator=torch.Generator().manual_seed(32))
     exp = ologps.per_token_logps(hidden.view(B, L, H), weight, ids)
 
-    class Backbone(torch.nn.Module):
-        def forward(self, input_ids=None, **kw):
-            return types.SimpleNamespace(last_hidden_state=hidden.view(B, L, H).cuda().bfloat16())
+    class Backbone(torch.nn.Module):          # text-only, as at the transformers commit the reference pins
+        def forward(self, inputs_embeds=None):
+            return types.SimpleNamespace(last_hidden_state=inputs_embeds)
 
-    class Model(torch.nn.Module):
+    class Model(torch.nn.Module):             # ...ForConditionalGeneration: merges vision features, then lm_head
         def __init__(self):
             super().__init__()
             self.model = Backbone()
             self.lm_head = torch.nn.Linear(H, V, bias=False).cuda().bfloat16()
             self.lm_head.weight.data.copy_(weight)
+            self.seen = None
+
+        def forward(self, input_ids, pixel_values_videos=None, video_grid_thw=None):
+            self.seen = (pixel_values_videos, video_grid_thw)
+            h = self.model(inputs_embeds=hidden.view(B, L, H).cuda().bfloat16()).last_hidden_state
+            logits = self.lm_head(h)
+            return types.SimpleNamespace(logits=logits.float())
 
     class T(O3VB200TrainerMixin):
         num_generations, beta, epsilon_low, epsilon_high, gspo = G, 0.04, 0.2, 0.2, True
         reward_funcs = []
 
     t, model = T(), torch.nn.parallel.DataParallel(Model()) if False else Model()
-    lp = t._get_per_token_logps(model, ids.cuda())
+    lp = t._get_per_token_logps(model, ids.cuda(), pixel_values_videos="pix", video_grid_thw="thw")
+    assert model.seen == ("pix", "thw")                               # the reference's kwargs reach model.forward
+    assert isinstance(model.lm_head, torch.nn.Linear)                 # the head is back in place
     assert lp.shape == (B, L - 1)
     assert ((lp.cpu() - exp).abs() / exp.abs().clamp(min=1e-2)).max() < 1e-3
     t.o3v_prompt_length = 25
