@@ -453,11 +453,12 @@ def grounded_rewards(completions, **kwargs) -> np.ndarray:
     contents = [c[0]["content"] for c in completions]
     task = kwargs["task"][0]                                   # the reference reads element 0 for the batch
     step = kwargs["step_percent"][0] if "step_percent" in kwargs else 0.0
-    # the trainer calls every reward callable with the same batch (grpo_trainer.py:646-656): compute the five
-    # columns once per batch.  The key holds the completion texts and answers by VALUE (immutable strings) and the
-    # structured ground truth by identity and length: building a value snapshot of the nested key frames / items for
-    # every one of the five calls cost more than the whole GPU path at training batch sizes.
-    ident = lambda name: (id(kwargs.get(name)), len(kwargs[name]) if kwargs.get(name) is not None else -1)
+    # the trainer calls every reward callable with the same batch (grpo_trainer.py:646-656) but REBUILDS the kwargs
+    # lists for each of them (:650-654) out of the same example objects: compute the five columns once per batch.
+    # The key holds the completion texts and answers by VALUE (immutable strings) and the structured ground truth
+    # by the identity of its per-rollout elements; a value snapshot of the nested key frames / items for every one
+    # of the five calls cost more than the whole GPU path at training batch sizes.
+    ident = lambda name: tuple(map(id, kwargs[name])) if kwargs.get(name) is not None else None
     ans = kwargs.get("answer")
     key = (tuple(contents), task, step, tuple(ans) if ans is not None else None, ident("key_frames"), ident("key_items"),
            ident("image_size"), ident("image_size_refine"))

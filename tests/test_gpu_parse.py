@@ -164,7 +164,7 @@ def test_text_to_rewards_matches_golden_reference(golden_dir):
 def test_reward_callables_share_ground_truth_within_a_group():
     """The trainer repeats each prompt's kwargs G times (same objects): the ground truth is packed once per prompt
     and the result equals the per-rollout oracle."""
-    from open_o3_video_b200 import rewards
+    from open_o3_video_b200 import _lib, rewards
     import warnings
     G = 4
     for task in ("temporal-spatial free-form QA", "visual QA", "temporal QA (MCQ)"):
@@ -183,6 +183,16 @@ def test_reward_callables_share_ground_truth_within_a_group():
             warnings.simplefilter("ignore")
             want = np.array([orw.rewards_for_rollout(op.rollout_from_text(t, dict(kw, step_percent=kws[0]["step_percent"])))
                              for t, kw in zip(texts, kws)])
-        got = np.array([rewards.reward_funcs_registry[n](prompts=None, completions=completions, **kwargs)
-                        for n in rewards.REWARD_NAMES]).T
-        np.testing.assert_allclose(got, want, rtol=0, atol=1e-6)
+        launches = []
+        cols = []
+        for n in rewards.REWARD_NAMES:                         # as grpo_trainer.py:646-656: kwargs lists rebuilt per callable
+            rebuilt = {k: list(v) for k, v in kwargs.items()}
+            t = _lib.Trace()
+            _lib.trace = t
+            try:
+                cols.append(rewards.reward_funcs_registry[n](prompts=None, completions=completions, **rebuilt))
+            finally:
+                _lib.trace = None
+            launches.append(t.launches)
+        np.testing.assert_allclose(np.array(cols).T, want, rtol=0, atol=1e-6)
+        assert launches[0] > 0 and not any(launches[1:])       # one GPU pass serves all five callables
