@@ -42,6 +42,8 @@ CONFIGS = {
     "c5": dict(head="qwen3-vl-8b", H=4096, V=151936, prompts=1, G=16, Tc=16384),
     "c1": dict(head="qwen2.5-vl-7b", H=3584, V=152064, prompts=1, G=4, Tc=512),
     "tiny": dict(head="tiny", H=256, V=8192, prompts=2, G=4, Tc=128),
+    # what ONE rank of the reference's own launch sees per step (per-device batch of 1 prompt x 8 generations)
+    "dev": dict(head="qwen2.5-vl-7b", H=3584, V=152064, prompts=1, G=8, Tc=2048),
 }
 METRIC = "completion tokens/s, fused logprob+GSPO fwd+bwd; % bf16 tensor-pipe peak"
 BETA, EPS = 0.04, 0.2
