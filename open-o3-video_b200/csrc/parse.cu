@@ -40,7 +40,7 @@ __device__ __forceinline__ scan::RolloutOut rows_of(const o3v_parse_args& a, int
 // list (one atomicAdd per rollout and type reserves the range), so that B's warps are full however
 // unevenly the candidates are spread over the rollouts.  Entry = rollout * capacity + slot.
 struct WorkLists {
-  unsigned int* count;    // [4]: claims, think times, think boxes, rollout ticket of A
+  unsigned int* count;    // [4]: claims, think times, think boxes, (unused)
   uint32_t* claims;       // [R * C]
   uint32_t* times;        // [R * P]
   uint32_t* tboxes;       // [R * Tb]
@@ -75,21 +75,14 @@ __device__ __forceinline__ void append_candidates(const WorkLists& w, const o3v_
 __global__ void __launch_bounds__(kScanWarps * 32, 4)
 parse_scan_kernel(const o3v_parse_args a, scan::Scratch* __restrict__ scratch, const WorkLists w) {
   extern __shared__ uint32_t mask_cache[];   // kScanWarps x Finder::kSmemWords (6 KB + a 32-entry list per warp)
+  const int64_t r = (int64_t)blockIdx.x * kScanWarps + (threadIdx.x >> 5);
+  if (r >= a.R) return;                      // whole warp leaves together
   const scan::Caps cap{a.P, a.C, a.Bc, a.Tb};
-  uint32_t* my_cache = mask_cache + (threadIdx.x >> 5) * scan::Finder::kSmemWords;
-  // persistent warps draw rollouts from a ticket (w.count[3]): long completions do not hold a CTA's other warps
-  for (;;) {
-    unsigned int ticket = 0;
-    if ((threadIdx.x & 31) == 0) ticket = atomicAdd(w.count + 3, 1u);
-    const int64_t r = __shfl_sync(0xffffffffu, ticket, 0);
-    if (r >= a.R) return;
-    scan::Scratch* sc = scratch + r;
-    scan::scan_rollout(a.text, a.offsets[a.R], a.offsets[r], a.offsets[r + 1], a.task[r / a.G], cap, rows_of(a, r), sc,
-                       my_cache);
-    __syncwarp();                              // lane 0 wrote the counts
-    append_candidates(w, a, r, min(sc->claim_cands, a.C), min(sc->time_cands, a.P), min(sc->tbox_cands, a.Tb));
-    __syncwarp();
-  }
+  scan::Scratch* sc = scratch + r;
+  scan::scan_rollout(a.text, a.offsets[a.R], a.offsets[r], a.offsets[r + 1], a.task[r / a.G], cap, rows_of(a, r), sc,
+                     mask_cache + (threadIdx.x >> 5) * scan::Finder::kSmemWords);
+  __syncwarp();                              // lane 0 wrote the counts
+  append_candidates(w, a, r, min(sc->claim_cands, a.C), min(sc->time_cands, a.P), min(sc->tbox_cands, a.Tb));
 }
 
 // B: CTA ranges [claims | think times | think boxes | answers]; within a range thread i converts list entry i
@@ -167,8 +160,7 @@ extern "C" int o3v_parse_completions(const o3v_parse_args* args, void* workspace
   if (rc) return rc;
   auto* scratch = reinterpret_cast<o3v::scan::Scratch*>(workspace);
   O3V_CUDA_TRY(cudaMemsetAsync(a.overflow, 0, 4 * sizeof(int32_t), st));
-  const int64_t want_a = (a.R + o3v::kScanWarps - 1) / o3v::kScanWarps, cap_a = (int64_t)o3v::num_sms() * 4;
-  const unsigned grid_a = (unsigned)(want_a < cap_a ? want_a : cap_a);
+  const unsigned grid_a = (unsigned)((a.R + o3v::kScanWarps - 1) / o3v::kScanWarps);
   const size_t smem_a = (size_t)o3v::kScanWarps * o3v::scan::Finder::kSmemWords * sizeof(uint32_t);
   O3V_CUDA_TRY(cudaFuncSetAttribute(o3v::parse_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
   const o3v::WorkLists lists = o3v::work_lists(workspace, a);
