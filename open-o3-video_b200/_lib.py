@@ -116,6 +116,7 @@ class Trace:
         self.events = events
         self.launches = 0
         self.records = {}
+        self.calls = []          # (entry point, its integer arguments in order): e.g. o3v_lmhead_fwd -> (T, V, H, ...)
 
     def durations_ms(self):
         """name -> list of elapsed ms (call after a device synchronize)."""
@@ -139,3 +140,4 @@ def call(name: str, n_kernels: int, fn, *args) -> None:
         check(fn(*args), name)
     if t is not None:
         t.launches += n_kernels
+        t.calls.append((name, tuple(a for a in args if isinstance(a, int) and not isinstance(a, bool))))

@@ -24,8 +24,17 @@ CHUNK_BUFFER_BYTES = 10 << 30
 
 def auto_chunk_tokens(v_local: int) -> int:
     return max(128, int(CHUNK_BUFFER_BYTES // (2 * v_local)))
-# autograd path: keep bf16 logits for backward when they fit in this many bytes, else recompute
+# autograd path (`fused_logprob` + a separate backward): the forward may keep its bf16 logits for the backward
+# (executed flops = algorithmic 6*T*H*V) or drop them and recompute per chunk (8*T*H*V, nothing of size [T, V]
+# alive between forward and backward).  They are kept only when they fit BOTH this cap and a quarter of the
+# memory that is free at forward time, so a 7B backbone's activations are never squeezed by the head.
 SAVE_LOGITS_BYTES = 24 << 30
+SAVE_LOGITS_FREE_FRACTION = 0.25
+
+
+def save_logits_budget(device) -> int:
+    free, _ = torch.cuda.mem_get_info(device)
+    return int(min(SAVE_LOGITS_BYTES, free * SAVE_LOGITS_FREE_FRACTION))
 
 
 _side_streams = {}
@@ -156,7 +165,7 @@ class _FusedLogprobFn(torch.autograd.Function):
         T, H = hidden.shape
         V = weight.shape[0]
         need_grad = hidden.requires_grad or weight.requires_grad
-        keep = need_grad and (T * V * 2 <= SAVE_LOGITS_BYTES)
+        keep = need_grad and (T * V * 2 <= save_logits_budget(hidden.device))
         logits = torch.empty(T, V, dtype=torch.bfloat16, device=hidden.device) if keep else None
         logp, lse = _stats_to_logp(hidden, weight, targets, v_offset, logits, group)
         ctx.save_for_backward(hidden, weight, targets, lse)
@@ -338,3 +347,50 @@ def fused_logprob_gspo(hidden: torch.Tensor, weight: torch.Tensor, completion_id
     return dict(loss=state["loss"].reshape(()), per_token_logps=logp, advantages=state["adv"],
                 mean_kl=state["mean_kl"].reshape(()), completion_length=state["clen"], reward_std=state["rstd"],
                 d_hidden=None if d_hidden is None else d_hidden.view(N, Tc, H), d_weight=d_weight)
+
+
+class _FusedPolicyStepFn(torch.autograd.Function):
+    """`fused_logprob_gspo` attached to autograd at (hidden, weight): the forward runs the whole chunked step and
+    already holds dHidden / dW; the backward only scales them by the incoming gradient of the loss."""
+
+    @staticmethod
+    def forward(ctx, hidden, weight, completion_ids, ref, mask, rpf, G, beta, eps_lo, eps_hi, gspo, old, opts):
+        need = hidden.requires_grad or weight.requires_grad
+        out = fused_logprob_gspo(hidden.detach(), weight.detach(), completion_ids, ref, mask, rpf, G, beta, eps_lo,
+                                 eps_hi, gspo, old, need_grad=need, **opts)
+        ctx.need = need
+        if need:
+            ctx.save_for_backward(out["d_hidden"], out["d_weight"])
+        ctx.w_dtype = weight.dtype
+        extras = (out["per_token_logps"], out["advantages"], out["mean_kl"], out["completion_length"],
+                  out["reward_std"])
+        ctx.mark_non_differentiable(*extras)
+        return (out["loss"].clone(),) + extras
+
+    @staticmethod
+    def backward(ctx, g_loss, *_):
+        if not ctx.need:
+            return (None,) * 13
+        d_hidden, d_weight = ctx.saved_tensors
+        g = g_loss.to(torch.float32)
+        dh = d_hidden if _is_one(g) else (d_hidden.float() * g).to(d_hidden.dtype)
+        dw = (d_weight if _is_one(g) else d_weight * g).to(ctx.w_dtype)
+        return (dh, dw) + (None,) * 11
+
+
+def _is_one(g) -> bool:
+    # gradient accumulation scales the loss by 1/steps: only skip the multiply when it is known to be a no-op
+    # WITHOUT reading the device (no sync)
+    return False
+
+
+def fused_policy_step(hidden, weight, completion_ids, ref_per_token_logps, completion_mask, rewards_per_func,
+                      num_generations, beta, epsilon_low=0.2, epsilon_high=0.2, gspo=True,
+                      old_per_token_logps=None, **opts):
+    """Autograd-enabled `fused_logprob_gspo`: returns the same dict (without d_hidden / d_weight); `loss.backward()`
+    delivers dHidden to whatever produced `hidden` (the backbone) and dW to `weight` (lm_head.weight)."""
+    res = _FusedPolicyStepFn.apply(hidden, weight, completion_ids, ref_per_token_logps, completion_mask,
+                                   rewards_per_func, int(num_generations), float(beta), float(epsilon_low),
+                                   float(epsilon_high), bool(gspo), old_per_token_logps, opts)
+    keys = ("loss", "per_token_logps", "advantages", "mean_kl", "completion_length", "reward_std")
+    return dict(zip(keys, res))

@@ -102,3 +102,82 @@ def load_vstar_functions():
     ns = {"np": _np, "ast": _ast}
     exec(compile(_ast.Module(body=body, type_ignores=[]), path, "exec"), ns)
     return types.SimpleNamespace(**{k: ns[k] for k in want})
+
+
+# ---------------------------------------------------------------------------------------------------
+# The INLINE numeric block of compute_loss, executed from the reference file itself
+# ---------------------------------------------------------------------------------------------------
+_LOSS_BLOCK_RANGES = {
+    # name: (first line, last line, identifiers that must appear: guards against a shifted file)
+    "mask": (590, 596, ("is_eos", "eos_idx", "completion_mask")),
+    "kl": (635, 636, ("x_clamped", "per_token_kl")),
+    "sum": (658, 658, ("rewards_per_func.sum",)),
+    "adv": (675, 681, ("mean_grouped_rewards", "std_grouped_rewards", "advantages")),
+    "objective": (691, 706, ("log_ratio", "coef_1", "coef_2", "per_token_loss", "loss")),
+    "mean_kl": (737, 737, ("mean_kl",)),
+}
+
+
+def _reference_lines(first, last, must):
+    import textwrap
+    path = os.path.join(_OPEN_R1, "trainer", "grpo_trainer.py")
+    with open(path) as f:
+        lines = f.readlines()
+    text = "".join(lines[first - 1:last])
+    for ident in must:
+        if ident not in text:
+            raise RuntimeError("grpo_trainer.py:%d-%d does not contain %r: the reference file moved" % (first, last, ident))
+    return textwrap.dedent(text)
+
+
+class _OldPolicyTensor:
+    pass
+
+
+def load_loss_block():
+    """The reference's own source lines grpo_trainer.py:590-596, 635-636, 658, 675-681, 691-706, 737, compiled
+    from the file where it lies and executed in a namespace that supplies what the lines read (`self`, `torch`,
+    the tensors).  Nothing is copied into this repository.  Returns (mask_block, loss_block):
+
+      mask_block(completion_ids, eos_token_id) -> dict(eos_idx, completion_mask)
+      loss_block(per_token_logps, ref_per_token_logps, completion_mask, rewards_per_func, num_generations, beta,
+                 epsilon_low, epsilon_high, gspo, old_per_token_logps=None) -> dict(...)
+
+    The one substitution: the reference's old policy IS the current one (`per_token_logps.detach()`, :691).  To
+    drive the off-policy (clipping) side of the same lines, `old_per_token_logps` is delivered through that very
+    `.detach()` call: `per_token_logps` is handed in as a tensor subclass whose `detach()` returns it."""
+    import torch
+    if not reference_available():
+        raise RuntimeError("reference not present at %s" % REFERENCE_ROOT)
+    code = {k: compile(_reference_lines(a, b, must), "grpo_trainer.py:%d-%d" % (a, b), "exec")
+            for k, (a, b, must) in _LOSS_BLOCK_RANGES.items()}
+
+    class _Logps(torch.Tensor):
+        def detach(self):
+            old = getattr(self, "_o3v_old", None)
+            return old if old is not None else super().detach()
+
+    def mask_block(completion_ids, eos_token_id):
+        self = types.SimpleNamespace(processing_class=types.SimpleNamespace(eos_token_id=eos_token_id),
+                                     accelerator=types.SimpleNamespace(device=completion_ids.device))
+        ns = dict(torch=torch, self=self, completion_ids=completion_ids)
+        exec(code["mask"], ns)
+        return dict(eos_idx=ns["eos_idx"], completion_mask=ns["completion_mask"])
+
+    def loss_block(per_token_logps, ref_per_token_logps, completion_mask, rewards_per_func, num_generations, beta,
+                   epsilon_low=0.2, epsilon_high=0.2, gspo=True, old_per_token_logps=None):
+        self = types.SimpleNamespace(num_generations=num_generations, beta=beta, epsilon_low=epsilon_low,
+                                     epsilon_high=epsilon_high, gspo=gspo)
+        lp = per_token_logps
+        if old_per_token_logps is not None:
+            lp = per_token_logps.as_subclass(_Logps)
+            lp._o3v_old = old_per_token_logps
+        ns = dict(torch=torch, self=self, per_token_logps=lp, ref_per_token_logps=ref_per_token_logps,
+                  completion_mask=completion_mask, rewards_per_func=rewards_per_func)
+        for k in ("kl", "sum", "adv", "objective", "mean_kl"):
+            exec(code[k], ns)
+        plain = lambda t: t.as_subclass(torch.Tensor) if isinstance(t, torch.Tensor) else t
+        return {k: plain(ns[k]) for k in ("per_token_kl", "rewards", "advantages", "std_grouped_rewards", "loss",
+                                          "mean_kl")}
+
+    return mask_block, loss_block

@@ -8,6 +8,10 @@ Outputs (committed):
     rewards_kat.json     the known-answer cases of SURVEY.md Appendix B, re-run here
     parse_cases.json     reference reward callables on seeded completion TEXT (well-formed and malformed):
                          pins the text extraction (regex / json / float) end to end
+    gspo_small.npz       the reference's inline loss block (grpo_trainer.py:590-596, 635-636, 658, 675-681,
+                         691-706, 737) executed from the reference file's own source lines
+    compute_loss_small.json  the reference's whole compute_loss on the fake model / processor of
+                         oracle/host_trainer.py (loss, metrics, gradient norms)
 Inputs are regenerated from the seed by the tests (oracle/synth.py); only outputs
 (and, for rewards, the small structured inputs) are stored.
 """
@@ -131,7 +135,73 @@ def gen_parse():
           "claims", sum(len(c) for c in claims))
 
 
+GSPO_CASES = {
+    # name: (N, Tc, G, off_policy, gspo, empty_row)
+    "on_gspo": (8, 48, 4, False, True, None),
+    "on_grpo": (8, 48, 4, False, False, None),
+    "off_gspo": (8, 48, 4, True, True, None),
+    "off_grpo": (8, 48, 4, True, False, None),
+    "off_gspo_empty_seq": (8, 48, 4, True, True, 5),     # a sequence with an all-zero mask (mean_kl becomes NaN, :737)
+    "off_gspo_g8": (16, 33, 8, True, True, None),
+}
+
+
+def gspo_case_inputs(name):
+    """Seeded inputs of one GSPO golden case (shared with tests/test_oracle_golden.py)."""
+    N, Tc, G, off, gs, empty = GSPO_CASES[name]
+    d = synth.gspo_inputs(N, Tc, G, seed=synth.SEED + 7 * len(name), off_policy=off)
+    return d, (N, Tc, G, off, gs, empty)
+
+
+def gen_gspo():
+    """The reference's INLINE loss block (grpo_trainer.py:590-596, 635-636, 658, 675-681, 691-706, 737), executed
+    from the reference file's own source lines (oracle/ref_import.load_loss_block)."""
+    mask_block, loss_block = ref_import.load_loss_block()
+    out = {}
+    for name in GSPO_CASES:
+        d, (N, Tc, G, off, gs, empty) = gspo_case_inputs(name)
+        m = mask_block(d["ids"], d["eos_id"])
+        mask = m["completion_mask"].clone()
+        if empty is not None:
+            mask[empty] = 0
+        lp = d["logp"].clone().requires_grad_(True)
+        r = loss_block(lp, d["ref"], mask, d["rewards_per_func"], G, 0.04, 0.2, 0.2, gs, d["old"] if off else None)
+        r["loss"].backward()
+        out[name + "/eos_idx"] = m["eos_idx"].numpy()
+        out[name + "/completion_mask"] = m["completion_mask"].numpy()
+        for k in ("per_token_kl", "rewards", "advantages", "std_grouped_rewards", "loss", "mean_kl"):
+            out[name + "/" + k] = r[k].detach().numpy()
+        out[name + "/grad"] = lp.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "gspo_small.npz"), **out)
+    print("gspo_small.npz", {k: float(out[k + "/loss"]) for k in GSPO_CASES})
+
+
+def gen_compute_loss():
+    """The reference's whole compute_loss (grpo_trainer.py:402-738) on the fakes of oracle/host_trainer.py."""
+    from oracle import host_trainer as ht
+    cls = ref_import.load_trainer_class()
+    ht.install_reference_fakes(sys.modules[cls.__module__])
+    res = {}
+    for key, gs in (("gspo", True), ("grpo", False)):
+        model, ref = ht.FakeVLModel(seed=11), ht.FakeVLModel(seed=12).eval()
+        t = ht.configure(cls.__new__(cls), model, ref, gspo=gs)
+        loss = t.compute_loss(model, [ht.make_example()])
+        loss.backward()
+        res[key] = dict(loss=repr(loss.item()), metrics={k: repr(float(v[0])) for k, v in t._metrics.items()},
+                        g_head=repr(model.lm_head.weight.grad.norm().item()),
+                        g_embed=repr(model.embed.weight.grad.norm().item()))
+    with open(os.path.join(HERE, "compute_loss_small.json"), "w") as f:
+        json.dump(res, f, indent=1)
+    print("compute_loss_small.json", res["gspo"]["loss"], res["grpo"]["loss"])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1:                     # e.g. `gen_golden.py gspo compute_loss`
+        for name in sys.argv[1:]:
+            globals()["gen_" + name]()
+        sys.exit(0)
+    gen_gspo()
+    gen_compute_loss()
     gen_parse()
     gen_logps()
     gen_rewards()
