@@ -187,13 +187,16 @@ int o3v_gspo_fwd_bwd(const float* logp, const float* old_logp, const float* ref_
 #define O3V_RF_ANS_BOX 8     /* answer holds a <box> that parsed to 4 numbers (:212, :361) */
 #define O3V_GF_VBOX 1        /* GT answer holds a <box>              (reward_func.py:204) */
 
+/* first double of the slot of a box >= 32 that is NOT a list of 4 numbers (a quiet-NaN payload no parsed number has) */
+#define O3V_INVALID_BOX_BITS 0x7FF8B0B0DEADBEEFull
+
 typedef struct o3v_rewards_soa {
   int64_t R;  /* rollouts */
   int64_t G;  /* rollouts per prompt; GT arrays have Q = R / G rows */
   int32_t P;  /* max think timestamps per rollout */
   int32_t C;  /* max claims per rollout */
-  int32_t Bc; /* max boxes per claim (<= 32) */
-  int32_t Tb; /* max think boxes per rollout, visual-QA branch (<= 32) */
+  int32_t Bc; /* max boxes per claim */
+  int32_t Tb; /* max think boxes per rollout, visual-QA branch */
   int32_t K;  /* max key frames per prompt */
   int32_t O;  /* max objects per key frame */
   int32_t Gb; /* max GT boxes per object */
@@ -207,10 +210,11 @@ typedef struct o3v_rewards_soa {
   const int32_t* n_claims;    /* [R] (= len(parsed_claims), the divisor at :603) */
   const double* claim_t;      /* [R, C] */
   const int32_t* claim_nbox;  /* [R, C] */
-  const uint32_t* claim_valid;/* [R, C] bit b: box b is a list of 4 numbers (:361) */
+  const uint32_t* claim_valid;/* [R, C] bit b: box b < 32 is a list of 4 numbers (:361); boxes b >= 32 (degenerate
+                                 repetition loops) are valid unless their slot starts with O3V_INVALID_BOX_BITS */
   const double* claim_box;    /* [R, C, Bc, 4] pixels */
   const int32_t* n_tboxes;    /* [R] */
-  const uint32_t* tbox_valid; /* [R] */
+  const uint32_t* tbox_valid; /* [R] same convention */
   const double* think_box;    /* [R, Tb, 4] pixels */
   /* per prompt */
   const int32_t* task;        /* [Q] O3V_TASK_* */

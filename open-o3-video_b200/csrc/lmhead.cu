@@ -290,11 +290,13 @@ extern "C" int o3v_set_tunable(const char* name, int value) {
 }
 
 extern "C" size_t o3v_lmhead_fwd_workspace_bytes(int64_t T, int64_t V, int64_t H) {
-  (void)H;
   if (T <= 0 || V <= 0) return 0;
-  // worst case over the tunables: one part per n-tile
-  const int64_t groups = ceil_div(V, 256);
-  return (size_t)(groups * 3 * T) * sizeof(float);
+  // one partial triple per token and per vocab group of the plan o3v_lmhead_fwd will make for this shape under the
+  // current tunables (4-16 groups; the worst case, one group per 256-column tile, was 0.9 GB at T = 131072)
+  GemmParams p = {};
+  p.M = T; p.N = V; p.K = H;
+  plan_tiles(p, g_cta_fwd, fwd_groups(T, V, g_cta_fwd));
+  return (size_t)((int64_t)p.num_n_groups * 3 * T) * sizeof(float);
 }
 
 extern "C" int o3v_lmhead_fwd(const void* hidden, const void* weight, const int64_t* targets,

@@ -142,7 +142,7 @@ extern "C" int o3v_parse_completions(const o3v_parse_args* args, void* workspace
   if (!args) return O3V_ERR_INVALID_ARG;
   const o3v_parse_args& a = *args;
   if (a.R < 0 || a.G <= 0 || (a.R % a.G) != 0) return O3V_ERR_INVALID_ARG;
-  if (a.P < 1 || a.C < 1 || a.Bc < 1 || a.Bc > 32 || a.Tb < 1 || a.Tb > 32) return O3V_ERR_INVALID_ARG;
+  if (a.P < 1 || a.C < 1 || a.Bc < 1 || a.Tb < 1) return O3V_ERR_INVALID_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   if (a.R == 0) {
     if (a.overflow) O3V_CUDA_TRY(cudaMemsetAsync(a.overflow, 0, 4 * sizeof(int32_t), st));

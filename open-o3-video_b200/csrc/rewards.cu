@@ -30,6 +30,11 @@ __device__ __forceinline__ double box_iou(const double a[4], const double b[4]) 
   return uni > 0.0 ? __ddiv_rn(inter, uni) : 0.0;
 }
 
+// boxes beyond the 32 bits of the validity mask carry their validity in the slot (include/o3v.h)
+__device__ __forceinline__ bool box_slot_valid(const double* p) {
+  return (unsigned long long)__double_as_longlong(*p) != O3V_INVALID_BOX_BITS;
+}
+
 __device__ __forceinline__ void load4(const double* p, double o[4]) {
   const double2 lo = *reinterpret_cast<const double2*>(p);
   const double2 hi = *reinterpret_cast<const double2*>(p + 2);
@@ -188,8 +193,8 @@ rewards_kernel(const o3v_rewards_soa s, double* __restrict__ out) {
         const unsigned valid = s.tbox_valid[r];
         double best = 0.0;
         for (int b = lane; b < nb; b += kLanes) {
-          if ((valid >> b) & 1u) {
-            double pb[4];
+          double pb[4];
+          if (b < 32 ? ((valid >> b) & 1u) != 0u : box_slot_valid(s.think_box + (r * s.Tb + b) * 4)) {
             load4(s.think_box + (r * s.Tb + b) * 4, pb);
             best = fmax(best, box_iou(gvb, pb));
           }
@@ -244,7 +249,7 @@ rewards_kernel(const o3v_rewards_soa s, double* __restrict__ out) {
                   bool first = true;
                   for (int b = 0; b < nb; ++b) {                            // :592-593 max(list)
                     double v = 0.0;
-                    if ((valid >> b) & 1u) {
+                    if (b < 32 ? ((valid >> b) & 1u) != 0u : box_slot_valid(cb + b * 4)) {
                       if (b == 0) v = box_iou(g4, cb0);
                       else if (b == 1) v = box_iou(g4, cb1);
                       else { double pb[4]; load4(cb + b * 4, pb); v = box_iou(g4, pb); }
@@ -279,7 +284,7 @@ extern "C" int o3v_grounded_rewards(const o3v_rewards_soa* soa, double* out, voi
   if (!soa || !out) return O3V_ERR_INVALID_ARG;
   const o3v_rewards_soa& s = *soa;
   if (s.R < 0 || s.G <= 0 || (s.R % s.G) != 0) return O3V_ERR_INVALID_ARG;
-  if (s.P < 0 || s.C < 0 || s.Bc < 0 || s.Bc > 32 || s.Tb < 0 || s.Tb > 32 || s.K < 0 || s.O < 0 || s.Gb < 0)
+  if (s.P < 0 || s.C < 0 || s.Bc < 0 || s.Tb < 0 || s.K < 0 || s.O < 0 || s.Gb < 0)
     return O3V_ERR_INVALID_ARG;
   if (!s.flags || !s.ans_seg || !s.ans_box || !s.n_times || !s.think_times || !s.n_claims || !s.claim_t ||
       !s.claim_nbox || !s.claim_valid || !s.claim_box || !s.n_tboxes || !s.tbox_valid || !s.think_box ||

@@ -505,6 +505,21 @@ O3V_HD uint64_t big_rounded_integer(const BigDec& b) {
   return n + (up ? 1 : 0);
 }
 
+// In-slot markers of box validity (include/o3v.h: O3V_INVALID_BOX_BITS).  Quiet NaNs with a payload that neither
+// float() / json.loads (canonical 0x7FF8000000000000) nor a packed candidate range (text offsets < 2^33) can produce.
+constexpr uint64_t kInvalidBoxBits = 0x7FF8B0B0DEADBEEFull;   // a JSON list that is not 4 numbers
+constexpr uint64_t kDroppedBoxBits = 0x7FF8B0B0DEADD00Dull;   // not JSON at all (internal to K6: never leaves phase C)
+
+O3V_HD uint64_t double_to_bits(double v) {
+#if defined(__CUDA_ARCH__)
+  return (uint64_t)__double_as_longlong(v);
+#else
+  union { uint64_t u; double d; } c;
+  c.d = v;
+  return c.u;
+#endif
+}
+
 O3V_HD double bits_to_double(uint64_t bits) {
 #if defined(__CUDA_ARCH__)
   return __longlong_as_double((long long)bits);
@@ -940,7 +955,7 @@ struct RolloutOut {            // pointers to THIS rollout's rows (o3v_rewards_s
 struct Scratch {
   int64_t think_end, answer_end;
   int32_t time_cands, claim_cands, tbox_cands;
-  uint32_t tbox_kept, tbox_numeric;   // bit j: candidate j is JSON / is a 4-number box
+  uint32_t unused0_, unused1_;        // (were 32-bit kept / numeric masks of the think boxes: now slot markers)
   int32_t pad_;
 };
 
@@ -1169,8 +1184,8 @@ O3V_HD void scan_rollout(const uint8_t* t, int64_t total, int64_t beg, int64_t e
     sc->time_cands = n_time;
     sc->claim_cands = n_claim;
     sc->tbox_cands = n_tbox;
-    sc->tbox_kept = 0;
-    sc->tbox_numeric = 0;
+    sc->unused0_ = 0;
+    sc->unused1_ = 0;
   }
 }
 
@@ -1242,12 +1257,16 @@ O3V_HD void convert_item(const uint8_t* t, int item, const Caps& cap, const Roll
       if (found == 1) {
         int n; bool numeric; double v[4];
         if (json_box(t, i, j + 1, &n, &numeric, v, parsers) != kJsonList) { keep = false; continue; }   // JSONDecodeError
-        if (n == 4 && numeric && nb < 32) {
-          valid |= 1u << nb;
+        // validity of box b: bit b of `valid` for b < 32; beyond that (degenerate repetition loops) an invalid
+        // box is marked IN its slot with kInvalidBoxBits, a NaN payload no parsed number can have
+        if (n == 4 && numeric) {
+          if (nb < 32) valid |= 1u << nb;
           if (nb < cap.Bc) {
             double* dst = cbox + 4 * nb;
             dst[0] = v[0]; dst[1] = v[1]; dst[2] = v[2]; dst[3] = v[3];
           }
+        } else if (nb >= 32 && nb < cap.Bc) {
+          cbox[4 * nb] = bits_to_double(kInvalidBoxBits);
         }
         ++nb;
         i = j + 1;
@@ -1269,11 +1288,14 @@ O3V_HD void convert_item(const uint8_t* t, int item, const Caps& cap, const Roll
     double* dst = o.think_box + 4 * item;
     unpack_range(dst[0], &bs, &be);
     int n; bool numeric; double v[4];
-    if (json_box(t, bs, be - bs >= kMaxRange ? bs : be, &n, &numeric, v, lanes) != kJsonList) return;   // not JSON: skipped
-    const bool box = n == 4 && numeric;
-    if (box) { dst[0] = v[0]; dst[1] = v[1]; dst[2] = v[2]; dst[3] = v[3]; }
-    or_bits(&sc->tbox_kept, 1u << item);
-    if (box) or_bits(&sc->tbox_numeric, 1u << item);
+    if (json_box(t, bs, be - bs >= kMaxRange ? bs : be, &n, &numeric, v, lanes) != kJsonList) {         // not JSON: skipped
+      dst[0] = bits_to_double(kDroppedBoxBits);
+      return;
+    }
+    // kept (JSON list): a 4-number box keeps its values, anything else is marked invalid in its slot; a payload
+    // that is not JSON was marked dropped below.  (Slot markers instead of per-rollout bit masks: no 32-box limit.)
+    if (n == 4 && numeric) { dst[0] = v[0]; dst[1] = v[1]; dst[2] = v[2]; dst[3] = v[3]; }
+    else dst[0] = bits_to_double(kInvalidBoxBits);
     return;
   }
   item -= cap.Tb;
@@ -1337,11 +1359,14 @@ O3V_HD void finish_rollout(const Caps& cap, const RolloutOut& o, const Scratch* 
   k = 0;
   uint32_t valid = 0;
   for (int j = 0; j < n; ++j) {
-    if (!((sc->tbox_kept >> j) & 1u)) continue;
-    if ((sc->tbox_numeric >> j) & 1u) {
-      valid |= 1u << k;
+    const uint64_t b0 = double_to_bits(o.think_box[4 * j]);
+    if (b0 == kDroppedBoxBits) continue;
+    if (b0 != kInvalidBoxBits) {
+      if (k < 32) valid |= 1u << k;
       if (k != j)
         for (int i = 0; i < 4; ++i) o.think_box[4 * k + i] = o.think_box[4 * j + i];
+    } else if (k >= 32) {
+      o.think_box[4 * k] = bits_to_double(kInvalidBoxBits);
     }
     ++k;
   }

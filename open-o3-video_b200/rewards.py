@@ -28,6 +28,8 @@ TASK_IDS = {"visual QA": 0, "temporal QA": 1, "temporal QA (MCQ)": 2,
 REWARD_NAMES = ("ans_tiou_reward", "ans_viou_reward", "thk_temporal_segment_reward",
                 "thk_temporal_point_reward", "thk_spatial_reward")
 RF_HAS_THINK, RF_HAS_ANSWER, RF_ANS_SEG, RF_ANS_BOX, GF_VBOX = 1, 2, 4, 8, 1
+# O3V_INVALID_BOX_BITS (include/o3v.h): marks, in its own slot, a box with index >= 32 that is not a list of 4 numbers
+INVALID_BOX = np.array([0x7FF8B0B0DEADBEEF], np.uint64).view(np.float64)[0]
 
 
 # ----------------------------------------------------------------------------- parsing
@@ -175,8 +177,6 @@ def pack_rollouts(rollouts: Sequence[dict], G: int = 1):
     C = max([len(r["claims"]) for r in rollouts] + [1])
     Bc = max([len(b) for r in rollouts for _, b in r["claims"]] + [1])
     Tb = max([len(r["think_boxes"]) for r in rollouts] + [1])
-    if Bc > 32 or Tb > 32:
-        raise ValueError("more than 32 boxes per claim / think block")
     gts = [rollouts[q * G] for q in range(Q)]
     gt_arrays, gt_dims = pack_gt(gts)
     a = dict(
@@ -203,13 +203,19 @@ def pack_rollouts(rollouts: Sequence[dict], G: int = 1):
             a["claim_nbox"][i, c] = len(boxes)
             for b, box in enumerate(boxes):
                 if _box_ok(box):
-                    a["claim_valid"][i, c] |= np.uint32(1 << b)
+                    if b < 32:
+                        a["claim_valid"][i, c] |= np.uint32(1 << b)
                     a["claim_box"][i, c, b] = box
+                elif b >= 32:                                  # beyond the mask: validity lives in the slot
+                    a["claim_box"][i, c, b, 0] = INVALID_BOX
         a["n_tboxes"][i] = len(r["think_boxes"])
         for b, box in enumerate(r["think_boxes"]):
             if _box_ok(box):
-                a["tbox_valid"][i] |= np.uint32(1 << b)
+                if b < 32:
+                    a["tbox_valid"][i] |= np.uint32(1 << b)
                 a["think_box"][i, b] = box
+            elif b >= 32:
+                a["think_box"][i, b, 0] = INVALID_BOX
     a.update(gt_arrays)
     dims = dict(R=R, G=G, P=P, C=C, Bc=Bc, Tb=Tb, **gt_dims)
     return a, dims
@@ -370,11 +376,9 @@ def parse_completions_device(text: torch.Tensor, offsets: torch.Tensor, task: to
             over = out["overflow"].tolist()
             if not any(over):
                 break
-            if over[2] > 32 or over[3] > 32:
-                raise ValueError("more than 32 boxes per claim / think block")    # as pack_rollouts
             for k, v in zip(("P", "C", "Bc", "Tb"), over):
                 if v:
-                    caps[k] = min(32, v) if k in ("Bc", "Tb") else v
+                    caps[k] = v
     return out, caps
 
 
@@ -412,11 +416,9 @@ def rewards_from_text(contents: Sequence[str], gts: Sequence[dict], G: int = 1, 
             over = h_over.tolist()
             if not any(over):
                 break
-            if over[2] > 32 or over[3] > 32:
-                raise ValueError("more than 32 boxes per claim / think block")    # as pack_rollouts
             for k, v in zip(("P", "C", "Bc", "Tb"), over):
                 if v:
-                    caps[k] = min(32, v) if k in ("Bc", "Tb") else v
+                    caps[k] = v
     return h_out.numpy().copy() if to_host else out
 
 
@@ -448,8 +450,35 @@ def _shared_gt_group(kwargs, R: int) -> int:
     return G
 
 
-def grounded_rewards(completions, **kwargs) -> np.ndarray:
-    """All five numeric rewards for a batch: [len(completions), 5] float64 (host)."""
+class _Batch:
+    """The five reward columns of one batch plus what the per-callable failure semantics need."""
+    __slots__ = ("val", "G", "task", "gt_err", "seg_unpack_ok", "no_key_frames", "contents")
+
+
+def _gt_of_prompt(task, answer):
+    """-> (gt_seg, gt_vbox, error, unpack_ok).  `error`: what `ast.literal_eval` (or the MCQ split) raises on this
+    ground truth in the reference (reward_func.py:116-118, :146-147, :407-409); `unpack_ok`: the literal is a
+    sequence of exactly two numbers, so `start2, end2 = gt_ans` (:137, :165) works."""
+    try:
+        seg, vbox = parse_gt_answer(task, answer)
+        if len(seg) == 2:
+            return seg, vbox, None, True
+        if len(seg) > 2:                                  # evaluates, but `start2, end2 = gt_ans` cannot unpack it
+            return seg[:2], vbox, None, False
+        err = IndexError("list index out of range")       # gt_ans[1] at :419
+    except Exception as exc:                              # noqa: BLE001 - the reference catches Exception (:175)
+        err = exc
+    # literal_eval itself may have worked (e.g. three numbers): thk_temporal_segment_reward only reads [0] and [1]
+    try:
+        gt = answer.split("\n")[1] if task == "temporal QA (MCQ)" else answer
+        lit = ast.literal_eval(gt)
+        seg = [float(lit[0]), float(lit[1])]
+        return seg, None, None, False
+    except Exception:                                     # noqa: BLE001
+        return [0.0, 0.0], None, err, False
+
+
+def _batch_rewards(completions, kwargs) -> _Batch:
     contents = [c[0]["content"] for c in completions]
     task = kwargs["task"][0]                                   # the reference reads element 0 for the batch
     step = kwargs["step_percent"][0] if "step_percent" in kwargs else 0.0
@@ -467,21 +496,90 @@ def grounded_rewards(completions, **kwargs) -> np.ndarray:
     get = lambda name, i: (kwargs[name][i] if name in kwargs and kwargs[name] is not None else None)
     R = len(contents)
     G = _shared_gt_group(kwargs, R)
+    b = _Batch()
+    b.G, b.task, b.contents = G, task, contents
+    b.gt_err, b.seg_unpack_ok, b.no_key_frames = [], [], []
     gts = []
     for i in range(0, R, G):
-        gt_seg, gt_vbox = parse_gt_answer(task, get("answer", i) or "")
+        gt_seg, gt_vbox, err, unpack_ok = _gt_of_prompt(task, get("answer", i) or "")
+        b.gt_err.append(err)
+        b.seg_unpack_ok.append(unpack_ok)
+        b.no_key_frames.append(not (get("key_frames", i) or []))
         gts.append(dict(task=task, step_percent=step, gt_seg=gt_seg, gt_vbox=gt_vbox,
                         key_frames=get("key_frames", i) or [], key_items=get("key_items", i) or {},
                         image_size=get("image_size", i) or (1, 1),
                         image_size_refine=get("image_size_refine", i) or (1, 1)))
-    val = rewards_from_text(contents, gts, G, to_host=True)
-    _cache["key"], _cache["val"] = key, val
-    return val
+    b.val = rewards_from_text(contents, gts, G, to_host=True)
+    _cache["key"], _cache["val"] = key, b
+    return b
+
+
+def grounded_rewards(completions, **kwargs) -> np.ndarray:
+    """All five numeric rewards for a batch: [len(completions), 5] float64 (host), before the per-callable
+    failure semantics of `apply_failure_semantics`."""
+    return _batch_rewards(completions, kwargs).val
+
+
+_THINK_RE = re.compile(r"<think>(.*?)</think>", re.DOTALL)
+_TIME_RE = re.compile(r"<t>([\d.]+)</t>s")
+
+
+def apply_failure_semantics(j: int, col: np.ndarray, task: str, G: int, gt_err, seg_unpack_ok, no_key_frames,
+                            contents) -> List[float]:
+    """What the reference does when the GROUND TRUTH of a prompt is unusable, per callable (`col` = that callable's
+    column computed with a neutral ground truth for the broken prompts; prompts are blocks of G rollouts).
+
+    0 ans_tiou_reward: the per-rollout `try/except Exception -> 0.0` (reward_func.py:175-177) swallows the error,
+      but `idx += 1` sits INSIDE the try (:174): after the first rollout whose `ast.literal_eval(answer[idx])`
+      raises, idx never advances again, every later rollout of the batch re-reads that same broken answer and
+      scores 0.0 as well.  Reproduced: zeros from the first rollout of the first broken prompt to the end of the batch.
+      A literal that evaluates but is not two numbers only fails at `start2, end2 = gt_ans` for rollouts whose
+      answer matched: those score 0.0 here too (the idx drift that follows is not reproduced).
+    1 ans_viou_reward: GT box that is not JSON -> swallowed, 0.0 (:230-232).
+    2 thk_temporal_segment_reward: `ast.literal_eval` is OUTSIDE any try (:409): the reference raises out of the
+      callable for the first rollout that reaches it (a <think> block, task temporal QA / MCQ).  Same exception here.
+    3 thk_temporal_point_reward: `min([])` over an empty key-frame list raises ValueError (:457) for the first
+      rollout with a parsable timestamp in <think>.  Same here.
+    4 thk_spatial_reward: no ground-truth parsing that can fail before the arithmetic; unchanged."""
+    out = [float(x) for x in col]
+    temporal = task in ("temporal QA", "temporal QA (MCQ)")
+    if j == 0 and temporal:
+        for q, err in enumerate(gt_err):
+            if err is not None:
+                print("Error in reward_fn for question_type '%s': %s" % ("TG" if task == "temporal QA" else "TG_MCQ", err))
+                for i in range(q * G, len(out)):
+                    out[i] = 0.0
+                break
+            if not seg_unpack_ok[q]:
+                for i in range(q * G, (q + 1) * G):
+                    out[i] = 0.0
+    elif j == 2 and temporal:
+        for q, err in enumerate(gt_err):
+            if err is not None and any(_THINK_RE.search(c) for c in contents[q * G:(q + 1) * G]):
+                raise err
+    elif j == 3 and not (task in ("visual QA", "temporal QA", "temporal QA (MCQ)") or "General video QA" in task):
+        for q, empty in enumerate(no_key_frames):
+            if not empty:
+                continue
+            for c in contents[q * G:(q + 1) * G]:
+                m = _THINK_RE.search(c)
+                if not m:
+                    continue
+                try:
+                    times = [float(x) for x in _TIME_RE.findall(m.group(1))]
+                except ValueError:
+                    times = []
+                if times:
+                    raise ValueError("min() iterable argument is empty")      # what `min([])` says (:457)
+    return out
 
 
 def _column(j):
     def f(completions, **kwargs) -> List[float]:
-        return [float(x) for x in grounded_rewards(completions, **kwargs)[:, j]]
+        b = _batch_rewards(completions, kwargs)
+        if not any(e is not None for e in b.gt_err) and all(b.seg_unpack_ok) and not any(b.no_key_frames):
+            return [float(x) for x in b.val[:, j]]
+        return apply_failure_semantics(j, b.val[:, j], b.task, b.G, b.gt_err, b.seg_unpack_ok, b.no_key_frames, b.contents)
     return f
 
 

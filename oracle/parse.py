@@ -89,6 +89,9 @@ def parse_text(content, task):
     return r
 
 
+INVALID_BOX = np.array([0x7FF8B0B0DEADBEEF], np.uint64).view(np.float64)[0]   # O3V_INVALID_BOX_BITS (include/o3v.h)
+
+
 def box_ok(b):
     """calculate_iou's acceptance of a prediction (reward_func.py:361-367)."""
     if not (isinstance(b, list) and len(b) == 4):
@@ -123,19 +126,25 @@ def pack(parsed, P, C, Bc, Tb):
         for c, (t, boxes) in enumerate(r["claims"][:C]):
             a["claim_t"][i, c] = t
             a["claim_nbox"][i, c] = len(boxes)
-            for b, box in enumerate(boxes[:32]):
+            for b, box in enumerate(boxes):
                 v = box_ok(box)
                 if v is not None:
-                    a["claim_valid"][i, c] |= np.uint32(1 << b)
+                    if b < 32:
+                        a["claim_valid"][i, c] |= np.uint32(1 << b)
                     if b < Bc:
                         a["claim_box"][i, c, b] = v
+                elif 32 <= b < Bc:                      # include/o3v.h: beyond the mask, validity lives in the slot
+                    a["claim_box"][i, c, b, 0] = INVALID_BOX
         a["n_tboxes"][i] = len(r["think_boxes"])
-        for b, box in enumerate(r["think_boxes"][:32]):
+        for b, box in enumerate(r["think_boxes"]):
             v = box_ok(box)
             if v is not None:
-                a["tbox_valid"][i] |= np.uint32(1 << b)
+                if b < 32:
+                    a["tbox_valid"][i] |= np.uint32(1 << b)
                 if b < Tb:
                     a["think_box"][i, b] = v
+            elif 32 <= b < Tb:
+                a["think_box"][i, b, 0] = INVALID_BOX
     return a
 
 
@@ -152,10 +161,22 @@ def used_mask(a):
     m["claim_t"] = cm
     m["claim_nbox"] = cm
     m["claim_valid"] = cm
-    bits = (a["claim_valid"][:, :, None] >> np.arange(Bc, dtype=np.uint32)[None, None, :]) & 1
-    m["claim_box"] = np.repeat((cm[:, :, None] & (bits != 0))[..., None], 4, 3)
-    tb = (a["tbox_valid"][:, None] >> np.arange(Tb, dtype=np.uint32)[None, :]) & 1
-    m["think_box"] = np.repeat(((np.arange(Tb)[None, :] < a["n_tboxes"][:, None]) & (tb != 0))[..., None], 4, 2)
+    def box_mask(valid, boxes, exists):
+        """valid [..] uint32 masks, boxes [.., B, 4], exists [.., B] (slot < count) -> [.., B, 4] entries to compare:
+        all four numbers of a valid box; beyond bit 31 the first number always (value or the invalid marker) and the
+        rest when the slot is not marked invalid."""
+        B = boxes.shape[-2]
+        idx = np.arange(B)
+        low = ((valid[..., None] >> np.minimum(idx, 31).astype(np.uint32)) & 1) != 0
+        high_valid = boxes[..., 0].view(np.uint64) != np.uint64(0x7FF8B0B0DEADBEEF)
+        is_valid = np.where(idx < 32, low, high_valid) & exists
+        m4 = np.repeat(is_valid[..., None], 4, -1)
+        m4[..., 0] |= exists & (idx >= 32)
+        return m4
+    exists_c = cm[:, :, None] & (np.arange(Bc)[None, None, :] < a["claim_nbox"][:, :, None])
+    m["claim_box"] = box_mask(a["claim_valid"], a["claim_box"], exists_c)
+    exists_t = np.arange(Tb)[None, :] < a["n_tboxes"][:, None]
+    m["think_box"] = box_mask(a["tbox_valid"], a["think_box"], exists_t)
     return m
 
 

@@ -195,6 +195,56 @@ def gen_compute_loss():
     print("compute_loss_small.json", res["gspo"]["loss"], res["grpo"]["loss"])
 
 
+def reward_failure_cases():
+    """Batches (B prompts x G rollouts, kwargs repeated G times as grpo_trainer.py:650-654 builds them) in which
+    the GROUND TRUTH of one prompt is unusable.  Shared with the tests."""
+    seg = lambda a, b: "<think>at <t>%s</t>s and <t>%s</t>s</think><answer>From <t>%s</t>s to <t>%s</t>s</answer>" % (a, b, a, b)
+    nomatch = "<think>hm <t>3.0</t>s</think><answer>no idea</answer>"
+    kf = [{"idx": 3, "time": 5.0, "path": "a.jpg"}]
+    ki = {"3": {"dog": [[0.1, 0.1, 0.5, 0.5]]}}
+    def batch(task, answers, texts, G, key_frames=None):
+        B = len(answers)
+        rep = lambda xs: [x for x in xs for _ in range(G)]
+        return dict(task=task, G=G, texts=texts,
+                    kwargs=dict(task=rep([task] * B), answer=rep(answers), step_percent=rep([0.3] * B),
+                                key_frames=rep(key_frames if key_frames is not None else [kf] * B),
+                                key_items=rep([ki] * B), image_size=rep([(640, 360)] * B),
+                                image_size_refine=rep([(448, 252)] * B)))
+    six = [seg(12, 18), nomatch, seg(1, 2), seg(11.5, 30), seg(6, 8), nomatch]
+    return {
+        "tiou_bad_literal_middle": batch("temporal QA", ["[10.0, 20.0]", "oops(", "[5.0, 9.0]"], six, 2),
+        "tiou_bad_literal_first": batch("temporal QA", ["[", "[10.0, 20.0]", "[5.0, 9.0]"], six, 2),
+        "tiou_mcq_no_second_line": batch("temporal QA (MCQ)", ["B\n[10.0, 20.0]", "B", "C\n[5.0, 9.0]"], six, 2),
+        "tiou_three_numbers": batch("temporal QA", ["[10.0, 20.0]", "[1, 2, 3]", "[5.0, 9.0]"], six, 2),
+        "point_empty_key_frames": batch("temporal-spatial free-form QA", ["x", "y"], six[:4], 2, key_frames=[kf, []]),
+        "point_empty_key_frames_no_times": batch("temporal-spatial free-form QA", ["x", "y"],
+                                                 [six[0], six[1], "<think>none</think><answer>a</answer>", "plain"], 2,
+                                                 key_frames=[kf, []]),
+    }
+
+
+def gen_reward_failures():
+    """The live reference's five numeric reward callables on `reward_failure_cases()`: values, or the exception type
+    a callable raises out of."""
+    import contextlib
+    import io
+    rf = ref_import.load_reward_func()
+    res = {}
+    for name, c in reward_failure_cases().items():
+        comps = [[{"role": "assistant", "content": t}] for t in c["texts"]]
+        row = {}
+        for fn in orw.REWARD_NAMES:
+            try:
+                with contextlib.redirect_stdout(io.StringIO()):
+                    row[fn] = [repr(float(x)) for x in getattr(rf, fn)(completions=comps, prompts=None, **c["kwargs"])]
+            except Exception as exc:                       # noqa: BLE001
+                row[fn] = {"raises": type(exc).__name__}
+        res[name] = row
+        print(name, row)
+    with open(os.path.join(HERE, "reward_failures.json"), "w") as f:
+        json.dump(res, f, indent=1)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:                     # e.g. `gen_golden.py gspo compute_loss`
         for name in sys.argv[1:]:
@@ -202,6 +252,7 @@ if __name__ == "__main__":
         sys.exit(0)
     gen_gspo()
     gen_compute_loss()
+    gen_reward_failures()
     gen_parse()
     gen_logps()
     gen_rewards()

@@ -196,3 +196,36 @@ def test_reward_callables_share_ground_truth_within_a_group():
             launches.append(t.launches)
         np.testing.assert_allclose(np.array(cols).T, want, rtol=0, atol=1e-6)
         assert launches[0] > 0 and not any(launches[1:])       # one GPU pass serves all five callables
+
+
+def test_more_than_32_boxes_score_like_the_reference():
+    """Round-1 advisor finding: > 32 boxes in one claim / think block used to raise ValueError out of the reward
+    callable and abort the step; the reference scores such rollouts normally."""
+    from open_o3_video_b200 import rewards
+    from test_parse_cpu import many_box_texts
+    import warnings
+    cases = many_box_texts()
+    got_rows, exp_rows, caps = _check([t for t, _ in cases], [k for _, k in cases])
+    assert caps["Bc"] >= 70 and caps["Tb"] >= 45
+    kf = [{"idx": 3, "time": 5.4, "path": "a"}, {"idx": 9, "time": 12.0, "path": "b"}]
+    ki = {"3": {"dog": [[.05, .1, .5, .6]], "x": [[.2, .2, .9, .9], [.0, .0, .1, .1]]}, "9": {"cat": [[.02, .03, .1, .14]]}}
+    for text, task in cases:
+        kw = dict(task=task, answer="<box>[120, 90, 310, 300]</box>" if task == "visual QA" else "free", key_frames=kf,
+                  key_items=ki, image_size=(500, 400), image_size_refine=(448, 364), step_percent=0.3)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = orw.rewards_for_rollout(op.rollout_from_text(text, kw))
+        completions = [[{"role": "assistant", "content": text}]]
+        got = [rewards.reward_funcs_registry[n](prompts=None, completions=completions, **{k: [v] for k, v in kw.items()})[0]
+               for n in rewards.REWARD_NAMES]
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-6)
+        assert got[4] > 0.0                                    # the spatial reward really depends on the boxes
+    # the parsed-rollout route (pack_rollouts) takes them too
+    ro = [op.rollout_from_text(t, dict(task=k, answer="<box>[120, 90, 310, 300]</box>" if k == "visual QA" else "free",
+                                       key_frames=kf, key_items=ki, image_size=(500, 400), image_size_refine=(448, 364),
+                                       step_percent=0.3)) for t, k in cases]
+    for r in ro:
+        out = rewards.rewards_from_rollouts([r], 1).cpu().numpy()[0]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            np.testing.assert_allclose(out, orw.rewards_for_rollout(r), rtol=0, atol=1e-6)

@@ -258,3 +258,45 @@ def test_documented_deviations():
     assert (n, numeric) == (4, True) and math.isinf(v[0])
     # homogeneous nested lists become a 2-D array in the reference (then an ambiguous truth value): here the box scores 0
     assert scan_host.json_box("[[1],[2],[3],[4]]")[:2] == (4, False)
+
+
+# ------------------------------------------------------------------------------- more than 32 boxes (round-1 advisor finding)
+def many_box_texts():
+    """Degenerate repetition loops: 40-70 boxes in one claim / one visual-QA think block, invalid ones (wrong
+    length, strings, non-JSON) on both sides of the 32-bit validity mask."""
+    def boxes(n, bad=(), drop=()):
+        out = []
+        for b in range(n):
+            if b in drop:
+                out.append("<box>[1,2,3,4}</box>")                 # not JSON: claims are dropped, think boxes skipped
+            elif b in bad:
+                out.append("<box>[%d,2,3]</box>" % b if b % 2 else "<box>[\"a\",%d,3,4]</box>" % b)
+            else:
+                out.append("<box>[%d,%d,%d,%d]</box>" % (10 + b, 20 + b, 200 + 3 * b, 220 + 2 * b))
+        return "".join(out)
+    ts = "<think><obj>dog</obj>%sat<t>5.0</t>s then <obj>cat</obj><box>[10,10,50,50]</box>at<t>12.5</t>s</think><answer>B</answer>"
+    vq = "<think>%s</think><answer><box>[100,100,300,300]</box></answer>"
+    return [
+        (ts % boxes(40), "temporal-spatial free-form QA"),
+        (ts % boxes(40, bad=(0, 5, 31, 32, 33, 39)), "temporal-spatial free-form QA"),
+        (ts % boxes(70, bad=tuple(range(30, 70, 3))), "temporal-spatial free-form QA"),
+        (ts % boxes(33, bad=(32,)), "temporal-spatial free-form QA"),
+        (vq % boxes(40), "visual QA"),
+        (vq % boxes(45, bad=(2, 31, 32, 40), drop=(1, 30, 33, 44)), "visual QA"),
+        (vq % boxes(64, bad=tuple(range(0, 64, 2))), "visual QA"),
+    ]
+
+
+def test_scanner_more_than_32_boxes_marks_validity_in_the_slot():
+    texts, tasks = zip(*many_box_texts())
+    bad, got, exp, ov = _compare(list(texts), list(tasks))
+    assert not bad, sorted(bad)
+    assert exp["claim_nbox"].max() == 70 and exp["n_tboxes"].max() == 64
+    # the invalid markers are exact bit patterns (mismatches() treats every NaN as equal)
+    marker = np.uint64(0x7FF8B0B0DEADBEEF)
+    used = op.used_mask(exp)
+    for name in ("claim_box", "think_box"):
+        g, e = got[name][..., 0].view(np.uint64), exp[name][..., 0].view(np.uint64)
+        u = used[name][..., 0]
+        assert np.array_equal((g == marker) & u, (e == marker) & u) and ((e == marker) & u).sum() > 3
+        assert not (u[..., :32] & (e[..., :32] == marker)).any()                     # below 32 the mask rules
