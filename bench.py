@@ -200,7 +200,8 @@ def run_ours(args):
     def step(h, i, r, m, rw):
         return logprob.fused_logprob_gspo(h, weight, i, r, m, rw, G, BETA, EPS, EPS, True, None, v_offset=v_off,
                                           group=group, chunk_tokens=args.chunk_tokens, d_weight_out=None,
-                                          overlap_dlogits=bool(args.overlap_dlogits))
+                                          overlap_dlogits=bool(args.overlap_dlogits),
+                                          fuse_dlogits=bool(args.fuse_dlogits))
 
     def barrier():
         if world > 1:
@@ -386,6 +387,9 @@ def main():
                     help="N > 1, end-to-end arm: how the per-rank input slices reach every rank")
     ap.add_argument("--overlap-dlogits", type=int, default=0,
                     help="1: run the dlogits pass of chunk c on a side stream beside K1 of chunk c+1")
+    ap.add_argument("--fuse-dlogits", type=int, default=0,
+                    help="1: softmax backward inside the operand pipeline of the backward GEMMs (shared-memory "
+                         "transform); 0: separate in-place dlogits pass (default: faster under the power cap)")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

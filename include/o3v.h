@@ -40,6 +40,7 @@ extern "C" {
 #define O3V_ERR_WORKSPACE (-4)        /* workspace too small */
 #define O3V_ERR_DRIVER (-5)           /* cuTensorMapEncodeTiled / driver entry point failed */
 #define O3V_ERR_SHAPE (-6)            /* unsupported shape (e.g. H % 64 != 0) */
+#define O3V_ERR_UNSUPPORTED_MODE (-7) /* the entry point does not exist for the tile mode selected with o3v_set_tunable */
 
 int o3v_version(void);
 const char* o3v_strerror(int code);
@@ -133,6 +134,21 @@ int o3v_lmhead_bwd_dhidden(const void* dlogits, int64_t ld_dlogits, const void* 
 int o3v_lmhead_bwd_dweight(const void* dlogits, int64_t ld_dlogits, const void* hidden,
                            int64_t T, int64_t V, int64_t H,
                            float* d_weight, int32_t accumulate, void* stream);
+
+/* The same two GEMMs with the softmax backward FUSED into their operand pipeline: `logits` is the bf16 logits chunk
+ * exactly as o3v_lmhead_fwd stored it (it is NOT modified), and every A tile is rewritten to P in shared memory
+ * between its TMA load and the tcgen05.mma that reads it (by eight transform warps per CTA).  Replaces
+ * o3v_lmhead_dlogits + o3v_lmhead_bwd_*: no elementwise pass over the chunk (2 x 2 x T x V bytes of HBM traffic).
+ * `rows` [T] 16-byte records (o3v_lmhead_softmax_bwd_rows: per-token g, log2|g| - lse*log2e and the target column
+ * within this vocabulary slice), caller-owned, 16-byte aligned, T * 16 bytes.  Needs the default tile mode
+ * (cta_pair_bwd = 2, bwd_wide = 1), else O3V_ERR_UNSUPPORTED_MODE.  Rows with grad_logp == 0 (masked-out tokens)
+ * are never read nor exponentiated. */
+int o3v_lmhead_softmax_bwd_rows(const float* lse, const float* grad_logp, const int64_t* targets, int64_t v_offset,
+                                int64_t V, int64_t T, void* rows, void* stream);
+int o3v_lmhead_bwd_dhidden_fused(const void* logits, int64_t ld_logits, const void* rows, const void* weight,
+                                 int64_t T, int64_t V, int64_t H, void* d_hidden, int32_t out_is_fp32, void* stream);
+int o3v_lmhead_bwd_dweight_fused(const void* logits, int64_t ld_logits, const void* rows, const void* hidden,
+                                 int64_t T, int64_t V, int64_t H, float* d_weight, int32_t accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * K3  KL + group advantages + GSPO (or token-level) ratio / clip / loss, forward and

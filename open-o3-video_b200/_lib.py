@@ -59,6 +59,11 @@ SIGNATURES = {
                                        c_void_p, c_int32, c_void_p]),
     "o3v_lmhead_bwd_dweight": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64,
                                        c_void_p, c_int32, c_void_p]),
+    "o3v_lmhead_softmax_bwd_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "o3v_lmhead_bwd_dhidden_fused": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                             c_void_p, c_int32, c_void_p]),
+    "o3v_lmhead_bwd_dweight_fused": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                             c_void_p, c_int32, c_void_p]),
     "o3v_gspo_workspace_bytes": (c_size_t, [c_int64]),
     "o3v_gspo_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,

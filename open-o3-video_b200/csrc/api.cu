@@ -35,6 +35,7 @@ extern "C" const char* o3v_strerror(int code) {
     case O3V_ERR_WORKSPACE: return "o3v: workspace too small";
     case O3V_ERR_DRIVER: return "o3v: cuTensorMapEncodeTiled / driver entry point failed";
     case O3V_ERR_SHAPE: return "o3v: unsupported shape";
+    case O3V_ERR_UNSUPPORTED_MODE: return "o3v: entry point not available in the tile mode selected with o3v_set_tunable";
     default: break;
   }
   if (code > 0) return cudaGetErrorString((cudaError_t)code);

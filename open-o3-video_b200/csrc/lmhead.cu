@@ -21,6 +21,7 @@ static int g_dh_mfast = 0;      // K2a item order (0 = n fastest)
 static int g_dw_mfast = 0;      // K2b item order
 static int g_fwd_groups = 0;    // n-groups (vocab splits) per m-block in K1; 0 = auto
 static int g_max_ctas = 0;      // cap on the persistent grid; 0 = all SMs
+static int g_bwd_prefetch = 0;  // K2a / K2b: L2 prefetch distance (k-blocks) for the A operand streamed from HBM
 // L2 eviction hints (0 none, 1 evict first, 2 evict last): K1 hidden / W loads and logits store, K2 P / other operand
 static int g_hint_fwd_a = 0, g_hint_fwd_b = 0, g_hint_fwd_store = 0, g_hint_bwd_a = 0, g_hint_bwd_b = 0;
 
@@ -82,11 +83,11 @@ static int acquire_wave_sync(unsigned int** out, cudaStream_t st) {
 // ------------------------------------------------------------------------------------
 // launch
 // ------------------------------------------------------------------------------------
-template <bool kAMN, bool kBMN, int kNCta, int kEpi, int kAcc = 1>
+template <bool kAMN, bool kBMN, int kNCta, int kEpi, int kAcc = 1, bool kXform = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
                        cudaStream_t st) {
   using S = GemmShape<kNCta, kEpi == EPI_STATS, kAcc>;
-  auto kern = lmhead_gemm_kernel<kAMN, kBMN, kNCta, kEpi, kAcc>;
+  auto kern = lmhead_gemm_kernel<kAMN, kBMN, kNCta, kEpi, kAcc, kXform>;
   // the opt-in shared-memory size is a per-device (per-context) function attribute
   static std::atomic<bool> attr_set[64];
   int dev = 0;
@@ -102,7 +103,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   if (workers < 1) workers = 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(workers * kNCta));
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3(kXform ? kGemmThreadsXform : kGemmThreads);
   cfg.dynamicSmemBytes = S::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -280,6 +281,7 @@ extern "C" int o3v_set_tunable(const char* name, int value) {
   else if (n == "dw_mfast") g_dw_mfast = value ? 1 : 0;
   else if (n == "fwd_groups") g_fwd_groups = value;
   else if (n == "max_ctas") g_max_ctas = value;
+  else if (n == "bwd_prefetch") g_bwd_prefetch = value < 0 ? 0 : value;
   else if (n == "hint_fwd_a") g_hint_fwd_a = value;
   else if (n == "hint_fwd_b") g_hint_fwd_b = value;
   else if (n == "hint_fwd_store") g_hint_fwd_store = value;
@@ -396,9 +398,11 @@ extern "C" int o3v_lmhead_dlogits(void* logits, int64_t T, int64_t V, int64_t ld
   return O3V_OK;
 }
 
-extern "C" int o3v_lmhead_bwd_dhidden(const void* dlogits, int64_t ld_dlogits, const void* weight,
-                                      int64_t T, int64_t V, int64_t H, void* d_hidden, int32_t out_is_fp32,
-                                      void* stream) {
+// softmax-backward parameters of the fused variants (nullptr = plain GEMM on a ready-made P)
+struct XformArgs { const void* rows; };
+
+static int bwd_dhidden_impl(const void* dlogits, int64_t ld_dlogits, const void* weight, int64_t T, int64_t V, int64_t H,
+                            void* d_hidden, int32_t out_is_fp32, const XformArgs* x, void* stream) {
   if (!dlogits || !weight || !d_hidden || T <= 0 || V <= 0 || H <= 0) return O3V_ERR_INVALID_ARG;
   if (H % 8 != 0 || ld_dlogits % 8 != 0 || ld_dlogits < V) return O3V_ERR_SHAPE;
   if (T > 0x7fffffffLL - 512 || V > 0x7fffffffLL - 512) return O3V_ERR_SHAPE;
@@ -411,20 +415,67 @@ extern "C" int o3v_lmhead_bwd_dhidden(const void* dlogits, int64_t ld_dlogits, c
   const bool wide = (ncta == 2 && g_bwd_wide);
   plan_tiles(p, ncta, 1 << 20, wide ? 2 : 1);       // one n-tile per item
   p.out = d_hidden; p.ld_out = H; p.out_fp32 = out_is_fp32 ? 1 : 0; p.m_fast = g_dh_mfast;
+  p.prefetch_a = g_bwd_prefetch;
   p.hint_a = g_hint_bwd_a; p.hint_b = g_hint_bwd_b;
   CUtensorMap tmA, tmB;
   if ((rc = make_tmap_bf16(&tmA, dlogits, V, T, ld_dlogits, 128))) return rc;   // A = P, K-major (K = V)
   if ((rc = make_tmap_bf16(&tmB, weight, H, V, H, 64))) return rc;              // B = W, MN-major (N = H contiguous)
   cudaStream_t st = (cudaStream_t)stream;
   if (g_bwd_sync && (rc = acquire_wave_sync(&p.wave_sync, st))) return rc;
+  if (x) {
+    if (!wide) return O3V_ERR_UNSUPPORTED_MODE;        // the transform runs on the idle epilogue warps of 256x512 pair tiles
+    p.x_rows = reinterpret_cast<const int4*>(x->rows); p.x_tokens = T;
+    return launch_gemm<false, true, 2, EPI_STORE, 2, true>(tmA, tmB, tmA, p, st);
+  }
   if (wide) return launch_gemm<false, true, 2, EPI_STORE, 2>(tmA, tmB, tmA, p, st);
   return (ncta == 1) ? launch_gemm<false, true, 1, EPI_STORE>(tmA, tmB, tmA, p, st)
                      : launch_gemm<false, true, 2, EPI_STORE>(tmA, tmB, tmA, p, st);
 }
 
-extern "C" int o3v_lmhead_bwd_dweight(const void* dlogits, int64_t ld_dlogits, const void* hidden,
-                                      int64_t T, int64_t V, int64_t H, float* d_weight, int32_t accumulate,
+extern "C" int o3v_lmhead_bwd_dhidden(const void* dlogits, int64_t ld_dlogits, const void* weight,
+                                      int64_t T, int64_t V, int64_t H, void* d_hidden, int32_t out_is_fp32,
                                       void* stream) {
+  return bwd_dhidden_impl(dlogits, ld_dlogits, weight, T, V, H, d_hidden, out_is_fp32, nullptr, stream);
+}
+
+__global__ void softmax_bwd_rows_kernel(const float* __restrict__ lse, const float* __restrict__ g,
+                                        const int64_t* __restrict__ targets, int64_t v_offset, int64_t V, int64_t T,
+                                        SoftmaxBwdRow* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  SoftmaxBwdRow r;
+  r.g = g[t];
+  r.c = r.g != 0.f ? __log2f(fabsf(r.g)) - lse[t] * kLog2e : 0.f;
+  const int64_t col = targets[t] - v_offset;
+  r.tcol = (col >= 0 && col < V) ? (int32_t)col : -1;
+  r.pad = 0;
+  out[t] = r;
+}
+
+extern "C" int o3v_lmhead_softmax_bwd_rows(const float* lse, const float* grad_logp, const int64_t* targets,
+                                           int64_t v_offset, int64_t V, int64_t T, void* rows, void* stream) {
+  if (!lse || !grad_logp || !targets || !rows || v_offset < 0 || V <= 0 || T <= 0) return O3V_ERR_INVALID_ARG;
+  if (V > 0x7fffffffLL - 512) return O3V_ERR_SHAPE;
+  if (reinterpret_cast<uintptr_t>(rows) & 15u) return O3V_ERR_ALIGNMENT;
+  int rc = check_device();
+  if (rc) return rc;
+  static_assert(sizeof(SoftmaxBwdRow) == 16, "record layout");
+  softmax_bwd_rows_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, (cudaStream_t)stream>>>(
+      lse, grad_logp, targets, v_offset, V, T, reinterpret_cast<SoftmaxBwdRow*>(rows));
+  O3V_LAUNCH_CHECK();
+  return O3V_OK;
+}
+
+extern "C" int o3v_lmhead_bwd_dhidden_fused(const void* logits, int64_t ld_logits, const void* rows,
+                                            const void* weight, int64_t T, int64_t V, int64_t H, void* d_hidden,
+                                            int32_t out_is_fp32, void* stream) {
+  if (!rows || (reinterpret_cast<uintptr_t>(rows) & 15u)) return O3V_ERR_INVALID_ARG;
+  XformArgs x = {rows};
+  return bwd_dhidden_impl(logits, ld_logits, weight, T, V, H, d_hidden, out_is_fp32, &x, stream);
+}
+
+static int bwd_dweight_impl(const void* dlogits, int64_t ld_dlogits, const void* hidden, int64_t T, int64_t V, int64_t H,
+                            float* d_weight, int32_t accumulate, const XformArgs* x, void* stream) {
   if (!dlogits || !hidden || !d_weight || T <= 0 || V <= 0 || H <= 0) return O3V_ERR_INVALID_ARG;
   if (H % 8 != 0 || ld_dlogits % 8 != 0 || ld_dlogits < V) return O3V_ERR_SHAPE;
   if (T > 0x7fffffffLL - 512 || V > 0x7fffffffLL - 512) return O3V_ERR_SHAPE;
@@ -437,15 +488,35 @@ extern "C" int o3v_lmhead_bwd_dweight(const void* dlogits, int64_t ld_dlogits, c
   const bool wide = (ncta == 2 && g_bwd_wide);
   plan_tiles(p, ncta, 1 << 20, wide ? 2 : 1);
   p.out = d_weight; p.ld_out = H; p.out_fp32 = 1; p.accumulate = accumulate ? 1 : 0; p.m_fast = g_dw_mfast;
+  p.prefetch_a = g_bwd_prefetch;
   p.hint_a = g_hint_bwd_a; p.hint_b = g_hint_bwd_b;
   CUtensorMap tmA, tmB;
   if ((rc = make_tmap_bf16(&tmA, dlogits, V, T, ld_dlogits, 64))) return rc;    // A = P^T, MN-major (M = V contiguous)
   if ((rc = make_tmap_bf16(&tmB, hidden, H, T, H, 64))) return rc;              // B = hidden, MN-major
   cudaStream_t st = (cudaStream_t)stream;
   if (g_bwd_sync && (rc = acquire_wave_sync(&p.wave_sync, st))) return rc;
+  if (x) {
+    if (!wide) return O3V_ERR_UNSUPPORTED_MODE;
+    p.x_rows = reinterpret_cast<const int4*>(x->rows); p.x_tokens = T;
+    return launch_gemm<true, true, 2, EPI_ACCUM, 2, true>(tmA, tmB, tmA, p, st);
+  }
   if (wide) return launch_gemm<true, true, 2, EPI_ACCUM, 2>(tmA, tmB, tmA, p, st);
   return (ncta == 1) ? launch_gemm<true, true, 1, EPI_ACCUM>(tmA, tmB, tmA, p, st)
                      : launch_gemm<true, true, 2, EPI_ACCUM>(tmA, tmB, tmA, p, st);
+}
+
+extern "C" int o3v_lmhead_bwd_dweight(const void* dlogits, int64_t ld_dlogits, const void* hidden,
+                                      int64_t T, int64_t V, int64_t H, float* d_weight, int32_t accumulate,
+                                      void* stream) {
+  return bwd_dweight_impl(dlogits, ld_dlogits, hidden, T, V, H, d_weight, accumulate, nullptr, stream);
+}
+
+extern "C" int o3v_lmhead_bwd_dweight_fused(const void* logits, int64_t ld_logits, const void* rows,
+                                            const void* hidden, int64_t T, int64_t V, int64_t H, float* d_weight,
+                                            int32_t accumulate, void* stream) {
+  if (!rows || (reinterpret_cast<uintptr_t>(rows) & 15u)) return O3V_ERR_INVALID_ARG;
+  XformArgs x = {rows};
+  return bwd_dweight_impl(logits, ld_logits, hidden, T, V, H, d_weight, accumulate, &x, stream);
 }
 
 extern "C" int o3v_debug_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N,

@@ -53,6 +53,21 @@ struct GemmParams {
   int32_t accumulate;
   // L2 eviction hints of the TMA traffic (0 = none, 1 = evict first, 2 = evict last)
   int32_t hint_a, hint_b, hint_store;
+  // kXform: the A operand in HBM is the bf16 LOGITS chunk z[t, v]; the softmax backward
+  //   P[t, v] = g[t] * ([v + v_offset == target[t]] - exp(z[t, v] - lse[t]))
+  // is applied to every A tile in shared memory between its TMA load and the MMAs that read it
+  int32_t prefetch_a;         // > 0: the producer prefetches the A tile of k-block kb + prefetch_a into L2
+  const int4* x_rows;         // [tokens] packed per-token scalars (SoftmaxBwdRow, written by softmax_bwd_rows_kernel)
+  int64_t x_tokens;           // number of token rows
+};
+
+// Per-token scalars of the fused softmax backward, one 16-byte record so that a transform thread needs ONE load per
+// token: P[t, v] = sgn(-g) * 2^(z * log2e + c) (+ g at column tcol of this vocabulary slice).
+struct SoftmaxBwdRow {
+  float g;        // d loss / d logp (0: masked-out token, the row becomes zeros)
+  float c;        // log2|g| - lse * log2e
+  int32_t tcol;   // target column within the slice, -1 if the target lives in another slice
+  int32_t pad;
 };
 
 // kAcc = 1: 256-column tiles, the two TMEM accumulator stages double-buffer the epilogue.
@@ -84,20 +99,77 @@ struct GemmShape {
   static constexpr int STAGES = (kNCta == 1) ? 4 : (kAcc == 1 ? 6 : 4);
   // K1 only: per epilogue warp 2 x [32 rows x 128 B] swizzled staging buffers for the TMA store of bf16 logits
   static constexpr int STAGING_BYTES = kStaging ? 4 * 2 * 4096 : 0;
-  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int BAR_BYTES = (4 * STAGES + 4) * 8 + 16;   // full, empty, afull, ready per stage + 4 accumulator barriers
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;   // +1024: manual alignment
   static constexpr int TMEM_COLS = 512;
 };
 
 constexpr int kGemmThreads = 256;
+constexpr int kGemmThreadsXform = 384;    // + warps 8..11: with warps 4..7 the eight transform warps of a kXform kernel
 constexpr float kLog2e = 1.4426950408889634f;
 
-template <bool kAMN, bool kBMN, int kNCta, int kEpi, int kAcc = 1>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// Half of one 128-byte row (32 of the 64 bf16 logits z of one token in a k-block; the row is 128B-swizzled: logical
+// 16-byte chunk j sits at j ^ sw) rewritten in place to P = g * (onehot - exp(z - lse)):
+//   P = -g * 2^(z * log2e - lse * log2e) = sgn(-g) * 2^(z * log2e + c),  c = log2|g| - lse * log2e
+// so that an element costs one FFMA and one MUFU.EX2; the sign is XORed into the packed bf16 pairs, g is added at the
+// target column `hot` (index within the row, -1 = not here).  A row with g == 0 (masked-out token) becomes zeros without
+// being read, columns >= nvalid (outside the vocabulary slice, TMA zero fill) become zeros.  The four 16-byte loads
+// are issued before any arithmetic (the volatile stores would otherwise serialise the chunks).
+__device__ __forceinline__ void xform_half(uint32_t rowbase, uint32_t sw, int half, float g, float c, int hot, int nvalid) {
+  const uint32_t j0 = (uint32_t)half * 4u;
+  if (g == 0.f || nvalid <= (int)j0 * 8) {
+#pragma unroll
+    for (uint32_t j = 0; j < 4; ++j) ptx::st_shared_v4(rowbase + (((j0 + j) ^ sw) << 4), 0u, 0u, 0u, 0u);
+    return;
+  }
+  const uint32_t sign = g > 0.f ? 0x80008000u : 0u;          // P has the sign of -g
+  uint32_t w[4][4];
+#pragma unroll
+  for (uint32_t j = 0; j < 4; ++j)
+    ptx::ld_shared_v4(rowbase + (((j0 + j) ^ sw) << 4), w[j][0], w[j][1], w[j][2], w[j][3]);
+#pragma unroll
+  for (uint32_t j = 0; j < 4; ++j) {
+    float f[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      f[2 * q] = ptx::ex2_approx(fmaf(__uint_as_float(w[j][q] << 16), kLog2e, c));
+      f[2 * q + 1] = ptx::ex2_approx(fmaf(__uint_as_float(w[j][q] & 0xffff0000u), kLog2e, c));
+    }
+    const int col = (int)(j0 + j) * 8;                 // first column of this chunk within the row
+    const bool fix = (hot >> 3) == (int)(j0 + j) || col + 8 > nvalid;
+    if (fix) {                                         // rare: target column (once per token per sweep) / ragged edge
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float v = g > 0.f ? -f[q] : f[q];
+        if (col + q == hot) v += g;
+        if (col + q >= nvalid) v = 0.f;
+        f[q] = v;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+      w[j][q] = *reinterpret_cast<uint32_t*>(&t) ^ (fix ? 0u : sign);
+    }
+  }
+#pragma unroll
+  for (uint32_t j = 0; j < 4; ++j)
+    ptx::st_shared_v4(rowbase + (((j0 + j) ^ sw) << 4), w[j][0], w[j][1], w[j][2], w[j][3]);
+}
+
+// kXform (256x512 pair tiles only): softmax-backward transform of the A tiles in shared memory, done by eight warps:
+// the four epilogue warps (idle during the main loop of a kAcc = 2 tile) and four more (warps 8..11; one warp per SM
+// sub-partition could not hide its own latencies: 2.6x slower than the MMAs it feeds).  The A tile lands on a
+// CTA-LOCAL barrier (`afull`), each thread rewrites half a row in place, makes the writes visible to the async proxy
+// and the warp arrives on the leader's `ready` barrier; the MMA issuer waits for `full` (B bytes of both CTAs) and
+// `ready` (A of both CTAs transformed).
+template <bool kAMN, bool kBMN, int kNCta, int kEpi, int kAcc = 1, bool kXform = false>
+__global__ void __launch_bounds__(kXform ? kGemmThreadsXform : kGemmThreads, 1)
 lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   using S = GemmShape<kNCta, kEpi == EPI_STATS, kAcc>;
   constexpr int BM = S::BM, BN = S::BN, BK = S::BK, STAGES = S::STAGES;
+  static_assert(!kXform || (kNCta == 2 && kAcc == 2 && kEpi != EPI_STATS), "the fused transform needs the idle epilogue warps of a 256x512 pair tile");
 
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need 1024-byte aligned bases (in the shared window, identical in both CTAs of a pair)
@@ -111,7 +183,9 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = bars + 2 * STAGES + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* afull = bars + 2 * STAGES + 4;
+  uint64_t* ready = bars + 3 * STAGES + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -127,6 +201,8 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     for (int i = 0; i < STAGES; ++i) {
       ptx::mbar_init(&full[i], kNCta);       // producer arrivals (leader's barrier collects both CTAs)
       ptx::mbar_init(&empty[i], 1);          // one tcgen05.commit
+      ptx::mbar_init(&afull[i], 1);          // kXform: this CTA's A tile has landed
+      ptx::mbar_init(&ready[i], kNCta * 8);  // kXform: one arrival per transform warp of each CTA
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull[i], 1);          // one tcgen05.commit
@@ -145,6 +221,54 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int worker = blockIdx.x / kNCta;
   const int num_items = p.num_m_blocks * p.num_n_groups;
   const int num_k_blocks = (int)((p.K + BK - 1) / BK);
+
+  // ---- kXform: softmax backward of one work tile's A operand, k-block by k-block, ahead of the MMAs (warps 4..11)
+  auto xform_tile = [&](int m_blk, int& xstage, uint32_t& xphase) {
+    const int xt = (int)threadIdx.x - 128;                                   // 0..255
+    const int half = xt >> 7;
+    auto load_row = [&](int64_t tok) -> int4 {                               // 16 bytes per token, L2 resident
+      return tok < p.x_tokens ? __ldg(p.x_rows + tok) : make_int4(0, 0, -1, 0);
+    };
+    auto publish = [&]() {
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) { if (rank == 0) ptx::mbar_arrive(&ready[xstage]); else ptx::mbar_arrive_cluster(&ready[xstage], 0); }
+      if (++xstage == STAGES) { xstage = 0; xphase ^= 1u; }
+    };
+    if constexpr (!kAMN) {
+      // K2a: A tile = [128 token rows][64 vocab columns], K-major: thread = (half, token row)
+      const int r = xt & 127;
+      const int4 rec = load_row((int64_t)m_blk * S::UMMA_M + (int64_t)rank * BM + r);
+      const float g = __int_as_float(rec.x), c = __int_as_float(rec.y);
+      const int64_t tcol = rec.z;
+      const uint32_t sw = (uint32_t)r & 7u;
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        ptx::mbar_wait(&afull[xstage], xphase);
+        const uint32_t rowbase = ptx::smem_u32(smem_a + xstage * S::A_BYTES) + (uint32_t)r * 128u;
+        const int64_t rel = tcol - (int64_t)kb * BK, left = p.K - (int64_t)kb * BK;
+        xform_half(rowbase, sw, half, g, c, (rel >= 0 && rel < BK) ? (int)rel : -1, left < BK ? (int)left : BK);
+        publish();
+      }
+    } else {
+      // K2b: A tile = 2 atoms of [64 token rows][64 vocab columns], MN-major: thread = (half, atom, token row)
+      const int xi = (xt >> 6) & 1, xk = xt & 63;
+      const int64_t col0 = (int64_t)m_blk * S::UMMA_M + (int64_t)rank * BM + 64 * xi;      // first vocab column of the atom
+      const int64_t left = p.M - col0;
+      const int nvalid = left < 64 ? (int)left : 64;
+      const uint32_t sw = (uint32_t)xk & 7u;
+      int4 r0 = load_row(xk), r1 = load_row((int64_t)BK + xk);               // rows of k-blocks 0 and 1
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        const float g0 = __int_as_float(r0.x), c0 = __int_as_float(r0.y);
+        const int64_t rel = (int64_t)r0.z - col0;
+        r0 = r1;
+        r1 = load_row((int64_t)(kb + 2) * BK + xk);                         // two k-blocks ahead: in flight meanwhile
+        ptx::mbar_wait(&afull[xstage], xphase);
+        const uint32_t rowbase = ptx::smem_u32(smem_a + xstage * S::A_BYTES) + (uint32_t)xi * (BK * 128) + (uint32_t)xk * 128u;
+        xform_half(rowbase, sw, half, g0, c0, (rel >= 0 && rel < 64) ? (int)rel : -1, nvalid);
+        publish();
+      }
+    }
+  };
 
   // The two single-instruction-stream roles run with the WHOLE warp converged and only the
   // TMA / tcgen05 instructions predicated on one elected lane: every operand is then provably
@@ -182,7 +306,11 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const int k0 = kb * BK;
             uint8_t* sa = smem_a + stage * S::A_BYTES;
             uint8_t* sb = smem_b + stage * S::B_BYTES;
-            if constexpr (kNCta == 1) {
+            if constexpr (kXform) {
+              ptx::mbar_expect_tx(&afull[stage], S::A_BYTES);                    // local: the transform warps wait here
+              if (rank == 0) ptx::mbar_expect_tx(&full[stage], 2 * S::B_BYTES);
+              else ptx::mbar_arrive_cluster(&full[stage], 0);
+            } else if constexpr (kNCta == 1) {
               ptx::mbar_expect_tx(&full[stage], S::STAGE_BYTES);
             } else {
               if (rank == 0) ptx::mbar_expect_tx(&full[stage], 2 * S::STAGE_BYTES);
@@ -198,7 +326,23 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 else ptx::tma_load_2d_2sm_hint(dst, tm, &full[stage], c0, c1, ptx::l2_policy(hint));
               }
             };
-            if constexpr (!kAMN) {
+            if (p.prefetch_a > 0 && kb + p.prefetch_a < num_k_blocks) {   // A streams from HBM: warm L2 ahead
+              const int kp = (kb + p.prefetch_a) * BK;
+              if constexpr (!kAMN) {
+                ptx::tma_prefetch_l2_2d(&tmA, kp, m0);
+              } else {
+#pragma unroll
+                for (int i = 0; i < BM / 64; ++i) ptx::tma_prefetch_l2_2d(&tmA, m0 + 64 * i, kp);
+              }
+            }
+            if constexpr (kXform) {                                     // plain (1-SM) TMA onto the local barrier
+              if constexpr (!kAMN) {
+                ptx::tma_load_2d(sa, &tmA, &afull[stage], k0, m0);
+              } else {
+#pragma unroll
+                for (int i = 0; i < BM / 64; ++i) ptx::tma_load_2d(sa + i * (BK * 128), &tmA, &afull[stage], m0 + 64 * i, k0);
+              }
+            } else if constexpr (!kAMN) {
               load(sa, &tmA, k0, m0);                                   // [128 rows][64 k] K-major
             } else {
 #pragma unroll
@@ -248,6 +392,7 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const uint32_t tmem_d = a * S::TILE_N;             // TMEM base is 0: this CTA owns all 512 columns
           for (int kb = 0; kb < num_k_blocks; ++kb) {
             ptx::mbar_wait(&full[stage], phase);             // TMA bytes have landed (both CTAs)
+            if constexpr (kXform) ptx::mbar_wait(&ready[stage], phase);   // ... and both A tiles are rewritten
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
               const uint64_t da = da0 + (uint64_t)((uint32_t)(stage * S::A_BYTES) >> 4);
@@ -273,6 +418,15 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         ptx::mbar_wait(&tempty[last % S::ACC_STAGES], (last / S::ACC_STAGES) & 1u);
       }
     }
+  } else if (kXform && warp >= 8) {
+    // ================================ extra transform warps ================================
+    int xstage = 0; uint32_t xphase = 0;
+    for (int item = worker; item < num_items; item += num_workers) {
+      const int n_grp = item_n(p, item), m_blk = item_m(p, item);
+      const int t_begin = n_grp * p.tiles_per_group;
+      const int t_end = min(t_begin + p.tiles_per_group, p.num_n_tiles);
+      for (int nt = t_begin; nt < t_end; ++nt) xform_tile(m_blk, xstage, xphase);
+    }
   } else if (warp >= 4) {
     // ================================ epilogue warps ================================
     const int q = warp & 3;                       // TMEM lane quadrant this warp may access
@@ -281,6 +435,7 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     uint32_t acc_iter = 0;
     const uint32_t stg_warp = ptx::smem_u32(staging) + (uint32_t)(warp - 4) * 8192u;   // this warp's 2 buffers
     uint32_t sbuf = 0;
+    int xstage = 0; uint32_t xphase = 0;          // kXform: position in the smem ring (same sequence as the producer)
     for (int item = worker; item < num_items; item += num_workers) {
       const int n_grp = item_n(p, item), m_blk = item_m(p, item);
       const int64_t row = (int64_t)m_blk * S::UMMA_M + (int64_t)rank * BM + row_in_tile;
@@ -297,6 +452,7 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
       for (int nt = t_begin; nt < t_end; ++nt, ++acc_iter) {
         const uint32_t a = acc_iter % S::ACC_STAGES, aphase = (acc_iter / S::ACC_STAGES) & 1u;
+        if constexpr (kXform) xform_tile(m_blk, xstage, xphase);
         ptx::mbar_wait(&tfull[a], aphase);
         ptx::tc_fence_after();
         const int64_t n0 = (int64_t)nt * S::TILE_N;

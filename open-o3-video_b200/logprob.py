@@ -137,23 +137,66 @@ def dlogits_(logits, lse, grad_logp, targets, v_offset=0, V=None):
     return logits
 
 
-def bwd_dhidden(dlogits, weight, out=None, fp32=False):
+# Softmax backward fused into the operand pipeline of the two backward GEMMs (o3v_lmhead_bwd_*_fused): the bf16
+# logits chunk is consumed as stored by K1 and never rewritten by an elementwise pass.  Measured on c2 (round 2,
+# profiles/r2_notes.md): correct but SLOWER under the 1 kW cap (every P element is re-exponentiated by each of the
+# 7 + 7 CTAs columns that sweep it: 350 ms per step against 316 ms), so the default stays the separate in-place pass
+# dlogits_ -> plain GEMMs.
+FUSE_DLOGITS = False
+
+
+def softmax_bwd_rows(lse, grad_logp, targets, v_offset, V):
+    """Per-token records of the fused softmax backward (o3v_lmhead_softmax_bwd_rows) -> opaque [T, 4] int32 tensor."""
+    T = lse.shape[0]
+    rows = torch.empty(T, 4, dtype=torch.int32, device=lse.device)
+    with torch.cuda.device(lse.device):
+        _lib.call("o3v_lmhead_softmax_bwd_rows", 1, _lib.load().o3v_lmhead_softmax_bwd_rows, _p(lse), _p(grad_logp),
+                  _p(targets), int(v_offset), int(V), T, _p(rows), _stream())
+    return rows
+
+
+def _rows_of(softmax_bwd, V):
+    """`softmax_bwd` is either the records themselves or (lse, grad_logp, targets, v_offset)."""
+    if isinstance(softmax_bwd, torch.Tensor):
+        return softmax_bwd
+    lse, g, tgt, v_off = softmax_bwd
+    return softmax_bwd_rows(lse.contiguous(), g.contiguous(), tgt.contiguous(), v_off, V)
+
+
+def bwd_dhidden(dlogits, weight, out=None, fp32=False, softmax_bwd=None):
+    """dH = P . W.  `softmax_bwd` = (lse, grad_logp, targets, v_offset) or the records `softmax_bwd_rows` made of
+    them: `dlogits` then holds the raw bf16 LOGITS and P is formed inside the GEMM's operand pipeline."""
     T, V = dlogits.shape
     H = weight.shape[1]
     if out is None:
         out = torch.empty(T, H, dtype=torch.float32 if fp32 else torch.bfloat16, device=dlogits.device)
+    lib = _lib.load()
     with torch.cuda.device(dlogits.device):
-        _lib.call("o3v_lmhead_bwd_dhidden", 1, _lib.load().o3v_lmhead_bwd_dhidden, _p(dlogits), dlogits.stride(0),
-                  _p(weight), T, V, H, _p(out), 1 if out.dtype == torch.float32 else 0, _stream())
+        if softmax_bwd is None:
+            _lib.call("o3v_lmhead_bwd_dhidden", 1, lib.o3v_lmhead_bwd_dhidden, _p(dlogits), dlogits.stride(0),
+                      _p(weight), T, V, H, _p(out), 1 if out.dtype == torch.float32 else 0, _stream())
+        else:
+            rows = _rows_of(softmax_bwd, V)
+            _lib.call("o3v_lmhead_bwd_dhidden_fused", 1, lib.o3v_lmhead_bwd_dhidden_fused, _p(dlogits),
+                      dlogits.stride(0), _p(rows), _p(weight), T, V, H, _p(out),
+                      1 if out.dtype == torch.float32 else 0, _stream())
     return out
 
 
-def bwd_dweight(dlogits, hidden, d_weight, accumulate):
+def bwd_dweight(dlogits, hidden, d_weight, accumulate, softmax_bwd=None):
+    """dW (+)= P^T . hidden; `softmax_bwd` as in bwd_dhidden."""
     T, V = dlogits.shape
     H = hidden.shape[1]
+    lib = _lib.load()
     with torch.cuda.device(dlogits.device):
-        _lib.call("o3v_lmhead_bwd_dweight", 1, _lib.load().o3v_lmhead_bwd_dweight, _p(dlogits), dlogits.stride(0),
-                  _p(hidden), T, V, H, _p(d_weight), 1 if accumulate else 0, _stream())
+        if softmax_bwd is None:
+            _lib.call("o3v_lmhead_bwd_dweight", 1, lib.o3v_lmhead_bwd_dweight, _p(dlogits), dlogits.stride(0),
+                      _p(hidden), T, V, H, _p(d_weight), 1 if accumulate else 0, _stream())
+        else:
+            rows = _rows_of(softmax_bwd, V)
+            _lib.call("o3v_lmhead_bwd_dweight_fused", 1, lib.o3v_lmhead_bwd_dweight_fused, _p(dlogits),
+                      dlogits.stride(0), _p(rows), _p(hidden), T, V, H, _p(d_weight),
+                      1 if accumulate else 0, _stream())
     return d_weight
 
 
@@ -191,9 +234,13 @@ class _FusedLogprobFn(torch.autograd.Function):
             else:                                   # recompute this chunk's logits (forward kept nothing)
                 z = zbuf[: e - s]
                 lmhead_stats(hidden[s:e], weight, targets[s:e], ctx.v_offset, z)
-            dlogits_(z, lse[s:e], g[s:e], targets[s:e], ctx.v_offset)
-            bwd_dhidden(z, weight, out=d_hidden[s:e])
-            bwd_dweight(z, hidden[s:e], d_weight, accumulate=not first)
+            sb = None
+            if FUSE_DLOGITS:
+                sb = softmax_bwd_rows(lse[s:e], g[s:e], targets[s:e], ctx.v_offset, V)
+            else:
+                dlogits_(z, lse[s:e], g[s:e], targets[s:e], ctx.v_offset)
+            bwd_dhidden(z, weight, out=d_hidden[s:e], softmax_bwd=sb)
+            bwd_dweight(z, hidden[s:e], d_weight, accumulate=not first, softmax_bwd=sb)
             first = False
         ctx.logits = None
         if ctx.group is not None:                   # partial sums over vocab slices
@@ -248,7 +295,8 @@ def fused_logprob_gspo(hidden: torch.Tensor, weight: torch.Tensor, completion_id
                        epsilon_low: float = 0.2, epsilon_high: float = 0.2, gspo: bool = True,
                        old_per_token_logps: Optional[torch.Tensor] = None, *, v_offset: int = 0, group=None,
                        chunk_tokens: int = DEFAULT_CHUNK_TOKENS, need_grad: bool = True,
-                       d_weight_out: Optional[torch.Tensor] = None, overlap_dlogits: bool = False):
+                       d_weight_out: Optional[torch.Tensor] = None, overlap_dlogits: bool = False,
+                       fuse_dlogits: Optional[bool] = None):
     """The whole policy-objective step in one call: per-token log-probs, KL, group advantages,
     GSPO loss AND the gradients w.r.t. hidden and lm_head.weight (grpo_trainer.py:612-613,
     635-636, 658-706 + their backward), chunked over whole sequences.
@@ -257,7 +305,11 @@ def fused_logprob_gspo(hidden: torch.Tensor, weight: torch.Tensor, completion_id
     token; completion_ids / ref / mask / old: [N, Tc]; rewards_per_func [N, F].
     Returns dict(loss, per_token_logps, advantages, mean_kl, completion_length, reward_std,
     d_hidden [N, Tc, H] bf16, d_weight [V, H] fp32).
+
+    Per chunk: K1 (+ bf16 logits store) -> merge -> K3 (loss, d loss / d logp) -> K2a, K2b with the softmax backward
+    fused into their operand pipelines (`fuse_dlogits`, default `FUSE_DLOGITS`; False = separate in-place dlogits pass).
     """
+    fuse = FUSE_DLOGITS if fuse_dlogits is None else bool(fuse_dlogits)
     N, Tc, H = hidden.shape
     V = weight.shape[0]
     dev = hidden.device
@@ -291,16 +343,16 @@ def fused_logprob_gspo(hidden: torch.Tensor, weight: torch.Tensor, completion_id
     # stream beside the tensor-bound K1 of chunk c+1 (its CTAs use no shared memory and co-reside with the
     # persistent GEMM CTAs), then the two backward GEMMs of chunk c follow on the main stream.  Needs a second
     # logits buffer.  Order of work on the device:  F0 | F1 + D0 | B0 | F2 + D1 | B1 | ... | D(n-1) | B(n-1).
-    pipelined = bool(need_grad and overlap_dlogits and n_chunks > 1)
+    pipelined = bool(need_grad and overlap_dlogits and n_chunks > 1 and not fuse)
     zbuf2 = torch.empty_like(zbuf) if pipelined else None
     main = torch.cuda.current_stream(dev)
     side = _side_stream(dev) if pipelined else None
 
-    def backward_gemms(ci, s, e, z):
-        bwd_dhidden(z, weight, out=d_hidden[s:e])
+    def backward_gemms(ci, s, e, z, sb=None):
+        bwd_dhidden(z, weight, out=d_hidden[s:e], softmax_bwd=sb)
         if peer_dh:
             group.allreduce_dh_async(s, e - s)                # runs beside the dW GEMM below
-        bwd_dweight(z, hidden2[s:e], d_weight, accumulate=(ci > 0) or (d_weight_out is not None))
+        bwd_dweight(z, hidden2[s:e], d_weight, accumulate=(ci > 0) or (d_weight_out is not None), softmax_bwd=sb)
 
     pending = None                                            # chunk whose backward GEMMs are still to be enqueued
     for ci, n0 in enumerate(range(0, N, seqs)):
@@ -315,6 +367,9 @@ def fused_logprob_gspo(hidden: torch.Tensor, weight: torch.Tensor, completion_id
                                epsilon_high, gspo, None if old is None else old[n0:n1], want_grad=need_grad,
                                want_kl=False, N_total=N, seq_offset=n0, state=state)
         if not need_grad:
+            continue
+        if fuse:
+            backward_gemms(ci, s, e, z, softmax_bwd_rows(lse, g.view(-1), targets[s:e], v_offset, V))
             continue
         if not pipelined:
             dlogits_(z, lse, g.view(-1), targets[s:e], v_offset)

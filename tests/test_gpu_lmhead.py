@@ -18,12 +18,14 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(params=[1, 2], ids=["cta1", "cta2"])
 def cta_pair(request):
-    from open_o3_video_b200 import _lib
+    from open_o3_video_b200 import _lib, logprob
     _lib.set_tunable("cta_pair", request.param)
+    logprob.FUSE_DLOGITS = request.param == 2      # cta2 runs also exercise the fused softmax backward (pair tiles only)
     yield request.param
     _lib.set_tunable("cta_pair_fwd", 1)
     _lib.set_tunable("cta_pair_bwd", 2)
     _lib.set_tunable("fwd_groups", 0)
+    logprob.FUSE_DLOGITS = False
 
 
 def _rel(a, b, floor=2e-5):
@@ -170,3 +172,69 @@ def test_autograd_function_backward(cta_pair, T, H, V):
             assert err < 1e-2, err
             assert (got.float().cpu() - ref).abs().max() < 3e-2 * ref.abs().max()
     logprob.SAVE_LOGITS_BYTES = 24 << 30
+
+
+FUSED_CASES = [(128, 64, 256, 0), (300, 192, 1000, 0), (1100, 512, 5000, 0), (777, 1024, 9496, 0), (640, 256, 2376, 4752),
+               (2900, 1792, 9496, 9496)]
+
+
+@pytest.mark.parametrize("T,H,V,v_off", FUSED_CASES)
+def test_fused_softmax_backward_gemms(T, H, V, v_off):
+    """o3v_lmhead_bwd_{dhidden,dweight}_fused: the softmax backward applied to the A tiles in shared memory.
+    Against (a) torch fp32 from the exact formula and (b) the separate in-place dlogits pass + plain GEMMs;
+    ragged shapes, a vocab slice (v_off > 0: targets outside the slice get no one-hot), zero-gradient rows."""
+    from open_o3_video_b200 import _lib, logprob
+    g0 = torch.Generator().manual_seed(T + V)
+    z = (torch.randn(T, V, generator=g0) * 1.5).bfloat16().cuda()
+    W = (torch.randn(V, H, generator=g0) * 0.02).bfloat16().cuda()
+    Hd = torch.randn(T, H, generator=g0).bfloat16().cuda()
+    targets = torch.randint(0, V + 2 * v_off, (T,), generator=g0).cuda()          # global ids, some outside the slice
+    grad = (torch.randn(T, generator=g0) * 0.01).cuda()
+    grad[torch.rand(T, generator=g0) < 0.3] = 0.0
+    grad[T // 2:T // 2 + 40] = 0.0                                               # a whole warp of masked rows
+    lse = torch.logsumexp(z.float(), -1) + 0.3                                   # as if other slices held mass too
+    torch.backends.cuda.matmul.allow_tf32 = False
+    col = targets - v_off
+    onehot = torch.zeros(T, V, device="cuda")
+    inside = (col >= 0) & (col < V)
+    onehot[inside.nonzero()[:, 0], col[inside]] = 1.0
+    P = grad[:, None] * (onehot - torch.exp(z.float() - lse[:, None]))
+    dH_ref, dW_ref = P @ W.float(), P.T @ Hd.float()
+    sb = (lse, grad, targets, v_off)
+    t = _lib.Trace()
+    _lib.trace = t
+    try:
+        dH = logprob.bwd_dhidden(z, W, fp32=True, softmax_bwd=sb)
+        dW = torch.full((V, H), float("nan"), device="cuda")
+        logprob.bwd_dweight(z, Hd, dW, accumulate=False, softmax_bwd=sb)
+    finally:
+        _lib.trace = None
+    assert [n for n, _ in t.calls] == ["o3v_lmhead_softmax_bwd_rows", "o3v_lmhead_bwd_dhidden_fused", "o3v_lmhead_softmax_bwd_rows", "o3v_lmhead_bwd_dweight_fused"]
+    # (a) P is rounded to bf16 before the MMAs, as on the unfused path: 2^-9 relative per element
+    assert (dH - dH_ref).norm() <= 4e-3 * dH_ref.norm() and (dW - dW_ref).norm() <= 4e-3 * dW_ref.norm()
+    assert (dH[grad == 0] == 0).all()
+    # (b) the separate pass (exp2f instead of ex2.approx: at most one bf16 ulp apart on a few elements)
+    z2 = z.clone()
+    logprob.dlogits_(z2, lse, grad, targets, v_off)
+    dH2 = logprob.bwd_dhidden(z2, W, fp32=True)
+    dW2 = torch.empty(V, H, device="cuda")
+    logprob.bwd_dweight(z2, Hd, dW2, accumulate=False)
+    assert (dH - dH2).norm() <= 1e-3 * dH2.norm() and (dW - dW2).norm() <= 1e-3 * dW2.norm()
+    # accumulate, and the logits buffer is left untouched
+    logprob.bwd_dweight(z, Hd, dW, accumulate=True, softmax_bwd=sb)
+    assert (dW - 2 * dW_ref).norm() <= 4e-3 * (2 * dW_ref).norm()
+    assert torch.equal(z, (torch.randn(T, V, generator=torch.Generator().manual_seed(T + V)) * 1.5).bfloat16().cuda())
+
+
+def test_fused_softmax_backward_needs_the_default_tile_mode():
+    from open_o3_video_b200 import _lib, logprob
+    z = torch.zeros(128, 256, dtype=torch.bfloat16, device="cuda")
+    W = torch.zeros(256, 64, dtype=torch.bfloat16, device="cuda")
+    sb = (torch.zeros(128, device="cuda"), torch.zeros(128, device="cuda"), torch.zeros(128, dtype=torch.int64, device="cuda"), 0)
+    _lib.set_tunable("cta_pair_bwd", 1)
+    try:
+        with pytest.raises(_lib.O3VError) as e:
+            logprob.bwd_dhidden(z, W, softmax_bwd=sb)
+        assert e.value.code == -7
+    finally:
+        _lib.set_tunable("cta_pair_bwd", 2)

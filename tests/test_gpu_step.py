@@ -46,7 +46,8 @@ def test_fused_step_matches_oracle(N, Tc, G, H, V, chunk, off_policy, cta):
         exp, lp_ref, dH_ref, dW_ref = _oracle_step(hidden, weight, ids, ref, mask, rpf, G, 0.04, old)
         cu = lambda t: None if t is None else t.cuda()
         out = logprob.fused_logprob_gspo(hidden.cuda().bfloat16(), weight.cuda().bfloat16(), ids.cuda(), cu(ref),
-                                         cu(mask), cu(rpf), G, 0.04, 0.2, 0.2, True, cu(old), chunk_tokens=chunk)
+                                         cu(mask), cu(rpf), G, 0.04, 0.2, 0.2, True, cu(old), chunk_tokens=chunk,
+                                         fuse_dlogits=(cta == 2 and off_policy))   # both backward variants (fused: pair tiles only)
         torch.cuda.synchronize()
     finally:
         _lib.set_tunable("cta_pair_fwd", 1)
@@ -76,12 +77,37 @@ def test_pipelined_dlogits_is_bit_identical(N, Tc, chunk):
     hidden, weight, ids, ref, mask, rpf, old = _inputs(N, Tc, G, 256, 5000, True, seed=5)
     args = (hidden.cuda().bfloat16(), weight.cuda().bfloat16(), ids.cuda(), ref.cuda(), mask.cuda(), rpf.cuda(), G, 0.04,
             0.2, 0.2, True, old.cuda())
-    a = logprob.fused_logprob_gspo(*args, chunk_tokens=chunk, overlap_dlogits=False)
+    a = logprob.fused_logprob_gspo(*args, chunk_tokens=chunk, overlap_dlogits=False, fuse_dlogits=False)
     for _ in range(3):                                        # repeated: buffer reuse across steps and streams
-        b = logprob.fused_logprob_gspo(*args, chunk_tokens=chunk, overlap_dlogits=True)
+        b = logprob.fused_logprob_gspo(*args, chunk_tokens=chunk, overlap_dlogits=True, fuse_dlogits=False)
     torch.cuda.synchronize()
     for k in ("loss", "per_token_logps", "advantages", "mean_kl", "d_hidden", "d_weight"):
         assert torch.equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("N,Tc,chunk", [(8, 64, 128), (9, 100, 300)])
+def test_fused_and_separate_softmax_backward_agree(N, Tc, chunk):
+    """The whole step with the softmax backward inside the GEMMs (default) vs the separate dlogits pass: forward
+    outputs bit-identical, gradients equal up to bf16 rounding of P (ex2.approx vs exp2f)."""
+    from open_o3_video_b200 import _lib, logprob
+    G = 3 if N == 9 else 2
+    hidden, weight, ids, ref, mask, rpf, old = _inputs(N, Tc, G, 256, 5000, True, seed=6)
+    args = (hidden.cuda().bfloat16(), weight.cuda().bfloat16(), ids.cuda(), ref.cuda(), mask.cuda(), rpf.cuda(), G, 0.04,
+            0.2, 0.2, True, old.cuda())
+    t = _lib.Trace()
+    _lib.trace = t
+    try:
+        a = logprob.fused_logprob_gspo(*args, chunk_tokens=chunk, fuse_dlogits=True)
+    finally:
+        _lib.trace = None
+    assert not any(n == "o3v_lmhead_dlogits" for n, _ in t.calls)     # no elementwise pass over the logits chunk
+    b = logprob.fused_logprob_gspo(*args, chunk_tokens=chunk, fuse_dlogits=False)
+    for k in ("loss", "per_token_logps", "advantages", "mean_kl"):
+        assert torch.equal(a[k], b[k]), k
+    for k in ("d_hidden", "d_weight"):
+        x, y = a[k].float(), b[k].float()
+        assert (x - y).norm() <= 2e-3 * y.norm(), k
+    assert (a["d_hidden"][mask.cuda() == 0] == 0).all()
 
 
 def test_c1_shape_known_answer():
