@@ -90,8 +90,9 @@ class ClockSampler:
         sm = sorted(int(r[0]) for r in rows)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for j, n in enumerate(names) if any(r[3 + j].lower().startswith("active") for r in rows)]
+        pw = sorted(float(r[2]) for r in rows)
         return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=int(rows[0][1]), reasons=reasons, samples=len(rows),
-                    power_w_max=max(float(r[2]) for r in rows))
+                    power_w_max=pw[-1], power_w_median=pw[len(pw) // 2])
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
@@ -148,6 +149,91 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------- self-check (outside the timed regions)
+def parity_check(out, hidden, ids, ref, mask, rpf, G, H, V, Tc, weight, v_off, rank, world, dev):
+    """The step that was just timed against plain torch fp32 formulas (no library code, no oracle import) on a
+    subset: log-probs of the first and the last sequence against a full-vocabulary fp32 recompute (the weight slices
+    are all-gathered for it), the loss and d loss / d logp against an autograd restatement of grpo_trainer.py:635-706
+    fed with the library's log-probs, dHidden of the first sequence (rank 0 owns those rows in either collective
+    mode) and 256 columns of rank 0's dW slice.  Every entry is error / tolerance (tolerances of DESIGN.md section 6:
+    1e-3 relative for log-probs and loss, 1e-2 in norm for the gradients)."""
+    import torch.distributed as dist
+    N = hidden.shape[0]
+    torch.backends.cuda.matmul.allow_tf32 = False
+    if world > 1:
+        sizes = [0] * world
+        dist.all_gather_object(sizes, int(weight.shape[0]))
+        parts = [torch.empty(n, H, dtype=weight.dtype, device=dev) for n in sizes]
+        dist.all_gather(parts, weight.contiguous())
+        w_full = torch.cat(parts, 0)
+        del parts
+    else:
+        w_full = weight
+    lp = out["per_token_logps"]
+    res = {}
+    if rank == 0:
+        wf = w_full.float()
+        z_keep = None
+        errs = []
+        for n in (0, N - 1):
+            z = hidden[n].float() @ wf.T                                                  # [Tc, V] fp32
+            lse = torch.logsumexp(z, -1)
+            lp_ref = z.gather(1, ids[n][:, None])[:, 0] - lse
+            errs.append(((lp[n] - lp_ref).abs() / lp_ref.abs().clamp(min=1e-6)).max().item())
+            if n == 0:
+                z_keep, lse0 = z, lse
+        res["logp_max_rel"] = max(errs)
+        # loss + gradient w.r.t. the log-probs: autograd through the reference's formulas (on-policy: old = detach)
+        x = lp.detach().clone().requires_grad_(True)
+        m = mask.float()
+        r = rpf.sum(1)
+        mean_g = r.view(-1, G).mean(1).repeat_interleave(G)
+        std_g = r.view(-1, G).std(1).repeat_interleave(G)
+        adv = (r - mean_g) / (std_g + 1e-4)
+        xc = torch.clamp(ref - x, -10, 10)
+        kl = torch.exp(xc) - xc - 1
+        lr = x - x.detach()
+        c1 = torch.exp((lr * m).sum(-1) / m.sum(-1).clamp(min=1.0)).unsqueeze(-1)
+        c2 = torch.clamp(c1, 1 - EPS, 1 + EPS)
+        ptl = -torch.min(c1 * adv.unsqueeze(1), c2 * adv.unsqueeze(1)) + BETA * kl
+        loss = ((ptl * m).sum(-1) / m.sum(-1).clamp(min=1.0)).mean()
+        loss.backward()
+        res["loss_rel"] = abs(out["loss"].item() - loss.item()) / max(abs(loss.item()), 1e-12)
+        g0 = x.grad[0]                                                                   # [Tc]
+        P0 = torch.exp(z_keep - lse0[:, None]).mul_(-g0[:, None])
+        P0[torch.arange(Tc, device=dev), ids[0]] += g0
+        dh_ref = P0 @ wf
+        dh = out["d_hidden"].reshape(-1, H)[:Tc].float()                                  # rows 0..Tc: owned by rank 0
+        res["dh_rel_first_seq"] = ((dh - dh_ref).norm() / dh_ref.norm().clamp(min=1e-30)).item()
+        del P0, z_keep
+        # dW: 256 columns of rank 0's slice need P[:, cols] of ALL tokens: z[:, cols] and lse from the library's own
+        # log-probs are not available, so recompute lse by chunks over the full vocabulary
+        cols = torch.arange(v_off + 1024, v_off + 1280, device=dev)
+        gall = x.grad.view(-1)
+        hs = hidden.view(-1, H)
+        dW_ref = torch.zeros(256, H, device=dev)
+        T = hs.shape[0]
+        for s in range(0, T, 4096):
+            e = min(T, s + 4096)
+            if not bool((gall[s:e] != 0).any()):
+                continue
+            zc = hs[s:e].float() @ wf.T
+            lsec = torch.logsumexp(zc, -1)
+            Pc = torch.exp(zc[:, cols] - lsec[:, None]).mul_(-gall[s:e, None])
+            hit = (ids.view(-1)[s:e, None] == cols[None, :])
+            Pc += hit.float() * gall[s:e, None]
+            dW_ref += Pc.T @ hs[s:e].float()
+            del zc
+        dw = out["d_weight"][1024:1280]
+        res["dw_rel_256_cols"] = ((dw - dW_ref).norm() / dW_ref.norm().clamp(min=1e-30)).item()
+        res["max_err_over_tol"] = max(res["logp_max_rel"] / 1e-3, res["loss_rel"] / 1e-3, res["dh_rel_first_seq"] / 1e-2,
+                                      res["dw_rel_256_cols"] / 1e-2)
+        res["reference"] = "torch fp32 on the GPU from the formulas of grpo_trainer.py:371-384, 635-706 (no library code)"
+    if world > 1:
+        dist.barrier()
+    return res
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def run_ours(args):
     import torch.distributed as dist
@@ -185,7 +271,8 @@ def run_ours(args):
     _, mask = gspo.eos_mask(ids, eos_id)
     weight, v_off = sharded.shard_weight(w_full, rank, world)
     if world > 1 and args.exchange == "peer":
-        group = sharded.PeerExchange(dist.group.WORLD, capacity_tokens=T, hidden_size=H if args.overlap_allreduce else 0)
+        group = sharded.PeerExchange(dist.group.WORLD, capacity_tokens=T, hidden_size=H if args.overlap_allreduce else 0,
+                                     dh_mode=args.dh_collective)
     if not args.chunk_tokens:
         per_seq = max(1, min(N, logprob.auto_chunk_tokens(weight.shape[0]) // Tc))
         args.chunk_tokens = -(-N // (-(-N // per_seq))) * Tc      # evened out over whole sequences
@@ -201,7 +288,8 @@ def run_ours(args):
         return logprob.fused_logprob_gspo(h, weight, i, r, m, rw, G, BETA, EPS, EPS, True, None, v_offset=v_off,
                                           group=group, chunk_tokens=args.chunk_tokens, d_weight_out=None,
                                           overlap_dlogits=bool(args.overlap_dlogits),
-                                          fuse_dlogits=bool(args.fuse_dlogits))
+                                          **({"backward": "exp"} if args.backward == "exp" else
+                                             {"fuse_dlogits": args.backward == "smem"}))
 
     def barrier():
         if world > 1:
@@ -253,53 +341,38 @@ def run_ours(args):
     staging = [[torch.empty_like(t, device=dev) for t in full] for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
+    # Gather of the per-rank slices.  "p2p": `sharded.PeerGather`, every rank PUSHES its slice into all peers'
+    # peer-mapped buffers with copy-engine transfers over NVLink, so no SM is taken from the persistent GEMM kernels
+    # of the step that is running; "nccl": all-gather kernels (fallback).
     even = (N % world == 0)
-    # Gather of the per-rank slices.  "p2p": the staging buffers live in symmetric (peer-mapped) memory and every
-    # rank PUSHES its slice into all peers' buffers with copy-engine transfers over NVLink, so no SM is taken from
-    # the persistent GEMM kernels of the step that is running; "nccl": all-gather kernels (fallback).
-    gather, peer_views, handles = "nccl" if world > 1 else "none", None, None
+    gather, pgather = "nccl" if world > 1 else "none", None
     if world > 1 and args.e2e_gather == "p2p":
         try:
-            import torch.distributed._symmetric_memory as symm
-            st2, peer_views, handles = [], [], []
-            for _slot in range(2):
-                bufs, views, hs = [], [], []
-                for t in full:
-                    b = symm.empty(tuple(t.shape), dtype=t.dtype, device=dev)
-                    h = symm.rendezvous(b, pg)
-                    bufs.append(b)
-                    hs.append(h)
-                    views.append([h.get_buffer(r_, tuple(t.shape), t.dtype) for r_ in range(world)])
-                st2.append(bufs)
-                peer_views.append(views)
-                handles.append(hs)
-            staging, gather = st2, "p2p"
+            pgather = sharded.PeerGather(pg, [(tuple(t.shape), t.dtype) for t in full], device=dev, slots=2)
+            staging, gather = pgather.bufs, "p2p"
         except Exception as exc:                              # keep the bench alive on a box without P2P
             if rank == 0:
                 print("e2e gather: symmetric memory unavailable (%s), using NCCL all-gather" % exc, file=sys.stderr)
-            peer_views = handles = None
+            pgather = None
 
     def prefetch(slot):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[slot])          # the step that last used this slot is done
             if gather == "p2p":
-                # every peer must be done with this slot as well before anyone overwrites it
-                handles[slot][0].barrier(channel=4 + slot)
-            for d, h in zip(staging[slot], host):
-                d[seq_lo:seq_hi].copy_(h, non_blocking=True)
-            if gather == "p2p":
-                for ti, d in enumerate(staging[slot]):
-                    for r_ in range(world):
-                        if r_ != rank:
-                            peer_views[slot][ti][r_][seq_lo:seq_hi].copy_(d[seq_lo:seq_hi], non_blocking=True)
-                handles[slot][0].barrier(channel=6 + slot)  # all pushes into my buffers have landed
-            elif world > 1:
-                for d in staging[slot]:
-                    if even:
-                        dist.all_gather_into_tensor(d, d[seq_lo:seq_hi], group=pg)
-                    else:
-                        parts = [d[r * N // world:(r + 1) * N // world] for r in range(world)]
-                        dist.all_gather(parts, d[seq_lo:seq_hi], group=pg)
+                dev_local = [d[seq_lo:seq_hi] for d in staging[slot]]
+                for d, h in zip(dev_local, host):            # H2D of this rank's sequences (PCIe), in place in my buffer
+                    d.copy_(h, non_blocking=True)
+                pgather.gather(slot, dev_local, seq_lo)     # ... then pushed to every peer over NVLink
+            else:
+                for d, h in zip(staging[slot], host):
+                    d[seq_lo:seq_hi].copy_(h, non_blocking=True)
+                if world > 1:
+                    for d in staging[slot]:
+                        if even:
+                            dist.all_gather_into_tensor(d, d[seq_lo:seq_hi], group=pg)
+                        else:
+                            parts = [d[r * N // world:(r + 1) * N // world] for r in range(world)]
+                            dist.all_gather(parts, d[seq_lo:seq_hi], group=pg)
             ready[slot].record(copy_stream)
 
     def e2e_run(n):
@@ -324,6 +397,7 @@ def run_ours(args):
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
 
+    parity = parity_check(out, hidden, ids, ref, mask, rpf, G, H, V, Tc, weight, v_off, rank, world, dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -358,7 +432,8 @@ def run_ours(args):
                              "fused logprob+GSPO fwd+bwd" % (args.config, cfg["head"], H, V, cfg["prompts"], G, Tc, T),
                     parallelism="vocab-sharded x%d (%s exchange of softmax triples, %s of dHidden)"
                                 % (world, "fused NVLink peer-memory" if args.exchange == "peer" else "NCCL all-gather",
-                                   "one-shot P2P all-reduce beside the dW GEMM"
+                                   ("reduce-scatter fused into the K2a epilogue (NVLink stores to the token owners) + local slot sum"
+                                    if args.dh_collective == "reduce_scatter" else "one-shot P2P all-reduce beside the dW GEMM")
                                    if (args.exchange == "peer" and args.overlap_allreduce) else "NCCL all-reduce")
                     if world > 1 else "single GPU", chunk_tokens=args.chunk_tokens,
                     cache="inputs (%.1f GB) and per-chunk logits are far larger than the 126 MB L2; no flush needed"
@@ -372,7 +447,7 @@ def run_ours(args):
         kernel_ms_per_step=shares,
         e2e=dict(value=T / (ms_e2e * 1e-3), unit="tokens/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                  ms_per_step=ms_e2e, gather=gather),
-        gpu_launches=launches, clocks=clocks)
+        gpu_launches=launches, clocks=clocks, parity=parity, parity_max_err=parity["max_err_over_tol"])
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"], _ = cpu_reference(1, 0, cfg)
     print(json.dumps(line), flush=True)
@@ -387,9 +462,10 @@ def main():
                     help="N > 1, end-to-end arm: how the per-rank input slices reach every rank")
     ap.add_argument("--overlap-dlogits", type=int, default=0,
                     help="1: run the dlogits pass of chunk c on a side stream beside K1 of chunk c+1")
-    ap.add_argument("--fuse-dlogits", type=int, default=0,
-                    help="1: softmax backward inside the operand pipeline of the backward GEMMs (shared-memory "
-                         "transform); 0: separate in-place dlogits pass (default: faster under the power cap)")
+    ap.add_argument("--backward", default="exp", choices=["exp", "dlogits", "smem"],
+                    help="exp: K1 stores exp(z - ref), softmax backward folded into the GEMM epilogue / operands "
+                         "(default); dlogits: separate in-place elementwise pass (round 1); smem: shared-memory "
+                         "transform of the A tiles inside the GEMMs")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -401,6 +477,9 @@ def main():
                     help="N > 1: forward exchange of the softmax triples (peer = fused NVLink merge kernel)")
     ap.add_argument("--overlap-allreduce", type=int, default=1,
                     help="N > 1 with --exchange peer: one-shot P2P all-reduce of dHidden beside the dW GEMM (0 = NCCL)")
+    ap.add_argument("--dh-collective", default="reduce_scatter", choices=["reduce_scatter", "all_reduce"],
+                    help="N > 1: every rank gets ITS token rows of dHidden (data-parallel layout, SURVEY 8e; the K2a "
+                         "epilogue stores tiles at their owners) or the full dHidden (one-shot P2P all-reduce)")
     ap.add_argument("--tunable", action="append", default=[], help="name=value for o3v_set_tunable (diagnostics)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

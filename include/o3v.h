@@ -54,6 +54,10 @@ int o3v_check_device(void);
  *   "hint_fwd_a" / "hint_fwd_b" / "hint_fwd_store" / "hint_bwd_a" / "hint_bwd_b"  L2 eviction hint of the TMA
  *                loads of operand A / B and of the logits store (0 = none, 1 = evict first, 2 = evict last) */
 int o3v_set_tunable(const char* name, int value);
+/* Test helper: num_ctas CTAs holding smem_bytes of shared memory each spin for `clocks` SM clocks on `stream` (occupies
+ * SMs beside a persistent GEMM launched on another stream). */
+int o3v_debug_occupy_sms(int32_t num_ctas, int32_t smem_bytes, int64_t clocks, void* stream);
+
 /* Diagnostic: the tcgen05 GEMM template on an arbitrary problem, D[M,N] (+)= A . B^T with
  * bf16 operands.  a_mn / b_mn = 0: operand stored [rows, K] (K contiguous, "K-major");
  * = 1: stored [K, rows] (rows contiguous, "MN-major").  out: bf16 or fp32 [M, ld_out]. */
@@ -134,6 +138,54 @@ int o3v_lmhead_bwd_dhidden(const void* dlogits, int64_t ld_dlogits, const void* 
 int o3v_lmhead_bwd_dweight(const void* dlogits, int64_t ld_dlogits, const void* hidden,
                            int64_t T, int64_t V, int64_t H,
                            float* d_weight, int32_t accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Exp-store backward (default path of round 2): no elementwise pass over the [T, V] chunk at all.
+ *
+ * o3v_lmhead_fwd_exp is o3v_lmhead_fwd (identical statistics, bit for bit) except that what it stores is
+ *     E[t, v] = exp(z[t, v] - row_ref[t])   (bf16; rows with row_keep[t] == 0 store zeros, row_keep may be NULL)
+ * with a per-row reference row_ref[t] chosen BEFORE the sweep (any value within ~80 of the row maximum: the wrapper
+ * takes the maximum over a strided sample of 256 vocabulary rows, computed with this same kernel, plus 16).  Then
+ * softmax[t, v] = E[t, v] * exp(row_ref[t] - lse[t]) is a PER-ROW rescale of E, and by linearity
+ *     dH[t, :]  = a_t * (E . W)[t, :] + g_t * W[tcol_t, :]            a_t = -g_t * exp(row_ref[t] - lse[t])
+ *     dW[v, :]  = (E^T . (a * hidden))[v, :] + sum_{t: tcol_t = v} g_t * hidden[t, :]
+ * so both backward GEMMs read E as stored: the rescale and the one-hot term live in the K2a epilogue
+ * (o3v_lmhead_bwd_dhidden_exp, optionally storing at the token owners as o3v_lmhead_bwd_dhidden_scatter does when
+ * slot_ptrs != NULL), in a [T, H] pre-scale of the hidden states and in a deterministic scatter of T rows
+ * (o3v_lmhead_bwd_dweight_exp: three launches).  Storing exp(z - ref) in bf16 is also MORE accurate than storing z
+ * (relative error 2^-9 instead of |z| * 2^-9).
+ *   rows       [T] 16-byte records from o3v_lmhead_softmax_rows (g, a, target column in the slice); sort_key [T]
+ *              int64 (optional out): the caller sorts the tokens by it (stable) and passes the permutation as
+ *   order      [T] int64, which makes the one-hot scatter deterministic (sequential fp32 sum per dW row)
+ *   scaled_hidden  workspace, T * H bf16, 16-byte aligned
+ * ---------------------------------------------------------------------------------- */
+int o3v_lmhead_fwd_exp(const void* hidden, const void* weight, const int64_t* targets,
+                       int64_t T, int64_t V, int64_t H, int64_t v_offset,
+                       float* stats, void* expz, int64_t ld_expz, const float* row_ref, const int32_t* row_keep,
+                       void* workspace, size_t workspace_bytes, void* stream);
+int o3v_lmhead_softmax_rows(const float* lse, const float* grad_logp, const int64_t* targets, const float* row_ref,
+                            int64_t v_offset, int64_t V, int64_t T, void* rows, int64_t* sort_key, void* stream);
+int o3v_lmhead_bwd_dhidden_exp(const void* expz, int64_t ld_expz, const void* rows, const void* weight,
+                               int64_t T, int64_t V, int64_t H, void* d_hidden, int32_t out_is_fp32,
+                               void* const* slot_ptrs, int64_t P, int64_t rank, int64_t rows_per_owner,
+                               int64_t slot_rows, int64_t row0, void* stream);
+int o3v_lmhead_bwd_dweight_exp(const void* expz, int64_t ld_expz, const void* rows, const int64_t* order,
+                               const void* hidden, int64_t T, int64_t V, int64_t H, float* d_weight,
+                               int32_t accumulate, void* scaled_hidden, void* stream);
+
+/* K2a fused with the reduce-scatter of the vocab-parallel path (dHidden partial sums go back to the token
+ * owners).  Rank `rank` of P holds a vocabulary slice and computes partial dH for ALL token rows; row r of this call
+ * is global token row0 + r, owned by rank (row0 + r) / rows_per_owner.  The epilogue stores every bf16 output tile
+ * straight into the OWNER's slot buffer over NVLink (peer-mapped memory), slot `rank`:
+ *     slot_ptrs[owner] + ((rank * slot_rows + (row0 + r) - owner * rows_per_owner) * H + h) * 2 bytes
+ * so the transfer overlaps the GEMM tile by tile and no collective kernel runs beside it.  slot_ptrs: HOST array of
+ * the P ranks' slot buffers [P, slot_rows, H] bf16.  After a cross-rank barrier (all K2a done) each owner sums its P
+ * slots in rank order with o3v_sum_slots_bf16 (fp32 accumulate, deterministic, local HBM only). */
+int o3v_lmhead_bwd_dhidden_scatter(const void* dlogits, int64_t ld_dlogits, const void* weight,
+                                   int64_t T, int64_t V, int64_t H, void* const* slot_ptrs, int64_t P, int64_t rank,
+                                   int64_t rows_per_owner, int64_t slot_rows, int64_t row0, void* stream);
+int o3v_sum_slots_bf16(const void* slots, int64_t P, int64_t slot_rows, int64_t rows, int64_t H, void* out,
+                       int32_t num_ctas, void* stream);
 
 /* The same two GEMMs with the softmax backward FUSED into their operand pipeline: `logits` is the bf16 logits chunk
  * exactly as o3v_lmhead_fwd stored it (it is NOT modified), and every A tile is rewritten to P in shared memory

@@ -44,6 +44,7 @@ SIGNATURES = {
     "o3v_strerror": (c_char_p, [c_int]),
     "o3v_check_device": (c_int, []),
     "o3v_set_tunable": (c_int, [c_char_p, c_int]),
+    "o3v_debug_occupy_sms": (c_int, [c_int32, c_int32, c_int64, c_void_p]),
     "o3v_debug_gemm": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_int32,
                                c_void_p, c_int64, c_int32, c_int32, c_void_p]),
     "o3v_eos_mask": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
@@ -59,6 +60,17 @@ SIGNATURES = {
                                        c_void_p, c_int32, c_void_p]),
     "o3v_lmhead_bwd_dweight": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64,
                                        c_void_p, c_int32, c_void_p]),
+    "o3v_lmhead_fwd_exp": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
+                                   c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "o3v_lmhead_softmax_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p,
+                                        c_void_p, c_void_p]),
+    "o3v_lmhead_bwd_dhidden_exp": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p,
+                                           c_int32, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    "o3v_lmhead_bwd_dweight_exp": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                           c_void_p, c_int32, c_void_p, c_void_p]),
+    "o3v_lmhead_bwd_dhidden_scatter": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64,
+                                               c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    "o3v_sum_slots_bf16": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int32, c_void_p]),
     "o3v_lmhead_softmax_bwd_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "o3v_lmhead_bwd_dhidden_fused": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                              c_void_p, c_int32, c_void_p]),

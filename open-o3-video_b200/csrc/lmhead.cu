@@ -68,16 +68,25 @@ static int make_tmap_bf16(CUtensorMap* tm, const void* base, int64_t inner, int6
 // different streams do not share a counter.
 // ------------------------------------------------------------------------------------
 constexpr int kSyncSlots = 64;
-__device__ unsigned int g_wave_sync[kSyncSlots];
+__device__ unsigned int g_wave_sync[kSyncSlots][2];     // {arrivals, abandoned}
 
 static int acquire_wave_sync(unsigned int** out, cudaStream_t st) {
   static std::atomic<unsigned int> next{0};
   unsigned int* base = nullptr;
   O3V_CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_wave_sync));
-  unsigned int* slot = base + (next.fetch_add(1) % kSyncSlots);
-  O3V_CUDA_TRY(cudaMemsetAsync(slot, 0, sizeof(unsigned int), st));
+  unsigned int* slot = base + 2 * (next.fetch_add(1) % kSyncSlots);
+  O3V_CUDA_TRY(cudaMemsetAsync(slot, 0, 2 * sizeof(unsigned int), st));
   *out = slot;
   return O3V_OK;
+}
+
+// Test helper: `num_ctas` CTAs that each hold `smem_bytes` of shared memory and spin for `clocks` SM clocks, to occupy
+// SMs beside a persistent GEMM on another stream (tests/test_gpu_configs.py: the wave rendezvous must degrade, not trap).
+__global__ void occupy_sms_kernel(long long clocks) {
+  extern __shared__ uint8_t occupy_smem[];
+  occupy_smem[threadIdx.x] = (uint8_t)threadIdx.x;
+  const long long t0 = clock64();
+  while (clock64() - t0 < clocks) __nanosleep(1000);
 }
 
 // ------------------------------------------------------------------------------------
@@ -228,6 +237,110 @@ allreduce_bf16_peers_kernel(const PeerBufs bufs, int P, int64_t v0, int64_t v1) 
   }
 }
 
+// Sum of the P slot copies [P][slot_rows][H] (bf16, this rank's buffer: slot p was written by rank p's K2a epilogue over
+// NVLink) into out[rows][H]: fp32 in rank order (deterministic), one bf16 rounding.  Local HBM traffic only.
+__global__ void __launch_bounds__(256)
+sum_slots_bf16_kernel(const uint4* __restrict__ slots, int P, int64_t slot_vecs, int64_t n_vecs, uint4* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vecs; i += stride) {
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int p = 0; p < P; ++p) {
+      const uint4 a = __ldcs(slots + (int64_t)p * slot_vecs + i);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __bfloat1622float2(h[k]);
+        s[2 * k] += f.x; s[2 * k + 1] += f.y;
+      }
+    }
+    uint4 r;
+    __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = __floats2bfloat162_rn(s[2 * k], s[2 * k + 1]);
+    out[i] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// exp-store backward: P = a * E + g * onehot, so  dH = a * (E . W) + g * W[tcol]   (K2a epilogue)
+//                                                 dW = E^T . (a * hidden) + scatter_t g_t * hidden_t into row tcol_t
+// ------------------------------------------------------------------------------------
+__global__ void softmax_rows_kernel(const float* __restrict__ lse, const float* __restrict__ g,
+                                    const int64_t* __restrict__ targets, const float* __restrict__ row_ref,
+                                    int64_t v_offset, int64_t V, int64_t T, SoftmaxEpiRow* __restrict__ out,
+                                    int64_t* __restrict__ sort_key) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  SoftmaxEpiRow r;
+  r.g = g[t];
+  r.a = r.g != 0.f ? -r.g * exp2f((row_ref[t] - lse[t]) * kLog2e) : 0.f;
+  const int64_t col = targets[t] - v_offset;
+  r.tcol = (col >= 0 && col < V) ? (int32_t)col : -1;
+  r.pad = 0;
+  out[t] = r;
+  // key of the one-hot scatter: tokens that contribute to a row of dW sort by that row, the rest go last
+  if (sort_key) sort_key[t] = (r.g != 0.f && r.tcol >= 0) ? (int64_t)r.tcol : (int64_t)0x7fffffffffffLL;
+}
+
+// out[t, :] = a_t * hidden[t, :]  (bf16, 16 bytes per thread)
+__global__ void __launch_bounds__(256)
+scale_rows_kernel(const uint4* __restrict__ hidden, const SoftmaxEpiRow* __restrict__ rows, int64_t T, int64_t vec_per_row,
+                  uint4* __restrict__ out) {
+  const int64_t n = T * vec_per_row;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float a = rows[i / vec_per_row].a;
+    uint4 x = make_uint4(0, 0, 0, 0);
+    if (a != 0.f) {
+      x = hidden[i];
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&x);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __bfloat1622float2(h[k]);
+        h[k] = __floats2bfloat162_rn(a * f.x, a * f.y);
+      }
+    }
+    out[i] = x;
+  }
+}
+
+// One CTA per position i of the sorted token order; the CTA at the first token of a run of equal target columns sums
+// g_t * hidden[t, :] over the run sequentially in fp32 (deterministic) and adds it to dW[tcol, :] (single writer per row).
+__global__ void __launch_bounds__(128)
+onehot_scatter_kernel(const int64_t* __restrict__ order, const SoftmaxEpiRow* __restrict__ rows,
+                      const __nv_bfloat16* __restrict__ hidden, int64_t T, int64_t H, float* __restrict__ dW) {
+  const int64_t i = blockIdx.x;
+  const int64_t t0 = order[i];
+  const SoftmaxEpiRow r0 = rows[t0];
+  if (r0.g == 0.f || r0.tcol < 0) return;
+  if (i > 0) {
+    const SoftmaxEpiRow rp = rows[order[i - 1]];
+    if (rp.g != 0.f && rp.tcol == r0.tcol) return;          // not the first token of its run
+  }
+  float* dst = dW + (int64_t)r0.tcol * H;
+  for (int64_t h0 = (int64_t)threadIdx.x * 8; h0 < H; h0 += 128 * 8) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int64_t j = i; j < T; ++j) {
+      const int64_t t = order[j];
+      const SoftmaxEpiRow r = rows[t];
+      if (r.g == 0.f || r.tcol != r0.tcol) break;
+      const uint4 x = *reinterpret_cast<const uint4*>(hidden + t * H + h0);
+      const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&x);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __bfloat1622float2(hh[k]);
+        acc[2 * k] = fmaf(r.g, f.x, acc[2 * k]);
+        acc[2 * k + 1] = fmaf(r.g, f.y, acc[2 * k + 1]);
+      }
+    }
+    float4* d4 = reinterpret_cast<float4*>(dst + h0);
+    float4 lo = d4[0], hi = d4[1];
+    lo.x += acc[0]; lo.y += acc[1]; lo.z += acc[2]; lo.w += acc[3];
+    hi.x += acc[4]; hi.y += acc[5]; hi.z += acc[6]; hi.w += acc[7];
+    d4[0] = lo; d4[1] = hi;
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // dlogits: P[t,v] = g[t] * ([v + v_offset == target[t]] - exp(z[t,v] - lse[t])), in place, bf16
 // ------------------------------------------------------------------------------------
@@ -301,10 +414,10 @@ extern "C" size_t o3v_lmhead_fwd_workspace_bytes(int64_t T, int64_t V, int64_t H
   return (size_t)((int64_t)p.num_n_groups * 3 * T) * sizeof(float);
 }
 
-extern "C" int o3v_lmhead_fwd(const void* hidden, const void* weight, const int64_t* targets,
-                              int64_t T, int64_t V, int64_t H, int64_t v_offset,
-                              float* stats, void* logits, int64_t ld_logits,
-                              void* workspace, size_t workspace_bytes, void* stream) {
+static int lmhead_fwd_impl(const void* hidden, const void* weight, const int64_t* targets,
+                           int64_t T, int64_t V, int64_t H, int64_t v_offset,
+                           float* stats, void* logits, int64_t ld_logits, const float* row_ref, const int32_t* row_keep,
+                           void* workspace, size_t workspace_bytes, void* stream) {
   if (!hidden || !weight || !targets || !stats || !workspace) return O3V_ERR_INVALID_ARG;
   if (T <= 0 || V <= 0 || H <= 0 || v_offset < 0) return O3V_ERR_INVALID_ARG;
   if (H % 64 != 0) return O3V_ERR_SHAPE;
@@ -322,6 +435,7 @@ extern "C" int o3v_lmhead_fwd(const void* hidden, const void* weight, const int6
   if (workspace_bytes < (size_t)p.num_n_groups * 3 * T * sizeof(float)) return O3V_ERR_WORKSPACE;
   p.targets = targets; p.v_offset = v_offset; p.parts = reinterpret_cast<float*>(workspace);
   p.logits = reinterpret_cast<__nv_bfloat16*>(logits); p.ld_logits = ld_logits;
+  p.row_ref = row_ref; p.row_keep = row_keep;
   p.hint_a = g_hint_fwd_a; p.hint_b = g_hint_fwd_b; p.hint_store = g_hint_fwd_store;
   CUtensorMap tmA, tmB, tmC = {};
   if ((rc = make_tmap_bf16(&tmA, hidden, H, T, H, 128))) return rc;
@@ -334,6 +448,23 @@ extern "C" int o3v_lmhead_fwd(const void* hidden, const void* weight, const int6
   merge_stats_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, st>>>(p.parts, p.num_n_groups, T, stats, nullptr, nullptr);
   O3V_LAUNCH_CHECK();
   return O3V_OK;
+}
+
+extern "C" int o3v_lmhead_fwd(const void* hidden, const void* weight, const int64_t* targets,
+                              int64_t T, int64_t V, int64_t H, int64_t v_offset,
+                              float* stats, void* logits, int64_t ld_logits,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  return lmhead_fwd_impl(hidden, weight, targets, T, V, H, v_offset, stats, logits, ld_logits, nullptr, nullptr, workspace,
+                         workspace_bytes, stream);
+}
+
+extern "C" int o3v_lmhead_fwd_exp(const void* hidden, const void* weight, const int64_t* targets,
+                                  int64_t T, int64_t V, int64_t H, int64_t v_offset,
+                                  float* stats, void* expz, int64_t ld_expz, const float* row_ref, const int32_t* row_keep,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  if (!expz || !row_ref) return O3V_ERR_INVALID_ARG;
+  return lmhead_fwd_impl(hidden, weight, targets, T, V, H, v_offset, stats, expz, ld_expz, row_ref, row_keep, workspace,
+                         workspace_bytes, stream);
 }
 
 extern "C" int o3v_lmhead_merge_stats(const float* parts, int64_t P, int64_t T, float* logp, float* lse,
@@ -400,13 +531,18 @@ extern "C" int o3v_lmhead_dlogits(void* logits, int64_t T, int64_t V, int64_t ld
 
 // softmax-backward parameters of the fused variants (nullptr = plain GEMM on a ready-made P)
 struct XformArgs { const void* rows; };
+// reduce-scatter destination of K2a (nullptr = local store)
+struct ScatterArgs { void* const* slot_ptrs; int64_t P, rank, rows_per_owner, slot_rows, row0; };
+// exp-store path: the A operand is E and the softmax backward happens in the K2a epilogue (nullptr = A is P)
+struct SoftmaxEpiArgs { const void* rows; };
 
 static int bwd_dhidden_impl(const void* dlogits, int64_t ld_dlogits, const void* weight, int64_t T, int64_t V, int64_t H,
-                            void* d_hidden, int32_t out_is_fp32, const XformArgs* x, void* stream) {
-  if (!dlogits || !weight || !d_hidden || T <= 0 || V <= 0 || H <= 0) return O3V_ERR_INVALID_ARG;
+                            void* d_hidden, int32_t out_is_fp32, const XformArgs* x, void* stream,
+                            const ScatterArgs* sc = nullptr, const SoftmaxEpiArgs* sm = nullptr) {
+  if (!dlogits || !weight || (!d_hidden && !sc) || T <= 0 || V <= 0 || H <= 0) return O3V_ERR_INVALID_ARG;
   if (H % 8 != 0 || ld_dlogits % 8 != 0 || ld_dlogits < V) return O3V_ERR_SHAPE;
   if (T > 0x7fffffffLL - 512 || V > 0x7fffffffLL - 512) return O3V_ERR_SHAPE;
-  if (reinterpret_cast<uintptr_t>(d_hidden) & 15u) return O3V_ERR_ALIGNMENT;
+  if (d_hidden && (reinterpret_cast<uintptr_t>(d_hidden) & 15u)) return O3V_ERR_ALIGNMENT;
   int rc = check_device();
   if (rc) return rc;
   const int ncta = g_cta_bwd;
@@ -416,6 +552,23 @@ static int bwd_dhidden_impl(const void* dlogits, int64_t ld_dlogits, const void*
   plan_tiles(p, ncta, 1 << 20, wide ? 2 : 1);       // one n-tile per item
   p.out = d_hidden; p.ld_out = H; p.out_fp32 = out_is_fp32 ? 1 : 0; p.m_fast = g_dh_mfast;
   p.prefetch_a = g_bwd_prefetch;
+  if (sm) {
+    if (!sm->rows || (reinterpret_cast<uintptr_t>(sm->rows) & 15u) || x) return O3V_ERR_INVALID_ARG;
+    p.sm_rows = reinterpret_cast<const int4*>(sm->rows);
+    p.sm_weight = reinterpret_cast<const __nv_bfloat16*>(weight);
+  }
+  if (sc) {
+    if (out_is_fp32 || sc->P < 1 || sc->P > 16 || sc->rank < 0 || sc->rank >= sc->P || sc->rows_per_owner < 1 ||
+        sc->slot_rows < sc->rows_per_owner || sc->row0 < 0 || !sc->slot_ptrs)
+      return O3V_ERR_INVALID_ARG;
+    if (sc->row0 + T > sc->P * sc->rows_per_owner) return O3V_ERR_SHAPE;      // rows beyond the last owner's range
+    for (int64_t i = 0; i < sc->P; ++i) {
+      if (!sc->slot_ptrs[i] || (reinterpret_cast<uintptr_t>(sc->slot_ptrs[i]) & 15u)) return O3V_ERR_ALIGNMENT;
+      p.peer_out[i] = reinterpret_cast<__nv_bfloat16*>(sc->slot_ptrs[i]);
+    }
+    p.n_peers = (int32_t)sc->P; p.my_rank = (int32_t)sc->rank;
+    p.rows_per_owner = sc->rows_per_owner; p.slot_rows = sc->slot_rows; p.row0 = sc->row0;
+  }
   p.hint_a = g_hint_bwd_a; p.hint_b = g_hint_bwd_b;
   CUtensorMap tmA, tmB;
   if ((rc = make_tmap_bf16(&tmA, dlogits, V, T, ld_dlogits, 128))) return rc;   // A = P, K-major (K = V)
@@ -466,6 +619,57 @@ extern "C" int o3v_lmhead_softmax_bwd_rows(const float* lse, const float* grad_l
   return O3V_OK;
 }
 
+extern "C" int o3v_lmhead_bwd_dhidden_scatter(const void* dlogits, int64_t ld_dlogits, const void* weight,
+                                              int64_t T, int64_t V, int64_t H, void* const* slot_ptrs, int64_t P,
+                                              int64_t rank, int64_t rows_per_owner, int64_t slot_rows, int64_t row0,
+                                              void* stream) {
+  ScatterArgs sc = {slot_ptrs, P, rank, rows_per_owner, slot_rows, row0};
+  return bwd_dhidden_impl(dlogits, ld_dlogits, weight, T, V, H, nullptr, 0, nullptr, stream, &sc);
+}
+
+extern "C" int o3v_lmhead_softmax_rows(const float* lse, const float* grad_logp, const int64_t* targets,
+                                       const float* row_ref, int64_t v_offset, int64_t V, int64_t T, void* rows,
+                                       int64_t* sort_key, void* stream) {
+  if (!lse || !grad_logp || !targets || !row_ref || !rows || v_offset < 0 || V <= 0 || T <= 0) return O3V_ERR_INVALID_ARG;
+  if (V > 0x7fffffffLL - 512) return O3V_ERR_SHAPE;
+  if (reinterpret_cast<uintptr_t>(rows) & 15u) return O3V_ERR_ALIGNMENT;
+  int rc = check_device();
+  if (rc) return rc;
+  static_assert(sizeof(SoftmaxEpiRow) == 16, "record layout");
+  softmax_rows_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, (cudaStream_t)stream>>>(
+      lse, grad_logp, targets, row_ref, v_offset, V, T, reinterpret_cast<SoftmaxEpiRow*>(rows), sort_key);
+  O3V_LAUNCH_CHECK();
+  return O3V_OK;
+}
+
+extern "C" int o3v_lmhead_bwd_dhidden_exp(const void* expz, int64_t ld_expz, const void* rows, const void* weight,
+                                          int64_t T, int64_t V, int64_t H, void* d_hidden, int32_t out_is_fp32,
+                                          void* const* slot_ptrs, int64_t P, int64_t rank, int64_t rows_per_owner,
+                                          int64_t slot_rows, int64_t row0, void* stream) {
+  SoftmaxEpiArgs sm = {rows};
+  if (slot_ptrs) {
+    ScatterArgs sc = {slot_ptrs, P, rank, rows_per_owner, slot_rows, row0};
+    return bwd_dhidden_impl(expz, ld_expz, weight, T, V, H, nullptr, 0, nullptr, stream, &sc, &sm);
+  }
+  return bwd_dhidden_impl(expz, ld_expz, weight, T, V, H, d_hidden, out_is_fp32, nullptr, stream, nullptr, &sm);
+}
+
+extern "C" int o3v_sum_slots_bf16(const void* slots, int64_t P, int64_t slot_rows, int64_t rows, int64_t H, void* out,
+                                  int32_t num_ctas, void* stream) {
+  if (!slots || !out || P < 1 || P > 16 || rows < 0 || slot_rows < rows || H <= 0 || (H % 8) != 0) return O3V_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(slots) & 15u) || (reinterpret_cast<uintptr_t>(out) & 15u)) return O3V_ERR_ALIGNMENT;
+  int rc = check_device();
+  if (rc) return rc;
+  if (rows == 0) return O3V_OK;
+  const int64_t n_vecs = rows * H / 8, slot_vecs = slot_rows * H / 8;
+  int ctas = num_ctas > 0 ? num_ctas : 2 * num_sms();
+  ctas = (int)std::min<int64_t>(ctas, ceil_div(n_vecs, 256));
+  sum_slots_bf16_kernel<<<ctas, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(slots), (int)P, slot_vecs,
+                                                                n_vecs, reinterpret_cast<uint4*>(out));
+  O3V_LAUNCH_CHECK();
+  return O3V_OK;
+}
+
 extern "C" int o3v_lmhead_bwd_dhidden_fused(const void* logits, int64_t ld_logits, const void* rows,
                                             const void* weight, int64_t T, int64_t V, int64_t H, void* d_hidden,
                                             int32_t out_is_fp32, void* stream) {
@@ -511,12 +715,46 @@ extern "C" int o3v_lmhead_bwd_dweight(const void* dlogits, int64_t ld_dlogits, c
   return bwd_dweight_impl(dlogits, ld_dlogits, hidden, T, V, H, d_weight, accumulate, nullptr, stream);
 }
 
+extern "C" int o3v_lmhead_bwd_dweight_exp(const void* expz, int64_t ld_expz, const void* rows, const int64_t* order,
+                                          const void* hidden, int64_t T, int64_t V, int64_t H, float* d_weight,
+                                          int32_t accumulate, void* scaled_hidden, void* stream) {
+  if (!rows || !order || !scaled_hidden || !hidden || T <= 0 || H <= 0 || (H % 8) != 0) return O3V_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(rows) & 15u) || (reinterpret_cast<uintptr_t>(scaled_hidden) & 15u) ||
+      (reinterpret_cast<uintptr_t>(hidden) & 15u))
+    return O3V_ERR_ALIGNMENT;
+  int rc = check_device();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t nvec = T * (H / 8);
+  const int ctas = (int)std::min<int64_t>(8 * (int64_t)num_sms(), ceil_div(nvec, 256));
+  scale_rows_kernel<<<ctas, 256, 0, st>>>(reinterpret_cast<const uint4*>(hidden),
+                                          reinterpret_cast<const SoftmaxEpiRow*>(rows), T, H / 8,
+                                          reinterpret_cast<uint4*>(scaled_hidden));
+  O3V_LAUNCH_CHECK();
+  rc = bwd_dweight_impl(expz, ld_expz, scaled_hidden, T, V, H, d_weight, accumulate, nullptr, stream);
+  if (rc) return rc;
+  onehot_scatter_kernel<<<(unsigned)T, 128, 0, st>>>(order, reinterpret_cast<const SoftmaxEpiRow*>(rows),
+                                                     reinterpret_cast<const __nv_bfloat16*>(hidden), T, H, d_weight);
+  O3V_LAUNCH_CHECK();
+  return O3V_OK;
+}
+
 extern "C" int o3v_lmhead_bwd_dweight_fused(const void* logits, int64_t ld_logits, const void* rows,
                                             const void* hidden, int64_t T, int64_t V, int64_t H, float* d_weight,
                                             int32_t accumulate, void* stream) {
   if (!rows || (reinterpret_cast<uintptr_t>(rows) & 15u)) return O3V_ERR_INVALID_ARG;
   XformArgs x = {rows};
   return bwd_dweight_impl(logits, ld_logits, hidden, T, V, H, d_weight, accumulate, &x, stream);
+}
+
+extern "C" int o3v_debug_occupy_sms(int32_t num_ctas, int32_t smem_bytes, int64_t clocks, void* stream) {
+  if (num_ctas < 1 || smem_bytes < 0 || smem_bytes > 227 * 1024 || clocks < 0) return O3V_ERR_INVALID_ARG;
+  int rc = check_device();
+  if (rc) return rc;
+  O3V_CUDA_TRY(cudaFuncSetAttribute(occupy_sms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  occupy_sms_kernel<<<num_ctas, 64, smem_bytes, (cudaStream_t)stream>>>((long long)clocks);
+  O3V_LAUNCH_CHECK();
+  return O3V_OK;
 }
 
 extern "C" int o3v_debug_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N,

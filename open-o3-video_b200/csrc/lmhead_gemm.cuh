@@ -37,15 +37,24 @@ struct GemmParams {
   int32_t num_n_groups;     // ceil(num_n_tiles / tiles_per_group)
   int32_t m_fast;           // item order: 0 = n-groups fastest (CTAs running together share A panels),
                             //             1 = m-blocks fastest (they share B panels)
-  unsigned int* wave_sync;  // optional global counter (zeroed before launch): the TMA producers of all CTAs
-                            // rendezvous at every wave boundary of the static schedule, so that CTAs which
-                            // stream the same operand panels stay inside each other's L2 window
+  unsigned int* wave_sync;  // optional pair of global words {arrivals, abandoned} (zeroed before launch): the TMA
+                            // producers of all CTAs rendezvous at every wave boundary of the static schedule, so
+                            // that CTAs which stream the same operand panels stay inside each other's L2 window.
+                            // A pure performance hint: if the grid is not fully co-resident (another kernel holds
+                            // SMs) the first CTA whose wait exceeds kWaveSyncTimeout raises `abandoned` and every CTA
+                            // runs on unsynchronised; nothing ever traps or deadlocks on it.
   // EPI_STATS
   const int64_t* targets;   // [M] global vocab ids
   int64_t v_offset;         // first vocab id of this slice
   float* parts;             // [num_n_groups, 3, M]: max, sum exp(z - max), target logit
   __nv_bfloat16* logits;    // optional [M, ld_logits]
   int64_t ld_logits;
+  // exp-store mode (row_ref != nullptr, needs `logits`): what is stored is not the logit z but
+  //   E[t, v] = exp(z[t, v] - row_ref[t])   (0 for rows with row_keep[t] == 0)
+  // with a per-row reference known BEFORE the sweep, so that softmax = E * exp(row_ref - lse) is a per-row rescale and
+  // the softmax backward folds into the epilogues / operands of the backward GEMMs by linearity (lmhead.cu).
+  const float* row_ref;     // [M]
+  const int32_t* row_keep;  // optional [M]
   // EPI_STORE / EPI_ACCUM
   void* out;                // [M, ld_out] bf16 or fp32
   int64_t ld_out;
@@ -56,9 +65,27 @@ struct GemmParams {
   // kXform: the A operand in HBM is the bf16 LOGITS chunk z[t, v]; the softmax backward
   //   P[t, v] = g[t] * ([v + v_offset == target[t]] - exp(z[t, v] - lse[t]))
   // is applied to every A tile in shared memory between its TMA load and the MMAs that read it
+  // EPI_STORE fused with the reduce-scatter of the vocab-parallel path: row r of the output belongs to the rank that
+  // owns token (row0 + r); the bf16 tile is stored STRAIGHT into that rank's peer-mapped slot buffer (NVLink P2P
+  // stores from the epilogue, tile by tile while the GEMM runs), slot = this rank.  n_peers == 0: plain local store.
+  __nv_bfloat16* peer_out[16];   // rank p's slot buffer [n_peers][slot_rows][ld_out]
+  int32_t n_peers, my_rank;
+  int64_t rows_per_owner, slot_rows, row0;
+  // EPI_STORE with the softmax backward folded into the epilogue (exp-store path): the A operand is E = exp(z - ref),
+  //   out[t, h] = a_t * acc[t, h] + g_t * W[tcol_t, h]      a_t = -g_t * exp(ref_t - lse_t)   (second term: target in slice)
+  const int4* sm_rows;           // [M] SoftmaxEpiRow records, nullptr = plain store
+  const __nv_bfloat16* sm_weight;   // W [K, N] row-major (the B operand), rows gathered at the target column
   int32_t prefetch_a;         // > 0: the producer prefetches the A tile of k-block kb + prefetch_a into L2
   const int4* x_rows;         // [tokens] packed per-token scalars (SoftmaxBwdRow, written by softmax_bwd_rows_kernel)
   int64_t x_tokens;           // number of token rows
+};
+
+// Per-token scalars of the exp-store backward (softmax_rows_kernel): P[t, v] = a * E[t, v] + g * [v == tcol].
+struct SoftmaxEpiRow {
+  float g;        // d loss / d logp (0: masked-out token)
+  float a;        // -g * exp(row_ref - lse)
+  int32_t tcol;   // target column within the slice, -1 if the target lives in another slice
+  int32_t pad;
 };
 
 // Per-token scalars of the fused softmax backward, one 16-byte record so that a transform thread needs ONE load per
@@ -104,6 +131,9 @@ struct GemmShape {
   static constexpr int TMEM_COLS = 512;
 };
 
+// longest legitimate wait at a wave rendezvous is the skew between CTAs of one wave (tens of microseconds);
+// ~4 ms of SM clocks means that part of the grid is not resident
+constexpr long long kWaveSyncTimeout = 8000000LL;
 constexpr int kGemmThreads = 256;
 constexpr int kGemmThreadsXform = 384;    // + warps 8..11: with warps 4..7 the eight transform warps of a kXform kernel
 constexpr float kLog2e = 1.4426950408889634f;
@@ -279,17 +309,24 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     // ================================ TMA producer ================================
     int stage = 0; uint32_t phase = 0;
     unsigned int sync_target = 0;
+    bool sync_off = false;
     for (int item = worker; item < num_items; item += num_workers) {
       if (p.wave_sync != nullptr) {
-        if (item != worker) {          // every CTA active in the previous wave has issued all of its loads
+        if (item != worker && !sync_off) {   // every CTA active in the previous wave has issued all of its loads
+          bool off = false;
           if (ptx::elect_one()) {
             const long long t0 = clock64();
             while (ptx::ld_acquire_gpu(p.wave_sync) < sync_target) {
+              if (ptx::ld_acquire_gpu(p.wave_sync + 1) != 0u) { off = true; break; }
               __nanosleep(200);
-              if (clock64() - t0 > 10000000000LL) ptx::mbar_timeout_trap(0xffffffffu, sync_target);
+              if (clock64() - t0 > kWaveSyncTimeout) {          // peers are not resident: give the hint up for good
+                ptx::red_release_gpu_add(p.wave_sync + 1, 1u);
+                off = true;
+                break;
+              }
             }
           }
-          __syncwarp();
+          sync_off = __any_sync(0xffffffffu, off);
         }
         const int wave_first = item - worker;                                  // first item of this wave
         sync_target += (unsigned int)(min(num_workers, num_items - wave_first) * kNCta);
@@ -445,9 +482,23 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
       float run_max = -INFINITY, run_sum = 0.f, tgt_logit = 0.f;
       int64_t tgt_col = -1;
+      float sm_g = 0.f, sm_a = 0.f;                          // EPI_STORE softmax epilogue: this row's record
+      int sm_tcol = -1;
+      if constexpr (kEpi == EPI_STORE) {
+        if (p.sm_rows != nullptr && row_ok) {
+          const int4 rec = __ldg(p.sm_rows + row);
+          sm_g = __int_as_float(rec.x); sm_a = __int_as_float(rec.y); sm_tcol = rec.z;
+        }
+      }
+      float ref_l2e = 0.f;                                   // exp-store mode: row_ref[row] * log2e
+      bool keep_row = false;
       if constexpr (kEpi == EPI_STATS) {
         if (row_ok) tgt_col = p.targets[row] - p.v_offset;   // may fall outside this slice
         if (tgt_col >= p.N) tgt_col = -1;                    // (never match a zero-filled column)
+        if (p.row_ref != nullptr && row_ok) {
+          ref_l2e = p.row_ref[row] * kLog2e;
+          keep_row = p.row_keep == nullptr || p.row_keep[row] != 0;
+        }
       }
 
       for (int nt = t_begin; nt < t_end; ++nt, ++acc_iter) {
@@ -461,44 +512,48 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int tgt_in_tile = (tgt_col >= n0 && tgt_col < n0 + S::TILE_N) ? (int)(tgt_col - n0) : -1;
         const uint32_t tmem_tile = tmem_row + a * S::TILE_N;
 
+        // bf16 copy of one 32-column chunk (scaled by `scale`) for the chunked backward: [32 rows x 64 cols] per warp
+        // staged in 128B-swizzled smem (conflict-free 16-byte stores), then ONE coalesced TMA store per 64 columns;
+        // the box is clipped against [T, V] by the TMA unit, so ragged edges need no guards.
+        auto store_chunk = [&](const uint32_t (&v)[32], const int c, const bool scaled, const float scale_in) {
+          const float scale = scaled ? scale_in : 1.0f;
+          const int cbase = c * 32;
+          const int half = c & 1;
+          if (half == 0) {
+            if (lane == 0) ptx::bulk_wait_read<1>();   // the store that last read this buffer is done
+            __syncwarp();
+          }
+          const uint32_t rowbase = stg_warp + sbuf * 4096u + (uint32_t)lane * 128u;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(scaled ? __uint_as_float(v[j * 8 + 0]) * scale : __uint_as_float(v[j * 8 + 0]), scaled ? __uint_as_float(v[j * 8 + 1]) * scale : __uint_as_float(v[j * 8 + 1]));
+            __nv_bfloat162 t1 = __floats2bfloat162_rn(scaled ? __uint_as_float(v[j * 8 + 2]) * scale : __uint_as_float(v[j * 8 + 2]), scaled ? __uint_as_float(v[j * 8 + 3]) * scale : __uint_as_float(v[j * 8 + 3]));
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(scaled ? __uint_as_float(v[j * 8 + 4]) * scale : __uint_as_float(v[j * 8 + 4]), scaled ? __uint_as_float(v[j * 8 + 5]) * scale : __uint_as_float(v[j * 8 + 5]));
+            __nv_bfloat162 t3 = __floats2bfloat162_rn(scaled ? __uint_as_float(v[j * 8 + 6]) * scale : __uint_as_float(v[j * 8 + 6]), scaled ? __uint_as_float(v[j * 8 + 7]) * scale : __uint_as_float(v[j * 8 + 7]));
+            const uint32_t chunk16 = (uint32_t)(half * 4 + j) ^ ((uint32_t)lane & 7u);   // 128B swizzle
+            ptx::st_shared_v4(rowbase + (chunk16 << 4), *reinterpret_cast<uint32_t*>(&t0),
+                              *reinterpret_cast<uint32_t*>(&t1), *reinterpret_cast<uint32_t*>(&t2),
+                              *reinterpret_cast<uint32_t*>(&t3));
+          }
+          if (half == 1) {
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              const int32_t r0 = (int32_t)((int64_t)m_blk * S::UMMA_M + (int64_t)rank * BM + q * 32);
+              if (p.hint_store == 0) ptx::tma_store_2d(&tmC, stg_warp + sbuf * 4096u, (int32_t)(n0 + cbase - 32), r0);
+              else ptx::tma_store_2d_hint(&tmC, stg_warp + sbuf * 4096u, (int32_t)(n0 + cbase - 32), r0,
+                                          ptx::l2_policy(p.hint_store));
+              ptx::bulk_commit();
+            }
+            sbuf ^= 1u;
+          }
+        };
+
         // one 32-column chunk of this thread's accumulator row
         auto process = [&](uint32_t (&v)[32], const int c) {
           const int cbase = c * 32;                       // first column of the chunk within the tile
           if constexpr (kEpi == EPI_STATS) {
-            if (p.logits != nullptr) {
-              // bf16 copy of the tile for the chunked backward: [32 rows x 64 cols] per warp staged in
-              // 128B-swizzled smem (conflict-free 16-byte stores), then ONE coalesced TMA store; the
-              // box is clipped against [T, V] by the TMA unit, so ragged edges need no guards.
-              const int half = c & 1;
-              if (half == 0) {
-                if (lane == 0) ptx::bulk_wait_read<1>();   // the store that last read this buffer is done
-                __syncwarp();
-              }
-              const uint32_t rowbase = stg_warp + sbuf * 4096u + (uint32_t)lane * 128u;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]));
-                __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
-                __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5]));
-                __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]));
-                const uint32_t chunk16 = (uint32_t)(half * 4 + j) ^ ((uint32_t)lane & 7u);   // 128B swizzle
-                ptx::st_shared_v4(rowbase + (chunk16 << 4), *reinterpret_cast<uint32_t*>(&t0),
-                                  *reinterpret_cast<uint32_t*>(&t1), *reinterpret_cast<uint32_t*>(&t2),
-                                  *reinterpret_cast<uint32_t*>(&t3));
-              }
-              if (half == 1) {
-                ptx::fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                  const int32_t r0 = (int32_t)((int64_t)m_blk * S::UMMA_M + (int64_t)rank * BM + q * 32);
-                  if (p.hint_store == 0) ptx::tma_store_2d(&tmC, stg_warp + sbuf * 4096u, (int32_t)(n0 + cbase - 32), r0);
-                  else ptx::tma_store_2d_hint(&tmC, stg_warp + sbuf * 4096u, (int32_t)(n0 + cbase - 32), r0,
-                                              ptx::l2_policy(p.hint_store));
-                  ptx::bulk_commit();
-                }
-                sbuf ^= 1u;
-              }
-            }
+            if (p.logits != nullptr && p.row_ref == nullptr) store_chunk(v, c, false, 1.0f);     // bf16 logits (dlogits path)
             if (cbase + 32 > n_valid) {            // ragged last tile: TMA zero-filled columns are not vocabulary
 #pragma unroll
               for (int j = 0; j < 32; ++j)
@@ -519,11 +574,17 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;      // 4 chains: the adds do not serialise
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
-                acc0 += ptx::ex2_approx(fmaf(__uint_as_float(v[j + 0]), kLog2e, neg));
-                acc1 += ptx::ex2_approx(fmaf(__uint_as_float(v[j + 1]), kLog2e, neg));
-                acc2 += ptx::ex2_approx(fmaf(__uint_as_float(v[j + 2]), kLog2e, neg));
-                acc3 += ptx::ex2_approx(fmaf(__uint_as_float(v[j + 3]), kLog2e, neg));
+                const float f0 = ptx::ex2_approx(fmaf(__uint_as_float(v[j + 0]), kLog2e, neg));
+                const float f1 = ptx::ex2_approx(fmaf(__uint_as_float(v[j + 1]), kLog2e, neg));
+                const float f2 = ptx::ex2_approx(fmaf(__uint_as_float(v[j + 2]), kLog2e, neg));
+                const float f3 = ptx::ex2_approx(fmaf(__uint_as_float(v[j + 3]), kLog2e, neg));
+                acc0 += f0; acc1 += f1; acc2 += f2; acc3 += f3;
+                // exp-store mode: the exponentials themselves are what the backward needs (dead stores otherwise)
+                v[j + 0] = __float_as_uint(f0); v[j + 1] = __float_as_uint(f1);
+                v[j + 2] = __float_as_uint(f2); v[j + 3] = __float_as_uint(f3);
               }
+              if (p.row_ref != nullptr)      // E = exp(z - max) * exp(max - ref); masked-out rows store zeros
+                store_chunk(v, c, true, keep_row ? ptx::ex2_approx(fmaf(new_max, kLog2e, -ref_l2e)) : 0.f);
               // rescale from the EXACT difference: an unchanged max must give a factor of exactly 1
               // (via fmaf(run_max, log2e, neg) the rounding of max*log2e would compound over the
               // ~4.7k chunks of a vocabulary sweep)
@@ -531,6 +592,30 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               run_max = new_max;
             }
           } else if constexpr (kEpi == EPI_STORE) {
+            if (p.sm_rows != nullptr && row_ok) {          // softmax backward by linearity: rescale + target row of W
+              if (sm_g == 0.f) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0u;    // masked-out token: exactly zero (never 0 * inf)
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(sm_a * __uint_as_float(v[j]));
+                if (sm_tcol >= 0 && cbase < n_valid) {
+                  const uint4* wrow = reinterpret_cast<const uint4*>(p.sm_weight + (int64_t)sm_tcol * p.N + n0 + cbase);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    if (cbase + j * 8 < n_valid) {         // N % 8 == 0: whole 16-byte groups
+                      const uint4 w8 = __ldg(wrow + j);
+                      const uint32_t ww[4] = {w8.x, w8.y, w8.z, w8.w};
+#pragma unroll
+                      for (int k = 0; k < 4; ++k) {
+                        v[j * 8 + 2 * k] = __float_as_uint(fmaf(sm_g, __uint_as_float(ww[k] << 16), __uint_as_float(v[j * 8 + 2 * k])));
+                        v[j * 8 + 2 * k + 1] = __float_as_uint(fmaf(sm_g, __uint_as_float(ww[k] & 0xffff0000u), __uint_as_float(v[j * 8 + 2 * k + 1])));
+                      }
+                    }
+                  }
+                }
+              }
+            }
             if (row_ok) {
               if (p.out_fp32) {
                 float* dst = reinterpret_cast<float*>(p.out) + row * p.ld_out + n0 + cbase;
@@ -539,7 +624,15 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                   if (cbase + j * 4 < n_valid)
                     *reinterpret_cast<uint4*>(dst + j * 4) = make_uint4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
               } else {
-                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ld_out + n0 + cbase;
+                __nv_bfloat16* dst;
+                if (p.n_peers > 0) {
+                  const int64_t grow = p.row0 + row;                       // global token row
+                  int owner = (int)(grow / p.rows_per_owner);
+                  if (owner >= p.n_peers) owner = p.n_peers - 1;
+                  dst = p.peer_out[owner] + ((int64_t)p.my_rank * p.slot_rows + (grow - (int64_t)owner * p.rows_per_owner)) * p.ld_out + n0 + cbase;
+                } else {
+                  dst = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ld_out + n0 + cbase;
+                }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   if (cbase + j * 8 < n_valid) {

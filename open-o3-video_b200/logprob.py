@@ -57,10 +57,12 @@ def _check_head(hidden, weight, targets):
         raise ValueError("targets must be [T]")
 
 
-def lmhead_stats(hidden, weight, targets, v_offset=0, logits_out=None, stats_out=None):
+def lmhead_stats(hidden, weight, targets, v_offset=0, logits_out=None, stats_out=None, row_ref=None, row_keep=None):
     """K1 on one vocab slice -> stats [3, T] fp32 (row max, sum exp(z - max), target logit).
-    `logits_out` ([T, ld] bf16, optional) also receives the bf16 logits; `stats_out` (a contiguous
-    [3, T] fp32 buffer, e.g. in peer-mapped memory) receives the triple instead of a new tensor."""
+    `logits_out` ([T, ld] bf16, optional) also receives the bf16 logits or, with `row_ref` ([T] fp32), the
+    exponentials exp(z - row_ref) (zeros for rows with `row_keep` == 0) that the exp-store backward consumes;
+    `stats_out` (a contiguous [3, T] fp32 buffer, e.g. in peer-mapped memory) receives the triple instead of a
+    new tensor."""
     T, H = hidden.shape
     V = weight.shape[0]
     lib = _lib.load()
@@ -69,10 +71,78 @@ def lmhead_stats(hidden, weight, targets, v_offset=0, logits_out=None, stats_out
     ws = torch.empty(int(lib.o3v_lmhead_fwd_workspace_bytes(T, V, H)), dtype=torch.uint8, device=dev)
     ld = 0 if logits_out is None else logits_out.stride(0)
     with torch.cuda.device(dev):
-        _lib.call("o3v_lmhead_fwd" if logits_out is None else "o3v_lmhead_fwd+store", 2, lib.o3v_lmhead_fwd,
-                  _p(hidden), _p(weight), _p(targets), T, V, H, int(v_offset), _p(stats),
-                  _p(logits_out), ld, _p(ws), ws.numel(), _stream())
+        if row_ref is None:
+            _lib.call("o3v_lmhead_fwd" if logits_out is None else "o3v_lmhead_fwd+store", 2, lib.o3v_lmhead_fwd,
+                      _p(hidden), _p(weight), _p(targets), T, V, H, int(v_offset), _p(stats),
+                      _p(logits_out), ld, _p(ws), ws.numel(), _stream())
+        else:
+            _lib.call("o3v_lmhead_fwd+store", 2, lib.o3v_lmhead_fwd_exp,
+                      _p(hidden), _p(weight), _p(targets), T, V, H, int(v_offset), _p(stats),
+                      _p(logits_out), ld, _p(row_ref), _p(row_keep), _p(ws), ws.numel(), _stream())
     return stats
+
+
+# ---- exp-store backward (include/o3v.h): K1 stores E = exp(z - row_ref), the softmax backward is folded into the K2a
+# epilogue and the B operand of K2b by linearity: no elementwise pass over the [T, V] chunk.
+ROW_REF_SAMPLE = 256       # vocabulary rows sampled (strided) for the per-row reference
+ROW_REF_MARGIN = 16.0      # reference = sampled maximum + margin: overflow only if a logit exceeds the sample by > 100
+
+
+def sample_weight(weight: torch.Tensor) -> torch.Tensor:
+    """ROW_REF_SAMPLE rows of this rank's lm_head slice, strided over the slice (gathered once per step, 1.8 MB)."""
+    V = weight.shape[0]
+    stride = max(1, V // ROW_REF_SAMPLE)
+    return weight[::stride][:ROW_REF_SAMPLE].contiguous()
+
+
+def row_reference(hidden, w_sample, targets) -> torch.Tensor:
+    """[T] fp32: max over the sampled vocabulary rows of hidden . w^T (K1 itself on a [256, H] weight) + margin."""
+    return lmhead_stats(hidden, w_sample, targets, v_offset=1 << 40)[0] + ROW_REF_MARGIN
+
+
+def softmax_rows(lse, grad_logp, targets, row_ref, v_offset, V):
+    """-> (records [T, 4] int32 opaque, order [T] int64): per-token (g, a, target column) of the exp-store backward and
+    the stable order of the tokens by target column that makes the one-hot scatter into dW deterministic."""
+    T = lse.shape[0]
+    rows = torch.empty(T, 4, dtype=torch.int32, device=lse.device)
+    key = torch.empty(T, dtype=torch.int64, device=lse.device)
+    with torch.cuda.device(lse.device):
+        _lib.call("o3v_lmhead_softmax_rows", 1, _lib.load().o3v_lmhead_softmax_rows, _p(lse), _p(grad_logp), _p(targets),
+                  _p(row_ref), int(v_offset), int(V), T, _p(rows), _p(key), _stream())
+    return rows, torch.sort(key, stable=True).indices
+
+
+def bwd_dhidden_exp(expz, rows, weight, out=None, fp32=False, scatter=None):
+    """dH = a * (E . W) + g * W[tcol] (K2a with the softmax backward in its epilogue).  `scatter` =
+    (PeerExchange, row0, tokens_total): tiles are stored at their token owners instead of `out`."""
+    T, V = expz.shape
+    H = weight.shape[1]
+    lib = _lib.load()
+    with torch.cuda.device(expz.device):
+        if scatter is None:
+            if out is None:
+                out = torch.empty(T, H, dtype=torch.float32 if fp32 else torch.bfloat16, device=expz.device)
+            _lib.call("o3v_lmhead_bwd_dhidden_exp", 1, lib.o3v_lmhead_bwd_dhidden_exp, _p(expz), expz.stride(0), _p(rows),
+                      _p(weight), T, V, H, _p(out), 1 if out.dtype == torch.float32 else 0, None, 0, 0, 0, 0, 0, _stream())
+            return out
+        ex, row0, total = scatter
+        arr = (ctypes.c_void_p * ex.world)(*ex._slot_ptrs)
+        _lib.call("o3v_lmhead_bwd_dhidden_exp", 1, lib.o3v_lmhead_bwd_dhidden_exp, _p(expz), expz.stride(0), _p(rows),
+                  _p(weight), T, V, H, None, 0, arr, ex.world, ex.rank, ex.owner_rows(total)[0], ex.slot_rows, int(row0),
+                  _stream())
+    return None
+
+
+def bwd_dweight_exp(expz, rows, order, hidden, d_weight, accumulate, scratch=None):
+    """dW (+)= E^T . (a * hidden) + one-hot scatter (pre-scale, K2b, scatter: three launches)."""
+    T, V = expz.shape
+    H = hidden.shape[1]
+    if scratch is None or scratch.numel() < T * H:
+        scratch = torch.empty(T, H, dtype=torch.bfloat16, device=expz.device)
+    with torch.cuda.device(expz.device):
+        _lib.call("o3v_lmhead_bwd_dweight_exp", 3, _lib.load().o3v_lmhead_bwd_dweight_exp, _p(expz), expz.stride(0),
+                  _p(rows), _p(order), _p(hidden), T, V, H, _p(d_weight), 1 if accumulate else 0, _p(scratch), _stream())
+    return d_weight
 
 
 def merge_stats(parts):
@@ -95,8 +165,9 @@ def _pg(group):
     return group.group if _is_peer(group) else group
 
 
-def _stats_to_logp(hidden, weight, targets, v_offset, logits_out, group):
+def _stats_to_logp(hidden, weight, targets, v_offset, logits_out, group, row_ref=None, row_keep=None):
     """K1 on this rank's vocab slice + the cross-rank merge -> (logp, lse) over the full vocabulary."""
+    kw = dict(row_ref=row_ref, row_keep=row_keep)
     if _is_peer(group):
         T = hidden.shape[0]
         if T > group.cap:
@@ -106,12 +177,12 @@ def _stats_to_logp(hidden, weight, targets, v_offset, logits_out, group):
         # view only when T == cap, else write compactly and let merge use row_stride = cap
         buf = group.local_stats(slot)
         if T == group.cap:
-            lmhead_stats(hidden, weight, targets, v_offset, logits_out, stats_out=buf)
+            lmhead_stats(hidden, weight, targets, v_offset, logits_out, stats_out=buf, **kw)
         else:
-            st = lmhead_stats(hidden, weight, targets, v_offset, logits_out)
+            st = lmhead_stats(hidden, weight, targets, v_offset, logits_out, **kw)
             buf[:, :T].copy_(st)
         return group.merge(slot, T)
-    stats = lmhead_stats(hidden, weight, targets, v_offset, logits_out)
+    stats = lmhead_stats(hidden, weight, targets, v_offset, logits_out, **kw)
     return merge_stats(_gather_stats(stats, group))
 
 
@@ -143,6 +214,12 @@ def dlogits_(logits, lse, grad_logp, targets, v_offset=0, V=None):
 # 7 + 7 CTAs columns that sweep it: 350 ms per step against 316 ms), so the default stays the separate in-place pass
 # dlogits_ -> plain GEMMs.
 FUSE_DLOGITS = False
+# How the chunked backward forms P = g * (onehot - softmax):
+#   "exp"      K1 stores exp(z - row_ref); rescale + one-hot folded into the K2a epilogue and the K2b operands
+#              (o3v_lmhead_*_exp, default: no pass over the [T, V] chunk between K1 and the two GEMMs)
+#   "dlogits"  K1 stores z, an elementwise in-place pass turns it into P (round 1), or FUSE_DLOGITS rewrites the
+#              A tiles in shared memory inside the GEMMs
+BACKWARD = "exp"
 
 
 def softmax_bwd_rows(lse, grad_logp, targets, v_offset, V):
@@ -210,7 +287,11 @@ class _FusedLogprobFn(torch.autograd.Function):
         need_grad = hidden.requires_grad or weight.requires_grad
         keep = need_grad and (T * V * 2 <= save_logits_budget(hidden.device))
         logits = torch.empty(T, V, dtype=torch.bfloat16, device=hidden.device) if keep else None
-        logp, lse = _stats_to_logp(hidden, weight, targets, v_offset, logits, group)
+        ctx.mode = BACKWARD
+        ctx.row_ref = None
+        if keep and ctx.mode == "exp":
+            ctx.row_ref = row_reference(hidden, sample_weight(weight), targets)
+        logp, lse = _stats_to_logp(hidden, weight, targets, v_offset, logits, group, row_ref=ctx.row_ref)
         ctx.save_for_backward(hidden, weight, targets, lse)
         ctx.logits, ctx.v_offset, ctx.group, ctx.chunk_tokens = logits, v_offset, group, chunk_tokens
         ctx.mark_non_differentiable(lse)
@@ -227,13 +308,25 @@ class _FusedLogprobFn(torch.autograd.Function):
         chunk = min(T, ctx.chunk_tokens)
         zbuf = None if ctx.logits is not None else torch.empty(chunk, V, dtype=torch.bfloat16, device=hidden.device)
         first = True
+        exp_mode = ctx.mode == "exp"
+        w_sample = sample_weight(weight) if (exp_mode and ctx.logits is None) else None
+        scratch = torch.empty(chunk, H, dtype=torch.bfloat16, device=hidden.device) if exp_mode else None
         for s in range(0, T, chunk):
             e = min(T, s + chunk)
+            r = None if ctx.row_ref is None else ctx.row_ref[s:e]
             if ctx.logits is not None:
                 z = ctx.logits[s:e]
             else:                                   # recompute this chunk's logits (forward kept nothing)
                 z = zbuf[: e - s]
-                lmhead_stats(hidden[s:e], weight, targets[s:e], ctx.v_offset, z)
+                if exp_mode:
+                    r = row_reference(hidden[s:e], w_sample, targets[s:e])
+                lmhead_stats(hidden[s:e], weight, targets[s:e], ctx.v_offset, z, row_ref=r)
+            if exp_mode:
+                rows, order = softmax_rows(lse[s:e], g[s:e], targets[s:e], r, ctx.v_offset, V)
+                bwd_dhidden_exp(z, rows, weight, out=d_hidden[s:e])
+                bwd_dweight_exp(z, rows, order, hidden[s:e], d_weight, accumulate=not first, scratch=scratch)
+                first = False
+                continue
             sb = None
             if FUSE_DLOGITS:
                 sb = softmax_bwd_rows(lse[s:e], g[s:e], targets[s:e], ctx.v_offset, V)
@@ -296,7 +389,7 @@ def fused_logprob_gspo(hidden: torch.Tensor, weight: torch.Tensor, completion_id
                        old_per_token_logps: Optional[torch.Tensor] = None, *, v_offset: int = 0, group=None,
                        chunk_tokens: int = DEFAULT_CHUNK_TOKENS, need_grad: bool = True,
                        d_weight_out: Optional[torch.Tensor] = None, overlap_dlogits: bool = False,
-                       fuse_dlogits: Optional[bool] = None):
+                       fuse_dlogits: Optional[bool] = None, backward: Optional[str] = None):
     """The whole policy-objective step in one call: per-token log-probs, KL, group advantages,
     GSPO loss AND the gradients w.r.t. hidden and lm_head.weight (grpo_trainer.py:612-613,
     635-636, 658-706 + their backward), chunked over whole sequences.
@@ -304,12 +397,21 @@ def fused_logprob_gspo(hidden: torch.Tensor, weight: torch.Tensor, completion_id
     hidden [N, Tc, H] bf16: final hidden states at the positions that PREDICT each completion
     token; completion_ids / ref / mask / old: [N, Tc]; rewards_per_func [N, F].
     Returns dict(loss, per_token_logps, advantages, mean_kl, completion_length, reward_std,
-    d_hidden [N, Tc, H] bf16, d_weight [V, H] fp32).
+    d_hidden [N, Tc, H] bf16, d_weight [V, H] fp32).  With `group=` a `sharded.PeerExchange(dh_mode="reduce_scatter")`
+    d_hidden is [hi - lo, H]: the token rows `d_hidden_rows = (lo, hi)` this rank owns (data-parallel layout).
 
-    Per chunk: K1 (+ bf16 logits store) -> merge -> K3 (loss, d loss / d logp) -> K2a, K2b with the softmax backward
-    fused into their operand pipelines (`fuse_dlogits`, default `FUSE_DLOGITS`; False = separate in-place dlogits pass).
+    Per chunk (`backward="exp"`, the default `BACKWARD`): row reference (K1 on 256 sampled vocabulary rows) -> K1 storing
+    exp(z - ref) -> merge -> K3 (loss, d loss / d logp) -> per-token records + sort -> K2a with the softmax backward in
+    its epilogue -> pre-scaled hidden, K2b, one-hot scatter.  `backward="dlogits"`: K1 stores z, then either the in-place
+    elementwise pass (round 1) or, with `fuse_dlogits=True`, the shared-memory transform inside the GEMMs.
     """
     fuse = FUSE_DLOGITS if fuse_dlogits is None else bool(fuse_dlogits)
+    mode = BACKWARD if (backward is None and fuse_dlogits is None) else (backward or "dlogits")
+    if mode not in ("exp", "dlogits"):
+        raise ValueError("backward must be 'exp' or 'dlogits'")
+    exp_mode = need_grad and mode == "exp"
+    if exp_mode:
+        fuse = False
     N, Tc, H = hidden.shape
     V = weight.shape[0]
     dev = hidden.device
@@ -330,7 +432,11 @@ def fused_logprob_gspo(hidden: torch.Tensor, weight: torch.Tensor, completion_id
     zbuf = torch.empty(seqs * Tc, V, dtype=torch.bfloat16, device=dev) if need_grad else None
     d_hidden = None
     peer_dh = False
-    if need_grad:
+    scatter_dh = bool(need_grad and _is_peer(group) and getattr(group, "dh_mode", "") == "reduce_scatter"
+                      and group.hidden_size == H)
+    if scatter_dh and fuse_dlogits:
+        raise ValueError("fuse_dlogits and the reduce-scatter K2a cannot be combined")
+    if need_grad and not scatter_dh:
         d_hidden = group.dh_view(N * Tc, H) if _is_peer(group) else None      # peer-mapped: overlapped all-reduce
         peer_dh = d_hidden is not None
         if d_hidden is None:
@@ -348,8 +454,30 @@ def fused_logprob_gspo(hidden: torch.Tensor, weight: torch.Tensor, completion_id
     main = torch.cuda.current_stream(dev)
     side = _side_stream(dev) if pipelined else None
 
+    dh_owned = [None]
+    w_sample = sample_weight(weight) if exp_mode else None
+    scratch = torch.empty(seqs * Tc, H, dtype=torch.bfloat16, device=dev) if exp_mode else None
+    mask_flat = mask.view(-1)
+
+    def backward_gemms_exp(ci, s, e, z, lse, g, r):
+        rows, order = softmax_rows(lse, g, targets[s:e], r, v_offset, V)
+        if scatter_dh:
+            bwd_dhidden_exp(z, rows, weight, scatter=(group, s, N * Tc))     # epilogue stores each tile at its owner
+            if e == N * Tc:
+                dh_owned[0] = group.dhidden_reduce_async(N * Tc)
+        else:
+            bwd_dhidden_exp(z, rows, weight, out=d_hidden[s:e])
+        if peer_dh:
+            group.allreduce_dh_async(s, e - s)
+        bwd_dweight_exp(z, rows, order, hidden2[s:e], d_weight, (ci > 0) or (d_weight_out is not None), scratch)
+
     def backward_gemms(ci, s, e, z, sb=None):
-        bwd_dhidden(z, weight, out=d_hidden[s:e], softmax_bwd=sb)
+        if scatter_dh:
+            group.dhidden_scatter(z, weight, s, N * Tc)       # K2a whose epilogue stores each tile at its owner (NVLink)
+            if e == N * Tc:
+                dh_owned[0] = group.dhidden_reduce_async(N * Tc)   # barrier + local slot sum beside the dW GEMM below
+        else:
+            bwd_dhidden(z, weight, out=d_hidden[s:e], softmax_bwd=sb)
         if peer_dh:
             group.allreduce_dh_async(s, e - s)                # runs beside the dW GEMM below
         bwd_dweight(z, hidden2[s:e], d_weight, accumulate=(ci > 0) or (d_weight_out is not None), softmax_bwd=sb)
@@ -361,12 +489,17 @@ def fused_logprob_gspo(hidden: torch.Tensor, weight: torch.Tensor, completion_id
         z = None
         if need_grad:
             z = (zbuf2 if (pipelined and (ci & 1)) else zbuf)[: e - s]
-        lp, lse = _stats_to_logp(hidden2[s:e], weight, targets[s:e], v_offset, z, group)
+        r = row_reference(hidden2[s:e], w_sample, targets[s:e]) if exp_mode else None
+        lp, lse = _stats_to_logp(hidden2[s:e], weight, targets[s:e], v_offset, z, group, row_ref=r,
+                                 row_keep=mask_flat[s:e] if exp_mode else None)
         logp[n0:n1] = lp.view(n1 - n0, Tc)
         state, g, _ = gspo_raw(logp[n0:n1], ref[n0:n1], mask[n0:n1], rpf, num_generations, beta, epsilon_low,
                                epsilon_high, gspo, None if old is None else old[n0:n1], want_grad=need_grad,
                                want_kl=False, N_total=N, seq_offset=n0, state=state)
         if not need_grad:
+            continue
+        if exp_mode:
+            backward_gemms_exp(ci, s, e, z, lse, g.view(-1), r)
             continue
         if fuse:
             backward_gemms(ci, s, e, z, softmax_bwd_rows(lse, g.view(-1), targets[s:e], v_offset, V))
@@ -394,14 +527,20 @@ def fused_logprob_gspo(hidden: torch.Tensor, weight: torch.Tensor, completion_id
     if pending is not None:
         main.wait_event(pending[-1])
         backward_gemms(*pending[:4])
-    if need_grad and peer_dh:
+    rows = None
+    if scatter_dh:
+        group.wait_allreduce()
+        d_hidden = dh_owned[0]
+        rows = group.owner_rows(N * Tc)[1:]
+    elif need_grad and peer_dh:
         group.wait_allreduce()
     elif need_grad and group is not None:
         import torch.distributed as dist
         dist.all_reduce(d_hidden, group=_pg(group))
     return dict(loss=state["loss"].reshape(()), per_token_logps=logp, advantages=state["adv"],
                 mean_kl=state["mean_kl"].reshape(()), completion_length=state["clen"], reward_std=state["rstd"],
-                d_hidden=None if d_hidden is None else d_hidden.view(N, Tc, H), d_weight=d_weight)
+                d_hidden=None if d_hidden is None else (d_hidden if scatter_dh else d_hidden.view(N, Tc, H)),
+                d_hidden_rows=rows, d_weight=d_weight)
 
 
 class _FusedPolicyStepFn(torch.autograd.Function):

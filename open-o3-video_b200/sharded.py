@@ -29,6 +29,14 @@ def shard_weight(weight, rank: int, world: int):
     return weight[v0:v1].contiguous(), v0
 
 
+def token_owner_rows(tokens: int, world: int, rank: int) -> Tuple[int, int, int]:
+    """(rows_per_owner, lo, hi): the data-parallel layout the reduce-scatter of dHidden assumes (include/o3v.h,
+    o3v_lmhead_bwd_dhidden_scatter): rank r owns the contiguous token rows [r * ceil(T / P), (r + 1) * ceil(T / P))
+    clipped to T."""
+    rpo = -(-tokens // world)
+    return rpo, min(rank * rpo, tokens), min((rank + 1) * rpo, tokens)
+
+
 class PeerExchange:
     """Forward exchange of the vocab-parallel path fused into the merge kernel.
 
@@ -43,11 +51,19 @@ class PeerExchange:
     `.group` is the torch.distributed group used for the remaining collective (dHidden all-reduce).
     """
 
-    def __init__(self, group, capacity_tokens: int, hidden_size: int = 0, device=None, allreduce_ctas: int = 0):
-        """`hidden_size` > 0 also allocates a peer-mapped [capacity, hidden] bf16 dHidden buffer: the
-        partial dHidden of every token chunk is then all-reduced by `o3v_allreduce_bf16_peers` on a side
-        stream WHILE the dW GEMM of the chunk runs (the kernel has no smem and ~43 registers, so its
-        CTAs share SMs with the persistent GEMM CTAs), instead of one exposed NCCL all-reduce."""
+    def __init__(self, group, capacity_tokens: int, hidden_size: int = 0, device=None, allreduce_ctas: int = 0,
+                 dh_mode: str = "all_reduce"):
+        """`hidden_size` > 0 also allocates peer-mapped dHidden storage [capacity, hidden] bf16, used in one of two ways:
+
+        dh_mode="all_reduce": every rank ends with the full dHidden.  The partial dHidden of every token chunk is
+        all-reduced by `o3v_allreduce_bf16_peers` on a side stream WHILE the dW GEMM of the chunk runs (the kernel
+        has no smem and ~43 registers, so its CTAs share SMs with the persistent GEMM CTAs).
+
+        dh_mode="reduce_scatter" (the data-parallel layout of the reference's launch: rank r owns token
+        rows [r * ceil(T / P), ...) and only needs ITS rows of dHidden): the K2a epilogue itself stores every output
+        tile into the owner's slot buffer over NVLink (`o3v_lmhead_bwd_dhidden_scatter`: GEMM and transfer are one
+        kernel, half the NVLink bytes of an all-reduce, no collective kernel beside the GEMMs); after one barrier
+        each owner sums its P slots locally (`o3v_sum_slots_bf16`, deterministic) while the dW GEMM runs."""
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
@@ -64,12 +80,67 @@ class PeerExchange:
         self._calls = 0
         self.hidden_size = int(hidden_size)
         self.dh = None
-        if self.hidden_size > 0:
+        if dh_mode not in ("all_reduce", "reduce_scatter"):
+            raise ValueError("dh_mode must be 'all_reduce' or 'reduce_scatter'")
+        self.dh_mode = dh_mode
+        self.slot_rows = -(-self.cap // self.world)
+        if self.hidden_size > 0 and dh_mode == "reduce_scatter":
+            self.dh_slots = symm.empty((self.world, self.slot_rows, self.hidden_size), dtype=torch.bfloat16, device=device)
+            self.dh_handle = symm.rendezvous(self.dh_slots, group)
+            self._slot_ptrs = [int(p) for p in self.dh_handle.buffer_ptrs]
+            self.side = torch.cuda.Stream(device=device)
+            self.ar_ctas = int(allreduce_ctas) if allreduce_ctas else torch.cuda.get_device_properties(device).multi_processor_count
+        elif self.hidden_size > 0:
             self.dh = symm.empty((self.cap, self.hidden_size), dtype=torch.bfloat16, device=device)
             self.dh_handle = symm.rendezvous(self.dh, group)
             self._dh_ptrs = [int(p) for p in self.dh_handle.buffer_ptrs]
             self.side = torch.cuda.Stream(device=device)
             self.ar_ctas = int(allreduce_ctas) if allreduce_ctas else torch.cuda.get_device_properties(device).multi_processor_count
+
+    # ------------------------------------------------------------------ reduce-scatter of dHidden (fused into K2a)
+    def owner_rows(self, tokens: int, rank=None):
+        """(rows_per_owner, lo, hi): token rows owned by `rank` (default: this rank) of a step of `tokens` rows."""
+        return token_owner_rows(tokens, self.world, self.rank if rank is None else rank)
+
+    def dhidden_scatter(self, dlogits, weight, row0: int, tokens_total: int):
+        """K2a of one chunk (rows row0 .. row0 + dlogits.shape[0] of the step): dH tiles go straight to their owners."""
+        import ctypes
+        import torch
+        from . import _lib
+        from .gspo import _p, _stream
+        if self.hidden_size != weight.shape[1] or tokens_total > self.cap:
+            raise ValueError("PeerExchange was sized for %d tokens x %d" % (self.cap, self.hidden_size))
+        T, V = dlogits.shape
+        rpo = self.owner_rows(tokens_total)[0]
+        arr = (ctypes.c_void_p * self.world)(*self._slot_ptrs)
+        with torch.cuda.device(dlogits.device):
+            _lib.call("o3v_lmhead_bwd_dhidden_scatter", 1, _lib.load().o3v_lmhead_bwd_dhidden_scatter, _p(dlogits),
+                      dlogits.stride(0), _p(weight), T, V, self.hidden_size, arr, self.world, self.rank, rpo,
+                      self.slot_rows, int(row0), _stream())
+
+    def dhidden_reduce_async(self, tokens_total: int):
+        """After the LAST K2a of the step: barrier (every rank's tiles have landed in my slots), then the local sum
+        of the P slots on the side stream (overlaps the dW GEMM that follows on the current stream).  Returns the
+        [rows_owned, hidden] bf16 result; call `wait_allreduce()` before using it."""
+        import ctypes
+        import torch
+        from . import _lib
+        from .gspo import _p
+        rpo, lo, hi = self.owner_rows(tokens_total)
+        out = torch.empty(hi - lo, self.hidden_size, dtype=torch.bfloat16, device=self.dh_slots.device)
+        cur = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ev)
+            self.dh_handle.barrier(channel=2)
+            with torch.cuda.device(self.dh_slots.device):
+                _lib.call("o3v_sum_slots_bf16", 1, _lib.load().o3v_sum_slots_bf16, _p(self.dh_slots), self.world,
+                          self.slot_rows, hi - lo, self.hidden_size, _p(out), self.ar_ctas,
+                          ctypes.c_void_p(self.side.cuda_stream))
+            self.dh_handle.barrier(channel=3)          # nobody overwrites my slots (next step's K2a) before I have read them
+        out.record_stream(self.side)
+        return out
 
     def dh_view(self, tokens: int, hidden: int):
         """[tokens, hidden] bf16 view of the peer-mapped dHidden buffer (valid until the next step)."""
@@ -126,3 +197,52 @@ class PeerExchange:
             _lib.call("o3v_lmhead_merge_stats_peers", 1, _lib.load().o3v_lmhead_merge_stats_peers, arr, self.world,
                       self.cap, T, _p(logp), _p(lse), _stream())
         return logp, lse
+
+
+class PeerGather:
+    """All-gather of per-rank ROW SLICES of several tensors by copy-engine pushes into peer-mapped buffers
+    (in the reference's data-parallel launch every rank holds the hidden states / ids / reference
+    log-probs of ITS sequences, the vocab-parallel head needs all rows on every rank).
+
+    Each rank copies its slice into its own buffer and PUSHES it into every peer's buffer with plain device-to-device
+    copies (cudaMemcpyAsync over NVLink, executed by the copy engines): no SM is taken from the persistent GEMM
+    kernels of a step that is running, unlike NCCL all-gather kernels (round 1: e2e at N=8 rose from 83 % to 94 % of
+    the device-resident rate).  `slots` buffers alternate so that step i+1 can be gathered while step i computes.
+    """
+
+    def __init__(self, group, shapes_dtypes, device=None, slots: int = 2):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.group, self.world = group, dist.get_world_size(group)
+        device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.bufs, self.views, self.handles = [], [], []
+        for _ in range(slots):
+            bs, vs, hs = [], [], []
+            for shape, dtype in shapes_dtypes:
+                b = symm.empty(tuple(shape), dtype=dtype, device=device)
+                h = symm.rendezvous(b, group)
+                bs.append(b)
+                hs.append(h)
+                vs.append([h.get_buffer(r, tuple(shape), dtype) for r in range(self.world)])
+            self.bufs.append(bs)
+            self.views.append(vs)
+            self.handles.append(hs)
+        self.rank = self.handles[0][0].rank
+
+    def gather(self, slot: int, locals_, row_lo: int):
+        """Enqueue on the CURRENT stream: wait until every rank is done with `slot`, copy `locals_[i]` (rows
+        row_lo .. row_lo + len) into all ranks' buffers, barrier.  Returns the list of full tensors of `slot`
+        (complete on every rank once the stream reaches this point)."""
+        h0 = self.handles[slot][0]
+        h0.barrier(channel=4 + 2 * (slot & 1))
+        for i, loc in enumerate(locals_):
+            hi = row_lo + loc.shape[0]
+            src = self.bufs[slot][i][row_lo:hi]
+            if loc.data_ptr() != src.data_ptr():             # (the caller may have filled its own rows in place)
+                src.copy_(loc, non_blocking=True)
+            for r in range(self.world):
+                if r != self.rank:
+                    self.views[slot][i][r][row_lo:hi].copy_(src, non_blocking=True)
+        h0.barrier(channel=5 + 2 * (slot & 1))
+        return self.bufs[slot]

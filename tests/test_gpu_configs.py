@@ -146,3 +146,39 @@ def test_determinism_run_to_run():
     b = logprob.fused_logprob_gspo(*args, chunk_tokens=512)
     for k in ("loss", "per_token_logps", "d_hidden", "d_weight", "advantages", "mean_kl"):
         assert torch.equal(a[k], b[k]), k
+
+
+def test_wave_rendezvous_degrades_when_sms_are_taken(reset_tunables):
+    """Round-1 finding: the wave rendezvous of K2a / K2b assumed every CTA of the persistent grid co-resident; with a
+    foreign kernel holding SMs (a collective of the trainer's comm stream, say) the resident CTAs used to spin and
+    after ~5 s trap the context.  Now the first CTA that waits too long switches the hint off for the launch."""
+    import ctypes
+    import time
+    lib = reset_tunables
+    from open_o3_video_b200 import _lib, logprob
+    T, H, V = 2900, 1792, 9496                      # multi-wave for both GEMMs
+    g = torch.Generator().manual_seed(6)
+    P = (torch.randn(T, V, generator=g) * 0.05).bfloat16().cuda()
+    W = (torch.randn(V, H, generator=g) * 0.02).bfloat16().cuda()
+    Hd = torch.randn(T, H, generator=g).bfloat16().cuda()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dH_ref = P.float() @ W.float()
+    dW_ref = P.float().T @ Hd.float()
+    lib.set_tunable("bwd_sync", 1)
+    side = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    # 48 CTAs x 200 KB of shared memory: 48 SMs cannot take a GEMM CTA for ~60 ms (1.2e8 clocks)
+    _lib.check(_lib.load().o3v_debug_occupy_sms(48, 200 * 1024, 120_000_000, ctypes.c_void_p(side.cuda_stream)), "occupy")
+    time.sleep(0.005)                               # let the blocker start first
+    t0 = time.time()
+    dH = logprob.bwd_dhidden(P, W, fp32=True)
+    dW = torch.zeros(V, H, device="cuda")
+    logprob.bwd_dweight(P, Hd, dW, accumulate=False)
+    torch.cuda.synchronize()                        # a trap would raise here
+    assert time.time() - t0 < 2.0
+    np.testing.assert_allclose(dH.cpu().numpy(), dH_ref.cpu().numpy(), rtol=1e-4, atol=1e-4 * dH_ref.abs().max().item())
+    np.testing.assert_allclose(dW.cpu().numpy(), dW_ref.cpu().numpy(), rtol=1e-4, atol=1e-4 * dW_ref.abs().max().item())
+    # and the context is alive and the rendezvous works again on an idle GPU
+    dH2 = logprob.bwd_dhidden(P, W, fp32=True)
+    torch.cuda.synchronize()
+    assert torch.equal(dH2, dH)

@@ -238,3 +238,62 @@ def test_fused_softmax_backward_needs_the_default_tile_mode():
         assert e.value.code == -7
     finally:
         _lib.set_tunable("cta_pair_bwd", 2)
+
+
+EXP_CASES = [(128, 64, 256, 0, 0.0), (300, 192, 1000, 0, 3.0), (1100, 512, 5000, 0, -20.0), (640, 256, 2376, 4752, 40.0),
+             (2900, 1792, 9496, 9496, 0.0)]
+
+
+@pytest.mark.parametrize("T,H,V,v_off,shift", EXP_CASES)
+def test_exp_store_backward(T, H, V, v_off, shift):
+    """The exp-store path end to end on one vocabulary slice: K1 storing E = exp(z - ref) (statistics bit-identical to the
+    plain K1), the softmax backward in the K2a epilogue, pre-scaled hidden + K2b + deterministic one-hot scatter, against
+    torch fp32 from the exact formulas.  `shift` moves every logit (rows far from 0: the reference must follow),
+    duplicate targets exercise the scatter runs, rows with g = 0 / row_keep = 0 must come out exactly zero."""
+    from open_o3_video_b200 import logprob
+    g0 = torch.Generator().manual_seed(T + V)
+    Hd = torch.randn(T, H, generator=g0).bfloat16().cuda()
+    W = (torch.randn(V, H, generator=g0) * 0.05).bfloat16().cuda()
+    if shift:
+        W[:, 0] = 0.0
+        Hd[:, 0] = 1.0
+        W[:, 0] = (torch.full((V,), shift)).bfloat16().cuda()           # z += shift for every column
+    targets = torch.randint(0, V + 2 * v_off, (T,), generator=g0).cuda()
+    targets[5:25] = v_off + 7                                          # a run of duplicates (one dW row, 20 tokens)
+    targets[T - 3:] = v_off + V - 1
+    grad = (torch.randn(T, generator=g0) * 0.01).cuda()
+    keep = (torch.rand(T, generator=g0) > 0.3).to(torch.int32).cuda()
+    keep[T // 2:T // 2 + 40] = 0
+    grad = grad * keep
+    torch.backends.cuda.matmul.allow_tf32 = False
+    z = Hd.float() @ W.float().T
+    lse = torch.logsumexp(z, -1) + 0.3                                 # as if other slices held mass too
+    col = targets - v_off
+    inside = (col >= 0) & (col < V)
+    onehot = torch.zeros(T, V, device="cuda")
+    onehot[inside.nonzero()[:, 0], col[inside]] = 1.0
+    P = grad[:, None] * (onehot - torch.exp(z - lse[:, None]))
+    dH_ref, dW_ref = P @ W.float(), P.T @ Hd.float()
+    # K1: same statistics with and without the store, E = exp(z - ref) * keep
+    ref = logprob.row_reference(Hd, logprob.sample_weight(W), targets)
+    assert (ref >= z.max(1).values - 40).all() and (ref <= z.max(1).values + logprob.ROW_REF_MARGIN + 1e-3).all()
+    E = torch.full((T, V + 8), 7.0, dtype=torch.bfloat16, device="cuda")
+    st = logprob.lmhead_stats(Hd, W, targets, v_off, E[:, :V], row_ref=ref, row_keep=keep)
+    assert torch.equal(st, logprob.lmhead_stats(Hd, W, targets, v_off))
+    E_ref = torch.exp(z - ref[:, None]) * keep[:, None]
+    assert ((E[:, :V].float() - E_ref).abs() <= 2 ** -7 * E_ref + 1e-30).all() and (E[:, V:] == 7.0).all()
+    # backward
+    rows, order = logprob.softmax_rows(lse, grad, targets, ref, v_off, V)
+    dH = logprob.bwd_dhidden_exp(E[:, :V], rows, W, fp32=True)
+    dW = torch.full((V, H), float("nan"), device="cuda")
+    logprob.bwd_dweight_exp(E[:, :V], rows, order, Hd, dW, accumulate=False)
+    assert (dH - dH_ref).norm() <= 4e-3 * dH_ref.norm() and (dW - dW_ref).norm() <= 4e-3 * dW_ref.norm()
+    assert (dH[grad == 0] == 0).all()
+    dH16 = logprob.bwd_dhidden_exp(E[:, :V], rows, W)
+    assert dH16.dtype == torch.bfloat16 and (dH16.float() - dH_ref).norm() <= 6e-3 * dH_ref.norm()
+    # deterministic (scatter runs are summed sequentially) and accumulating
+    dW2 = torch.full((V, H), float("nan"), device="cuda")
+    logprob.bwd_dweight_exp(E[:, :V], rows, order, Hd, dW2, accumulate=False)
+    assert torch.equal(dW, dW2)
+    logprob.bwd_dweight_exp(E[:, :V], rows, order, Hd, dW, accumulate=True)
+    assert (dW - 2 * dW_ref).norm() <= 4e-3 * (2 * dW_ref).norm()

@@ -110,6 +110,35 @@ def test_fused_and_separate_softmax_backward_agree(N, Tc, chunk):
     assert (a["d_hidden"][mask.cuda() == 0] == 0).all()
 
 
+@pytest.mark.parametrize("N,Tc,chunk", [(8, 64, 128), (9, 100, 300)])
+def test_exp_store_and_dlogits_backward_agree(N, Tc, chunk):
+    """The default exp-store backward vs the round-1 dlogits pass: forward outputs bit-identical (K1's statistics do not
+    depend on what it stores), gradients equal up to the bf16 rounding of the stored operand; no launch touches the
+    [T, V] chunk between K1 and the two GEMMs."""
+    from open_o3_video_b200 import _lib, logprob
+    G = 3 if N == 9 else 2
+    hidden, weight, ids, ref, mask, rpf, old = _inputs(N, Tc, G, 256, 5000, True, seed=7)
+    args = (hidden.cuda().bfloat16(), weight.cuda().bfloat16(), ids.cuda(), ref.cuda(), mask.cuda(), rpf.cuda(), G, 0.04,
+            0.2, 0.2, True, old.cuda())
+    t = _lib.Trace()
+    _lib.trace = t
+    try:
+        a = logprob.fused_logprob_gspo(*args, chunk_tokens=chunk)
+    finally:
+        _lib.trace = None
+    names = [n for n, _ in t.calls]
+    assert "o3v_lmhead_dlogits" not in names and "o3v_lmhead_bwd_dhidden_exp" in names and "o3v_lmhead_bwd_dweight_exp" in names
+    b = logprob.fused_logprob_gspo(*args, chunk_tokens=chunk, backward="dlogits")
+    for k in ("loss", "per_token_logps", "advantages", "mean_kl"):
+        assert torch.equal(a[k], b[k]), k
+    for k in ("d_hidden", "d_weight"):
+        x, y = a[k].float(), b[k].float()
+        assert (x - y).norm() <= 5e-3 * y.norm(), k
+    assert (a["d_hidden"][mask.cuda() == 0] == 0).all()
+    c = logprob.fused_logprob_gspo(*args, chunk_tokens=chunk)         # run to run bit-stable
+    assert torch.equal(a["d_hidden"], c["d_hidden"]) and torch.equal(a["d_weight"], c["d_weight"])
+
+
 def test_c1_shape_known_answer():
     """BASELINE config 1 / SURVEY Appendix B: 7B head, 1 x 4 x 512 tokens, on-policy,
     ref = logp + 0.1, rewards [0.5, 2.0, 1.25, 3.0], full mask -> loss = 0.000207."""

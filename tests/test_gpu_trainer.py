@@ -61,13 +61,14 @@ def test_dropin_compute_loss_matches_reference_golden(host, gspo):
         assert abs(got["metrics"][k] - float(v)) <= 1e-3 * max(abs(float(v)), 1e-3), k
     model = got["model"]
     n = 4 * model.completion_len                                        # B=1 prompt x G=4 x Tc
-    k1 = [ints[0] for name, ints in got["trace"].calls if name.startswith("o3v_lmhead_fwd")]
+    k1 = [ints[0] for name, ints in got["trace"].calls             # K1 over the whole vocabulary (not the 256-row
+          if name.startswith("o3v_lmhead_fwd") and ints[1] == model.vocab]   # sample of the row reference)
     assert k1 and all(rows == n for rows in k1), k1                     # never the 4 x (Lp + Tc - 1) rows of the reference
     assert len(k1) == 2 or (host != "HostTrainerFused" and len(k1) == 3)   # policy + ref (+ recompute in backward)
     names = {name for name, _ in got["trace"].calls}
     if host != "HostTrainer":
         assert "o3v_eos_mask" in names and "o3v_gspo_fwd_bwd" in names
-    assert {"o3v_lmhead_bwd_dhidden", "o3v_lmhead_bwd_dweight"} <= names
+    assert {"o3v_lmhead_bwd_dhidden_exp", "o3v_lmhead_bwd_dweight_exp"} <= names     # the default (exp-store) backward
     assert got["trainer"].o3v_prompt_length is None
     cpu = _cpu_reference(gspo)
     for name in ("embed", "mix", "lm_head"):

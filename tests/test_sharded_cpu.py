@@ -71,3 +71,65 @@ def test_stats_exchange_protocol_gloo_world2():
         p.join(120)
         assert p.exitcode == 0
     assert out.get(timeout=5) < 1e-5
+
+
+@pytest.mark.parametrize("T,world", [(768, 8), (1000, 8), (7, 4), (131072, 8), (5, 8)])
+def test_token_owner_rows_partition(T, world):
+    from open_o3_video_b200.sharded import token_owner_rows
+    rows = [token_owner_rows(T, world, r) for r in range(world)]
+    assert rows[0][1] == 0 and rows[-1][2] == T
+    assert all(a[2] == b[1] for a, b in zip(rows, rows[1:]))           # contiguous, in rank order
+    assert all(hi - lo <= rpo for rpo, lo, hi in rows)
+    # the owner formula of the K2a epilogue (include/o3v.h): owner = min(row / rows_per_owner, P - 1)
+    rpo = rows[0][0]
+    for t in (0, T // 2, T - 1):
+        owner = min(t // rpo, world - 1)
+        assert rows[owner][1] <= t < rows[owner][2]
+
+
+def _rs_worker(rank, world, port, T, H, out):
+    """The reduce-scatter protocol of the vocab-parallel backward with the device parts replaced by torch: every rank
+    holds a partial dHidden for ALL rows, 'stores' row r into slot `rank` of the owner's buffer (here: all_to_all of
+    the owners' row ranges), the owner sums its slots in rank order."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from open_o3_video_b200.sharded import token_owner_rows
+        g = torch.Generator().manual_seed(100 + rank)
+        partial = torch.randn(T, H, generator=g).bfloat16()
+        rpo = token_owner_rows(T, world, 0)[0]
+        slot_rows = rpo
+        send = []
+        for owner in range(world):
+            _, lo, hi = token_owner_rows(T, world, owner)
+            blk = torch.zeros(slot_rows, H, dtype=torch.bfloat16)
+            blk[: hi - lo] = partial[lo:hi]
+            send.append(blk)
+        slots = [torch.empty(slot_rows, H, dtype=torch.bfloat16) for _ in range(world)]
+        dist.all_to_all(slots, send) if dist.get_backend() != "gloo" else [dist.gather(send[o], slots if rank == o else None, dst=o) for o in range(world)]
+        _, lo, hi = token_owner_rows(T, world, rank)
+        acc = torch.zeros(hi - lo, H)
+        for p in range(world):                                           # fp32 in rank order, as o3v_sum_slots_bf16
+            acc += slots[p][: hi - lo].float()
+        mine = acc.bfloat16()
+        full = partial.float().clone()
+        dist.all_reduce(full)                                            # reference: sum over ranks of all rows
+        err = (mine.float() - full[lo:hi].bfloat16().float()).abs().max().item()
+        out.put((rank, err, hi - lo))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_reduce_scatter_protocol_gloo_world2():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rs_worker, args=(r, 2, port, 101, 16, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = sorted(out.get(timeout=5) for _ in range(2))
+    assert [g[2] for g in got] == [51, 50]
+    assert all(g[1] <= 2 ** -7 for g in got)                             # summation order differs by one bf16 rounding at most
