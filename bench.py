@@ -397,7 +397,8 @@ def run_ours(args):
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
 
-    parity = parity_check(out, hidden, ids, ref, mask, rpf, G, H, V, Tc, weight, v_off, rank, world, dev)
+    parity = dict(max_err_over_tol=None, skipped="--no-parity") if args.no_parity else \
+        parity_check(out, hidden, ids, ref, mask, rpf, G, H, V, Tc, weight, v_off, rank, world, dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -482,6 +483,7 @@ def main():
                          "epilogue stores tiles at their owners) or the full dHidden (one-shot P2P all-reduce)")
     ap.add_argument("--tunable", action="append", default=[], help="name=value for o3v_set_tunable (diagnostics)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the torch fp32 self-check after the timed regions (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
