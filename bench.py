@@ -20,7 +20,8 @@ all-reduced once per step -> strong scaling, T fixed.
 `roofline`: dominant kernel (the K1 tcgen05 GEMM with fused softmax-stats epilogue), timed
             live with CUDA events around its launches inside the timed region.
 `cpu_baseline`: the oracle port of the reference's torch path (fp32) on the host cores, on
-            a bounded sample (config 1: 4 x 512 tokens of the same head).
+            a bounded sample of the same workload (one group of G rollouts at the same head,
+            2048 tokens per step).
 `--impl reference`: that CPU path alone, same JSON shape.
 """
 import argparse
@@ -96,14 +97,26 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
+def workload_name(name, cfg):
+    """config.workload: the SAME string in both arms (the reference arm times a bounded sample of this workload)."""
+    return "%s: %s head (H=%d, V=%d), %d prompts x G=%d x %d completion tokens = %d tokens/step, fused logprob+GSPO fwd+bwd" % (
+        name, cfg["head"], cfg["H"], cfg["V"], cfg["prompts"], cfg["G"], cfg["Tc"], cfg["prompts"] * cfg["G"] * cfg["Tc"])
+
+
+CPU_SAMPLE_TOKENS = 2048
+
+
 def cpu_reference(steps, warmup, head_cfg):
     """The reference's torch path on the host: oracle/logps.py (grpo_trainer.py:371-384 with the
     lm_head) + oracle/gspo.py (the inline loss block) + loss.backward() to hidden and W, fp32,
-    all host threads.  Bounded sample: config 1's 4 x 512 tokens of the benchmarked head."""
+    all host threads.  Bounded sample of the benchmarked workload: ONE group of its G rollouts at its head shape,
+    completions cut to 2048 / G tokens (2048 tokens per step = config 1's size; the per-token cost of the path does
+    not depend on the number of groups or on the completion length)."""
     from oracle import gspo as ogspo, logps as ologps, synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    H, V, N, Tc, G = head_cfg["H"], head_cfg["V"], 4, 512, 4
+    H, V, G = head_cfg["H"], head_cfg["V"], head_cfg["G"]
+    N, Tc = G, max(1, CPU_SAMPLE_TOKENS // G)
     hidden, weight, _ = synth.head_inputs(N * Tc, H, V)
     d = synth.gspo_inputs(N, Tc, G, vocab=V, eos_id=V - 1)
     ids = d["ids"] % V
@@ -128,8 +141,8 @@ def cpu_reference(steps, warmup, head_cfg):
         times.append(time.perf_counter() - t0)
     best = min(times)
     return dict(value=N * Tc / best, unit="tokens/s", cores=cores, kind="port",
-                sample="%d steps of config 1 (1 prompt x G=4 x 512 tokens, %s head, fp32, fwd+bwd), best step %.2f s"
-                       % (steps, head_cfg["head"], best)), sum(times) / len(times)
+                sample="%d steps of 1 prompt x G=%d x %d tokens (= %d tokens) of this workload, %s head, fp32, fwd+bwd to hidden "
+                       "and W, best step %.2f s" % (steps, G, Tc, N * Tc, head_cfg["head"], best)), sum(times) / len(times)
 
 
 def run_reference(args):
@@ -142,8 +155,8 @@ def run_reference(args):
     line = dict(metric=METRIC, value=base["value"], unit="tokens/s", n_gpus=args.gpus, steps=steps,
                 warmup=min(args.warmup, 1), ms_per_step=mean_s * 1e3, higher_is_better=True, scaling="strong",
                 vs_baseline=None, dtype="fp32", data="synthetic", impl="reference",
-                config=dict(workload="%s: %s head (H=%d, V=%d), bounded CPU sample of the same head" %
-                                     (args.config, cfg["head"], cfg["H"], cfg["V"]), sample=base["sample"]),
+                config=dict(workload=workload_name(args.config, cfg), parallelism="host CPU, %d threads" % base["cores"],
+                            sample=base["sample"]),
                 cpu_baseline=base,
                 e2e=dict(value=base["value"], unit="tokens/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
@@ -429,8 +442,7 @@ def run_ours(args):
         metric=METRIC, value=value, unit="tokens/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=ms_dev, higher_is_better=True, scaling="strong", vs_baseline=None,
         dtype="bf16", data="synthetic",
-        config=dict(workload="%s: %s head (H=%d, V=%d), %d prompts x G=%d x %d completion tokens = %d tokens/step, "
-                             "fused logprob+GSPO fwd+bwd" % (args.config, cfg["head"], H, V, cfg["prompts"], G, Tc, T),
+        config=dict(workload=workload_name(args.config, cfg),
                     parallelism="vocab-sharded x%d (%s exchange of softmax triples, %s of dHidden)"
                                 % (world, "fused NVLink peer-memory" if args.exchange == "peer" else "NCCL all-gather",
                                    ("reduce-scatter fused into the K2a epilogue (NVLink stores to the token owners) + local slot sum"

@@ -1,11 +1,12 @@
 // K3a (first-EOS mask) and K3 (KL + group advantages + GSPO ratio/clip/loss, fwd+bwd).
 //
 // Replaces trainer/grpo_trainer.py:590-596 and :635-636, 658, 675-681, 691-706, 711, 737
-// of the reference.  Both are HBM/launch bound (about 20 B per token).  K3 runs as two tiny
-// launches over a (slice, sequence) grid -- masked partial sums, then sequence totals in fixed
-// slice order + d loss / d logp -- with warp-shuffle reductions and a deterministic last-CTA
-// mean over the sequences, so results are run-to-run bit-stable and long sequences (16 x 16384
-// tokens) still spread over the whole GPU.
+// of the reference.  Both are launch / latency bound (about 20 B per token, a few MB per step).  K3 is ONE
+// launch over a (slice, sequence) grid: every CTA reduces the masked partial sums of its slice with warp
+// shuffles; the CTA that arrives LAST for a sequence (per-sequence ticket) adds the slices up in fixed
+// slice order, writes the per-sequence outputs and d loss / d logp of the whole sequence (its inputs are
+// L2 hits by then), and the CTA that finishes the last sequence of the step takes the mean over the
+// sequences in index order.  No CTA ever waits for another one, and results are run-to-run bit-stable.
 #include <algorithm>
 
 #include "common.cuh"
@@ -17,26 +18,40 @@ constexpr int kGspoThreads = 256;
 // ------------------------------------------------------------------------------------
 // K3a: eos_idx[n] = first t with ids[n,t]==eos else Tc; mask[n,t] = (t <= eos_idx[n]).
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kGspoThreads)
+constexpr int kEosThreads = 512;
+constexpr int kEosBatch = 8;     // independent 8-byte loads in flight per thread
+
+__global__ void __launch_bounds__(kEosThreads)
 eos_mask_kernel(const int64_t* __restrict__ ids, int64_t Tc, int64_t eos_id,
                 int64_t* __restrict__ eos_idx, int32_t* __restrict__ mask) {
-  __shared__ int s_min[kGspoThreads / 32];
+  __shared__ int s_min[kEosThreads / 32];
   const int64_t n = blockIdx.x;
   const int64_t* row = ids + n * Tc;
   int first = (int)Tc;
-  // strided scan; a thread can stop at its first hit because its indices ascend
-  for (int64_t t = threadIdx.x; t < Tc; t += kGspoThreads) {
-    if (row[t] == eos_id) { first = (int)t; break; }
+  // strided scan in batches of kEosBatch loads issued together (one memory round trip per batch instead of one
+  // per element); a thread's indices ascend, so its first hit is its minimum and it can stop there
+  for (int64_t t0 = threadIdx.x; t0 < Tc && first == (int)Tc; t0 += (int64_t)kEosThreads * kEosBatch) {
+    int64_t v[kEosBatch];
+#pragma unroll
+    for (int j = 0; j < kEosBatch; ++j) {
+      const int64_t t = t0 + (int64_t)j * kEosThreads;
+      v[j] = t < Tc ? row[t] : eos_id - 1;          // (eos_id - 1 != eos_id: never a hit)
+    }
+#pragma unroll
+    for (int j = kEosBatch - 1; j >= 0; --j) {
+      const int64_t t = t0 + (int64_t)j * kEosThreads;
+      if (t < Tc && v[j] == eos_id) first = (int)t;  // descending j: the smallest index wins
+    }
   }
   first = warp_min_i(first);
   if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = first;
   __syncthreads();
   first = s_min[0];
 #pragma unroll
-  for (int w = 1; w < kGspoThreads / 32; ++w) first = min(first, s_min[w]);
+  for (int w = 1; w < kEosThreads / 32; ++w) first = min(first, s_min[w]);
   if (threadIdx.x == 0) eos_idx[n] = (int64_t)first;
   int32_t* mrow = mask + n * Tc;
-  for (int64_t t = threadIdx.x; t < Tc; t += kGspoThreads) mrow[t] = (t <= (int64_t)first) ? 1 : 0;
+  for (int64_t t = threadIdx.x; t < Tc; t += kEosThreads) mrow[t] = (t <= (int64_t)first) ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------
@@ -53,7 +68,7 @@ struct GspoParams {
   float beta, eps_lo, eps_hi; int gspo;
   float* loss; float* mean_kl; float* adv; float* rstd; int32_t* clen;
   float* grad; float* kl_out;
-  float* seq_loss; float* seq_kl; float* partials; unsigned int* ticket;   // workspace
+  float* seq_loss; float* seq_kl; float* partials; unsigned int* ticket; unsigned int* seq_ticket;   // workspace
 };
 
 __device__ __forceinline__ float block_sum(float v, float* smem) {
@@ -98,63 +113,65 @@ __device__ __forceinline__ void group_advantage(const GspoParams& p, int64_t n, 
   adv = (mine - mean) / (sd + 1e-4f);
 }
 
-// pass 1: masked partial sums of one slice of one sequence -> partials[n][slice][4]
+// One launch: masked partial sums of (slice, sequence); the last CTA to arrive for a sequence finishes it.
 __global__ void __launch_bounds__(kGspoThreads)
-gspo_partial_kernel(const GspoParams p) {
-  __shared__ float s_red[kGspoThreads / 32];
-  __shared__ float s_bcast[2];
-  const int64_t nl = blockIdx.y, n = p.seq_offset + nl;
-  const int64_t Tc = p.Tc;
-  const int64_t t0 = (int64_t)blockIdx.x * p.slice_len, t1 = min(t0 + p.slice_len, Tc);
-  const float* lp_row = p.logp + nl * Tc;
-  const float* old_row = p.old_logp ? p.old_logp + nl * Tc : nullptr;
-  const float* ref_row = p.ref + nl * Tc;
-  const int32_t* m_row = p.mask + nl * Tc;
-  if (threadIdx.x == 0) { float a, sd; group_advantage(p, n, a, sd); s_bcast[0] = a; }
-  __syncthreads();
-  const float A = s_bcast[0];
-  float cnt = 0.f, sum_lr = 0.f, sum_kl = 0.f, sum_obj = 0.f;
-  for (int64_t t = t0 + threadIdx.x; t < t1; t += kGspoThreads) {
-    const float lp = lp_row[t], rf = ref_row[t];
-    const float m = (float)m_row[t];
-    float kl, dkl;
-    kl_and_grad(lp, rf, kl, dkl);
-    if (p.kl_out) p.kl_out[nl * Tc + t] = kl;
-    const float lr = old_row ? (lp - old_row[t]) : 0.f;     // :691 (x - x.detach() == 0 exactly)
-    cnt += m;
-    sum_lr += lr * m;
-    sum_kl += kl * m;
-    if (!p.gspo) {                                          // token-level branch :696
-      const float c1 = expf(lr);
-      const float c2 = fminf(fmaxf(c1, 1.f - p.eps_lo), 1.f + p.eps_hi);
-      sum_obj += -fminf(c1 * A, c2 * A) * m;
-    }
-  }
-  cnt = block_sum(cnt, s_red);
-  sum_lr = block_sum(sum_lr, s_red);
-  sum_kl = block_sum(sum_kl, s_red);
-  sum_obj = block_sum(sum_obj, s_red);
-  if (threadIdx.x == 0) {
-    float* part = p.partials + (n * kMaxSlices + blockIdx.x) * 4;
-    part[0] = cnt; part[1] = sum_lr; part[2] = sum_kl; part[3] = sum_obj;
-  }
-}
-
-// pass 2: sequence totals (fixed slice order), per-sequence outputs, d loss / d logp of the slice,
-// and the deterministic mean over all N sequences by the last CTA of the step
-__global__ void __launch_bounds__(kGspoThreads)
-gspo_finish_kernel(const GspoParams p) {
+gspo_kernel(const GspoParams p) {
   __shared__ float s_red[kGspoThreads / 32];
   __shared__ float s_tot[8];
   __shared__ bool s_last;
   const int64_t nl = blockIdx.y, n = p.seq_offset + nl;
   const int64_t Tc = p.Tc;
-  const int64_t t0 = (int64_t)blockIdx.x * p.slice_len, t1 = min(t0 + p.slice_len, Tc);
+  const float* __restrict__ lp_row = p.logp + nl * Tc;
+  const float* __restrict__ old_row = p.old_logp ? p.old_logp + nl * Tc : nullptr;
+  const float* __restrict__ ref_row = p.ref + nl * Tc;
+  const int32_t* __restrict__ m_row = p.mask + nl * Tc;
+  float* __restrict__ kl_row = p.kl_out ? p.kl_out + nl * Tc : nullptr;
+  {
+    // ---- this CTA's slice: masked partial sums -> partials[n][slice][4]
+    const int64_t t0 = (int64_t)blockIdx.x * p.slice_len, t1 = min(t0 + p.slice_len, Tc);
+    if (threadIdx.x == 0) { float a, sd; group_advantage(p, n, a, sd); s_tot[0] = a; }
+    __syncthreads();
+    const float A = s_tot[0];
+    float cnt = 0.f, sum_lr = 0.f, sum_kl = 0.f, sum_obj = 0.f;
+#pragma unroll 4
+    for (int64_t t = t0 + threadIdx.x; t < t1; t += kGspoThreads) {
+      const float lp = lp_row[t], rf = ref_row[t];
+      const float m = (float)m_row[t];
+      float kl, dkl;
+      kl_and_grad(lp, rf, kl, dkl);
+      if (kl_row) kl_row[t] = kl;
+      const float lr = old_row ? (lp - old_row[t]) : 0.f;     // :691 (x - x.detach() == 0 exactly)
+      cnt += m;
+      sum_lr += lr * m;
+      sum_kl += kl * m;
+      if (!p.gspo) {                                          // token-level branch :696
+        const float c1 = expf(lr);
+        const float c2 = fminf(fmaxf(c1, 1.f - p.eps_lo), 1.f + p.eps_hi);
+        sum_obj += -fminf(c1 * A, c2 * A) * m;
+      }
+    }
+    cnt = block_sum(cnt, s_red);
+    sum_lr = block_sum(sum_lr, s_red);
+    sum_kl = block_sum(sum_kl, s_red);
+    sum_obj = block_sum(sum_obj, s_red);
+    if (threadIdx.x == 0) {
+      float* part = p.partials + (n * kMaxSlices + blockIdx.x) * 4;
+      __stcg(part + 0, cnt); __stcg(part + 1, sum_lr); __stcg(part + 2, sum_kl); __stcg(part + 3, sum_obj);
+      __threadfence();
+      const unsigned int arrived = atomicAdd(p.seq_ticket + n, 1u);
+      s_last = (arrived == (unsigned int)(p.S - 1));
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+  }
+
+  // ---- last CTA of sequence n: totals in fixed slice order, per-sequence outputs, d loss / d logp
   if (threadIdx.x == 0) {
     float cnt = 0.f, sum_lr = 0.f, sum_kl = 0.f, sum_obj = 0.f;
     for (int sidx = 0; sidx < p.S; ++sidx) {
       const float* part = p.partials + (n * kMaxSlices + sidx) * 4;
-      cnt += part[0]; sum_lr += part[1]; sum_kl += part[2]; sum_obj += part[3];
+      cnt += __ldcg(part + 0); sum_lr += __ldcg(part + 1); sum_kl += __ldcg(part + 2); sum_obj += __ldcg(part + 3);
     }
     float A, sd;
     group_advantage(p, n, A, sd);
@@ -170,27 +187,24 @@ gspo_finish_kernel(const GspoParams p) {
       gate_seq = (A > 0.f) ? (c1_seq <= 1.f + p.eps_hi ? 1.f : 0.f)
                : (A < 0.f) ? (c1_seq >= 1.f - p.eps_lo ? 1.f : 0.f) : 1.f;
     }
-    if (blockIdx.x == 0) {
-      p.seq_loss[n] = (sum_obj + p.beta * sum_kl) / denom;    // :704-706
-      p.seq_kl[n] = sum_kl / cnt;                             // :737 (no clamp: 0/0 -> NaN as reference)
-      if (p.clen) p.clen[n] = (int32_t)cnt;                   // :711
-      if (p.adv) p.adv[n] = A;
-      if (p.rstd) p.rstd[n] = sd;
-    }
+    p.seq_loss[n] = (sum_obj + p.beta * sum_kl) / denom;      // :704-706
+    p.seq_kl[n] = sum_kl / cnt;                               // :737 (no clamp: 0/0 -> NaN as reference)
+    if (p.clen) p.clen[n] = (int32_t)cnt;                     // :711
+    if (p.adv) p.adv[n] = A;
+    if (p.rstd) p.rstd[n] = sd;
+    p.seq_ticket[n] = 0u;                                     // re-armed
     s_tot[0] = A; s_tot[1] = cnt; s_tot[2] = denom; s_tot[3] = c1_seq; s_tot[4] = gate_seq;
   }
   __syncthreads();
   if (p.grad) {
     const float A = s_tot[0], cnt = s_tot[1], denom = s_tot[2], c1_seq = s_tot[3], gate_seq = s_tot[4];
-    const float* lp_row = p.logp + nl * Tc;
-    const float* old_row = p.old_logp ? p.old_logp + nl * Tc : nullptr;
-    const float* ref_row = p.ref + nl * Tc;
-    const int32_t* m_row = p.mask + nl * Tc;
     const float scale = 1.f / (denom * (float)p.N);
     // GSPO: the per-token objective is constant over t, its masked mean is obj*cnt/denom,
     // and ds/dlogp_t = mask_t/denom, so the factor is (cnt/denom) * mask_t/denom.
     const float w = p.gspo ? (cnt / denom) : 1.f;
-    for (int64_t t = t0 + threadIdx.x; t < t1; t += kGspoThreads) {
+    float* __restrict__ g_row = p.grad + nl * Tc;
+#pragma unroll 4
+    for (int64_t t = threadIdx.x; t < Tc; t += kGspoThreads) {
       const float lp = lp_row[t], rf = ref_row[t];
       const float m = (float)m_row[t];
       float kl, dkl;
@@ -205,14 +219,14 @@ gspo_finish_kernel(const GspoParams p) {
                          : (A < 0.f) ? (c1 >= 1.f - p.eps_lo ? 1.f : 0.f) : 1.f;
         dobj = -A * c1 * gate;
       }
-      p.grad[nl * Tc + t] = m * scale * (dobj * w + p.beta * dkl);
+      g_row[t] = m * scale * (dobj * w + p.beta * dkl);
     }
   }
-  // ---- deterministic final reduction by the last CTA of the step (across range calls)
+  // ---- deterministic final reduction by the CTA that finishes the last sequence of the step (across range calls)
   __threadfence();
   if (threadIdx.x == 0) {
     const unsigned int done = atomicAdd(p.ticket, 1u);
-    s_last = (done == (unsigned int)(p.N * p.S - 1));
+    s_last = (done == (unsigned int)(p.N - 1));
   }
   __syncthreads();
   if (s_last) {
@@ -241,7 +255,7 @@ extern "C" int o3v_eos_mask(const int64_t* completion_ids, int64_t N, int64_t Tc
   int rc = o3v::check_device();
   if (rc) return rc;
   if (N == 0) return O3V_OK;
-  o3v::eos_mask_kernel<<<(unsigned)N, o3v::kGspoThreads, 0, (cudaStream_t)stream>>>(
+  o3v::eos_mask_kernel<<<(unsigned)N, o3v::kEosThreads, 0, (cudaStream_t)stream>>>(
       completion_ids, Tc, eos_id, eos_idx, completion_mask);
   O3V_LAUNCH_CHECK();
   return O3V_OK;
@@ -249,7 +263,7 @@ extern "C" int o3v_eos_mask(const int64_t* completion_ids, int64_t N, int64_t Tc
 
 extern "C" size_t o3v_gspo_workspace_bytes(int64_t N) {
   if (N < 0) return 0;
-  return (size_t)(2 * N + 4 + N * o3v::kMaxSlices * 4) * sizeof(float);
+  return (size_t)(3 * N + 4 + N * o3v::kMaxSlices * 4) * sizeof(float);
 }
 
 extern "C" int o3v_gspo_fwd_bwd(const float* logp, const float* old_logp, const float* ref_logp,
@@ -280,15 +294,14 @@ extern "C" int o3v_gspo_fwd_bwd(const float* logp, const float* old_logp, const 
   p.loss = loss; p.mean_kl = mean_kl; p.adv = advantages; p.rstd = reward_std; p.clen = completion_len;
   p.grad = grad_logp; p.kl_out = per_token_kl;
   float* ws = (float*)workspace;
-  p.seq_loss = ws; p.seq_kl = ws + N; p.ticket = (unsigned int*)(ws + 2 * N); p.partials = ws + 2 * N + 4;
+  p.seq_loss = ws; p.seq_kl = ws + N; p.ticket = (unsigned int*)(ws + 2 * N); p.seq_ticket = p.ticket + 4;
+  p.partials = ws + 3 * N + 4;
   cudaStream_t st = (cudaStream_t)stream;
-  // the ticket counts finished CTAs ACROSS the range calls of one step; the CTA that finishes last
-  // reduces loss / mean_kl over all N sequences in index order
-  if (seq_offset == 0) O3V_CUDA_TRY(cudaMemsetAsync(p.ticket, 0, sizeof(unsigned int), st));
+  // tickets: arrivals per sequence (the last slice CTA finishes the sequence) and finished sequences ACROSS the
+  // range calls of one step (the CTA that finishes the last one reduces loss / mean_kl over all N in index order)
+  if (seq_offset == 0) O3V_CUDA_TRY(cudaMemsetAsync(p.ticket, 0, (size_t)(4 + N) * sizeof(unsigned int), st));
   const dim3 grid((unsigned)p.S, (unsigned)n_seq);
-  o3v::gspo_partial_kernel<<<grid, o3v::kGspoThreads, 0, st>>>(p);
-  O3V_LAUNCH_CHECK();
-  o3v::gspo_finish_kernel<<<grid, o3v::kGspoThreads, 0, st>>>(p);
+  o3v::gspo_kernel<<<grid, o3v::kGspoThreads, 0, st>>>(p);
   O3V_LAUNCH_CHECK();
   return O3V_OK;
 }

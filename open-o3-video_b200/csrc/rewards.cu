@@ -4,6 +4,11 @@
 // line map).  HBM-bound: 16 lanes cooperate on one rollout (lane = prediction index, so a
 // rollout's [P]/[C] rows are read with coalesced 128-byte requests); ground truth is shared
 // by the G rollouts of a prompt and is served from L1/L2 after the first touch.
+// Memory latency, not bandwidth, is what a rollout costs (a few hundred bytes behind a chain of
+// dependent loads), so the loads are issued in TWO rounds: (1) every per-rollout / per-prompt scalar
+// and the ground-truth staging copy, none of which depends on another load; (2) the lane's own
+// timestamp, claim, claim boxes and think box, predicated on the counts and the task from round 1.
+// The branches then run on registers and shared memory (round 1 used to be ~10 dependent round trips).
 // Arithmetic follows the reference's float64 operation order; explicit __d*_rn intrinsics
 // keep nvcc from contracting mul+add into FMA so that results are bit-identical to numpy's.
 #include <algorithm>
@@ -63,15 +68,37 @@ __host__ __device__ inline size_t gt_bytes_per_prompt(const o3v_rewards_soa& s) 
 }
 
 template <bool kStageGT>
-__global__ void __launch_bounds__(kRewardThreads, 3)
+__global__ void __launch_bounds__(kRewardThreads, 2)
 rewards_kernel(const o3v_rewards_soa s, double* __restrict__ out) {
   extern __shared__ double smem_gt[];
   const int lane = threadIdx.x & (kLanes - 1);
   const int64_t r0 = (int64_t)blockIdx.x * (kRewardThreads / kLanes);
-  const int64_t r = r0 + (threadIdx.x / kLanes);
+  const int64_t r_raw = r0 + (threadIdx.x / kLanes);
+  const bool live = r_raw < s.R;
+  const int64_t r = live ? r_raw : s.R - 1;      // a group past the end only takes part in the staging barrier
   const int base = (threadIdx.x & 31) & ~(kLanes - 1);
   const unsigned gmask = 0xffffu << base;
   const int64_t q_first = r0 / s.G;
+  const int64_t q = r / s.G;
+
+  // ---- load round 1: every scalar of the rollout and of its prompt (no load depends on another one)
+  const int flags = s.flags[r];
+  const int task = s.task[q];
+  const int n_times = s.n_times[r];
+  const int nc = s.n_claims[r];
+  const int ntb = s.n_tboxes[r];
+  const unsigned tvalid = s.tbox_valid[r];
+  const int nk = s.n_kf[q];
+  const int gtf = s.gt_flags[q];
+  const double sp = s.step_percent[q];
+  const double as0 = s.ans_seg[r * 2], as1 = s.ans_seg[r * 2 + 1];
+  const double gs0 = s.gt_seg[q * 2], gs1 = s.gt_seg[q * 2 + 1];
+  const double W = s.image_size[q * 2], H = s.image_size[q * 2 + 1];
+  const double rw = s.image_refine[q * 2], rh = s.image_refine[q * 2 + 1];
+  double vraw[4], abox[4];
+  load4(s.gt_vbox + q * 4, vraw);
+  load4(s.ans_box + r * 4, abox);
+
   if constexpr (kStageGT) {
     const int64_t r_last = min(r0 + kRewardThreads / kLanes, s.R) - 1;
     const int nq = (int)(r_last / s.G - q_first) + 1;
@@ -90,10 +117,39 @@ rewards_kernel(const o3v_rewards_soa s, double* __restrict__ out) {
       int32_t* dst = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(smem_gt) + pq * stride + (size_t)nd * 8);
       dst[j] = (j < s.K) ? s.n_obj[qq * s.K + j] : s.n_gtbox[qq * (int64_t)(ni - s.K) + (j - s.K)];
     }
-    __syncthreads();
   }
-  if (r >= s.R) return;   // whole 16-lane group leaves together
-  const int64_t q = r / s.G;
+
+  const bool has_think = flags & O3V_RF_HAS_THINK;
+  const bool has_answer = flags & O3V_RF_HAS_ANSWER;
+  const bool general = (task == O3V_TASK_GENERAL_MCQ || task == O3V_TASK_GENERAL_FREEFORM);
+  const bool temporal = (task == O3V_TASK_TEMPORAL_QA || task == O3V_TASK_TEMPORAL_QA_MCQ);
+  const bool visual = (task == O3V_TASK_VISUAL_QA);
+  const bool do_seg = has_think && !(visual || task == O3V_TASK_TS_FREEFORM || general);      // reward_func.py:396
+  const bool do_point = has_think && !(visual || temporal || general) && n_times > 0;         // :439
+  const bool do_vthink = has_think && has_answer && visual;                                    // :490
+  const bool do_claims = has_think && has_answer && !visual && !(temporal || general);         // :528
+
+  // ---- load round 2: this lane's timestamp / claim / boxes of the first 16-wide batch, predicated on round 1
+  double t_mine = 0.0;
+  if ((do_seg || do_point) && lane < n_times) t_mine = s.think_times[r * s.P + lane];
+  double ct_mine = 0.0;
+  int cnb_mine = 0;
+  unsigned cval_mine = 0u;
+  double cb0_mine[4] = {0, 0, 0, 0}, cb1_mine[4] = {0, 0, 0, 0};
+  if (do_claims && lane < nc) {
+    ct_mine = s.claim_t[r * s.C + lane];
+    cnb_mine = s.claim_nbox[r * s.C + lane];
+    cval_mine = s.claim_valid[r * s.C + lane];
+    const double* cb = s.claim_box + ((r * s.C + lane) * (int64_t)s.Bc) * 4;   // slots exist up to Bc whatever the count
+    if (s.Bc > 0) load4(cb, cb0_mine);
+    if (s.Bc > 1) load4(cb + 4, cb1_mine);
+  }
+  double tb_mine[4] = {0, 0, 0, 0};
+  if (do_vthink && lane < ntb) load4(s.think_box + (r * s.Tb + lane) * 4, tb_mine);
+
+  if constexpr (kStageGT) __syncthreads();
+  if (!live) return;   // whole 16-lane group leaves together
+
   // per-prompt GT arrays: shared-memory copies when staged, else the global arrays
   const double* kft; const double* gtb; const int32_t* nobj_p; const int32_t* ngt_p;
   if constexpr (kStageGT) {
@@ -109,19 +165,11 @@ rewards_kernel(const o3v_rewards_soa s, double* __restrict__ out) {
     ngt_p = s.n_gtbox + q * (int64_t)s.K * s.O;
   }
 
-  const int flags = s.flags[r];
-  const int task = s.task[q];
-  const bool has_think = flags & O3V_RF_HAS_THINK;
-  const bool has_answer = flags & O3V_RF_HAS_ANSWER;
-  const bool general = (task == O3V_TASK_GENERAL_MCQ || task == O3V_TASK_GENERAL_FREEFORM);
-  const bool temporal = (task == O3V_TASK_TEMPORAL_QA || task == O3V_TASK_TEMPORAL_QA_MCQ);
-
   double r_tiou = 0.0, r_viou = 0.0, r_seg = 0.0, r_point = 0.0, r_spatial = 0.0;
 
   // ---- ans_tiou_reward (reward_func.py:99-143)
   if (temporal && (flags & O3V_RF_ANS_SEG)) {
-    const double s1 = s.ans_seg[r * 2], e1 = s.ans_seg[r * 2 + 1];
-    const double s2 = s.gt_seg[q * 2], e2 = s.gt_seg[q * 2 + 1];
+    const double s1 = as0, e1 = as1, s2 = gs0, e2 = gs1;
     if (!(e1 < s1)) {                                                   // :128
       const double inter = fmax(0.0, dsub(fmin(e1, e2), fmax(s1, s2))); // :138-140
       const double uni = dsub(fmax(e1, e2), fmin(s1, s2));              // :141
@@ -131,43 +179,29 @@ rewards_kernel(const o3v_rewards_soa s, double* __restrict__ out) {
 
   // GT box of the visual-QA tasks, rescaled (convert_coord_format_gqa, :349-354)
   double gvb[4] = {0, 0, 0, 0};
-  const bool has_gvb = (task == O3V_TASK_VISUAL_QA) && (s.gt_flags[q] & O3V_GF_VBOX);
+  const bool has_gvb = visual && (gtf & O3V_GF_VBOX);
   if (has_gvb) {
-    double raw[4];
-    load4(s.gt_vbox + q * 4, raw);
-    const double W = s.image_size[q * 2], H = s.image_size[q * 2 + 1];
-    const double rw = s.image_refine[q * 2], rh = s.image_refine[q * 2 + 1];
-    gvb[0] = __ddiv_rn(dmul(raw[0], rw), W); gvb[1] = __ddiv_rn(dmul(raw[1], rh), H);
-    gvb[2] = __ddiv_rn(dmul(raw[2], rw), W); gvb[3] = __ddiv_rn(dmul(raw[3], rh), H);
+    gvb[0] = __ddiv_rn(dmul(vraw[0], rw), W); gvb[1] = __ddiv_rn(dmul(vraw[1], rh), H);
+    gvb[2] = __ddiv_rn(dmul(vraw[2], rw), W); gvb[3] = __ddiv_rn(dmul(vraw[3], rh), H);
   }
 
   // ---- ans_viou_reward (:196-226)
-  if (has_gvb && (flags & O3V_RF_ANS_BOX)) {
-    double pb[4];
-    load4(s.ans_box + r * 4, pb);
-    r_viou = box_iou(gvb, pb);
-  }
-
-  const int n_times = s.n_times[r];
+  if (has_gvb && (flags & O3V_RF_ANS_BOX)) r_viou = box_iou(gvb, abox);
 
   // ---- thk_temporal_segment_reward (:396, :416-420)
-  if (has_think && !(task == O3V_TASK_VISUAL_QA || task == O3V_TASK_TS_FREEFORM || general)) {
-    const double g0 = s.gt_seg[q * 2], g1 = s.gt_seg[q * 2 + 1];
+  if (do_seg) {
     int hits = 0;
     for (int p = lane; p < n_times; p += kLanes) {
-      const double t = s.think_times[r * s.P + p];
-      hits += (g0 <= t && t <= g1) ? 1 : 0;
+      const double t = (p == lane) ? t_mine : s.think_times[r * s.P + p];
+      hits += (gs0 <= t && t <= gs1) ? 1 : 0;
     }
 #pragma unroll
     for (int o = kLanes / 2; o > 0; o >>= 1) hits += __shfl_xor_sync(gmask, hits, o);
     if (n_times > 0) r_seg = __ddiv_rn((double)hits, (double)n_times);   // exact small integers
   }
 
-  const int nk = s.n_kf[q];
-
   // ---- thk_temporal_point_reward: adaptive temporal proximity (:439, :452-467)
-  if (has_think && !(task == O3V_TASK_VISUAL_QA || temporal || general) && n_times > 0) {
-    const double sp = s.step_percent[q];
+  if (do_point) {
     const double sigma = (sp < 0.75) ? dmul(4.0, dsub(1.0, sp)) : 1.0;  // :459-462
     const double two_s2 = dmul(2.0, dmul(sigma, sigma));
     double total = 0.0;
@@ -175,7 +209,7 @@ rewards_kernel(const o3v_rewards_soa s, double* __restrict__ out) {
       const int p = p0 + lane;
       double score = 0.0;
       if (p < n_times) {
-        const double t = s.think_times[r * s.P + p];
+        const double t = (p0 == 0) ? t_mine : s.think_times[r * s.P + p];
         double d = INFINITY;
         for (int k = 0; k < nk; ++k) d = fmin(d, fabs(dsub(t, kft[k])));   // :457
         score = exp(__ddiv_rn(-dmul(d, d), two_s2));                       // :463
@@ -186,90 +220,92 @@ rewards_kernel(const o3v_rewards_soa s, double* __restrict__ out) {
   }
 
   // ---- thk_spatial_reward (:484-603)
-  if (has_think && has_answer) {
-    if (task == O3V_TASK_VISUAL_QA) {                                      // :490-525
-      const int nb = s.n_tboxes[r];
-      if (nb > 0 && has_gvb) {
-        const unsigned valid = s.tbox_valid[r];
-        double best = 0.0;
-        for (int b = lane; b < nb; b += kLanes) {
-          double pb[4];
-          if (b < 32 ? ((valid >> b) & 1u) != 0u : box_slot_valid(s.think_box + (r * s.Tb + b) * 4)) {
+  if (do_vthink) {                                                         // :490-525
+    if (ntb > 0 && has_gvb) {
+      double best = 0.0;
+      for (int b = lane; b < ntb; b += kLanes) {
+        if (b < 32 ? ((tvalid >> b) & 1u) != 0u : box_slot_valid(s.think_box + (r * s.Tb + b) * 4)) {
+          if (b == lane) {
+            best = fmax(best, box_iou(gvb, tb_mine));
+          } else {
+            double pb[4];
             load4(s.think_box + (r * s.Tb + b) * 4, pb);
             best = fmax(best, box_iou(gvb, pb));
           }
         }
+      }
 #pragma unroll
-        for (int o = kLanes / 2; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(gmask, best, o));
-        r_spatial = best;
-      }
-    } else if (!(temporal || general)) {                                   // :528
-      const int nc = s.n_claims[r];
-      if (nc > 0) {
-        const double W = s.image_size[q * 2], H = s.image_size[q * 2 + 1];
-        double total = 0.0;
-        for (int c0 = 0; c0 < nc; c0 += kLanes) {
-          const int c = c0 + lane;
-          double score = 0.0;
-          if (c < nc) {
-            const double t = s.claim_t[r * s.C + c];
-            // temporal gating (:550-560): one-sided signed test, strict '<' keeps the first
-            int kbest = -1;
-            double dbest = INFINITY, tbest = -1.0;
-            for (int k = 0; k < nk; ++k) {
-              const double g = kft[k];
-              if (dsub(g, t) < 1.0) {
-                const double d = fabs(dsub(g, t));
-                if (d < dbest) { dbest = d; tbest = g; kbest = k; }
-              }
-            }
-            // :561 sentinel compare on the VALUE (a key frame at exactly -1 s is "none")
-            if (kbest >= 0 && tbest != -1.0) {
-              // :566-569 first key frame whose time equals the chosen one
-              int kf = kbest;
-              for (int k = 0; k < nk; ++k) if (kft[k] == tbest) { kf = k; break; }
-              const int nb = s.claim_nbox[r * s.C + c];
-              const unsigned valid = s.claim_valid[r * s.C + c];
-              const double* cb = s.claim_box + ((r * s.C + c) * (int64_t)s.Bc) * 4;
-              double cb0[4] = {0, 0, 0, 0}, cb1[4] = {0, 0, 0, 0};          // the common case: <= 2 boxes per claim
-              if (nb > 0) load4(cb, cb0);
-              if (nb > 1) load4(cb + 4, cb1);
-              const int nobj = nobj_p[kf];
-              double max_iou = 0.0;
-              for (int o = 0; o < nobj; ++o) {                              // :575
-                const int ng = ngt_p[kf * s.O + o];
-                if (ng <= 0) continue;                                      // :596 empty list
-                double acc = 0.0;
-                for (int gi = 0; gi < ng; ++gi) {                           // :590
-                  double nb4[4], g4[4];
-                  load4(gtb + (((kf * s.O + o) * s.Gb) + gi) * 4, nb4);
-                  g4[0] = dmul(nb4[0], W); g4[1] = dmul(nb4[1], H);         // :337-346
-                  g4[2] = dmul(nb4[2], W); g4[3] = dmul(nb4[3], H);
-                  double best = 0.0;
-                  bool first = true;
-                  for (int b = 0; b < nb; ++b) {                            // :592-593 max(list)
-                    double v = 0.0;
-                    if (b < 32 ? ((valid >> b) & 1u) != 0u : box_slot_valid(cb + b * 4)) {
-                      if (b == 0) v = box_iou(g4, cb0);
-                      else if (b == 1) v = box_iou(g4, cb1);
-                      else { double pb[4]; load4(cb + b * 4, pb); v = box_iou(g4, pb); }
-                    }
-                    best = first ? v : fmax(best, v);
-                    first = false;
-                  }
-                  acc = dadd(acc, best);                                    // :597 sum(...)
-                }
-                const double iou = __ddiv_rn(acc, (double)ng);
-                if (iou > max_iou) max_iou = iou;                           // :598-599
-              }
-              score = max_iou;
-            }
-          }
-          total = ordered_group_sum(score, min(kLanes, nc - c0), base, gmask, total);   // :601
-        }
-        r_spatial = __ddiv_rn(total, (double)nc);                           // :603
-      }
+      for (int o = kLanes / 2; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(gmask, best, o));
+      r_spatial = best;
     }
+  } else if (do_claims && nc > 0) {
+    double total = 0.0;
+    for (int c0 = 0; c0 < nc; c0 += kLanes) {
+      const int c = c0 + lane;
+      double score = 0.0;
+      if (c < nc) {
+        const bool pre = (c0 == 0);                                        // first batch: loaded in round 2
+        const double t = pre ? ct_mine : s.claim_t[r * s.C + c];
+        // temporal gating (:550-560): one-sided signed test, strict '<' keeps the first
+        int kbest = -1;
+        double dbest = INFINITY, tbest = -1.0;
+        for (int k = 0; k < nk; ++k) {
+          const double g = kft[k];
+          if (dsub(g, t) < 1.0) {
+            const double d = fabs(dsub(g, t));
+            if (d < dbest) { dbest = d; tbest = g; kbest = k; }
+          }
+        }
+        // :561 sentinel compare on the VALUE (a key frame at exactly -1 s is "none")
+        if (kbest >= 0 && tbest != -1.0) {
+          // :566-569 first key frame whose time equals the chosen one
+          int kf = kbest;
+          for (int k = 0; k < nk; ++k) if (kft[k] == tbest) { kf = k; break; }
+          const int nb = pre ? cnb_mine : s.claim_nbox[r * s.C + c];
+          const unsigned valid = pre ? cval_mine : s.claim_valid[r * s.C + c];
+          const double* cb = s.claim_box + ((r * s.C + c) * (int64_t)s.Bc) * 4;
+          double cb0[4] = {0, 0, 0, 0}, cb1[4] = {0, 0, 0, 0};          // the common case: <= 2 boxes per claim
+          if (pre) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { cb0[j] = cb0_mine[j]; cb1[j] = cb1_mine[j]; }
+          } else {
+            if (nb > 0) load4(cb, cb0);
+            if (nb > 1) load4(cb + 4, cb1);
+          }
+          const int nobj = nobj_p[kf];
+          double max_iou = 0.0;
+          for (int o = 0; o < nobj; ++o) {                              // :575
+            const int ng = ngt_p[kf * s.O + o];
+            if (ng <= 0) continue;                                      // :596 empty list
+            double acc = 0.0;
+            for (int gi = 0; gi < ng; ++gi) {                           // :590
+              double nb4[4], g4[4];
+              load4(gtb + (((kf * s.O + o) * s.Gb) + gi) * 4, nb4);
+              g4[0] = dmul(nb4[0], W); g4[1] = dmul(nb4[1], H);         // :337-346
+              g4[2] = dmul(nb4[2], W); g4[3] = dmul(nb4[3], H);
+              double best = 0.0;
+              bool first = true;
+              for (int b = 0; b < nb; ++b) {                            // :592-593 max(list)
+                double v = 0.0;
+                if (b < 32 ? ((valid >> b) & 1u) != 0u : box_slot_valid(cb + b * 4)) {
+                  if (b == 0) v = box_iou(g4, cb0);
+                  else if (b == 1) v = box_iou(g4, cb1);
+                  else { double pb[4]; load4(cb + b * 4, pb); v = box_iou(g4, pb); }
+                }
+                best = first ? v : fmax(best, v);
+                first = false;
+              }
+              acc = dadd(acc, best);                                    // :597 sum(...)
+            }
+            const double iou = __ddiv_rn(acc, (double)ng);
+            if (iou > max_iou) max_iou = iou;                           // :598-599
+          }
+          score = max_iou;
+        }
+      }
+      total = ordered_group_sum(score, min(kLanes, nc - c0), base, gmask, total);   // :601
+    }
+    r_spatial = __ddiv_rn(total, (double)nc);                           // :603
   }
 
   if (lane == 0) {

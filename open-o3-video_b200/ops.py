@@ -11,6 +11,8 @@ operator body is a call into libo3v.so through the wrappers of this package.
         -> (logp[T] f32, lse[T] f32, logits[T,V] bf16 or [0,V])                      K1 + merge
   o3v::lmhead_logprob_backward(grad_logp, hidden, weight, targets, lse, logits, v_offset, chunk_tokens)
         -> (d_hidden[T,H] bf16, d_weight[V,H] f32)                                   dlogits + K2a + K2b
+        (the operators keep the bf16 logits and run the in-place softmax-backward pass: the "dlogits" mode of
+        logprob.BACKWARD; the wrappers default to the exp-store mode, same parity bar)
   o3v::eos_mask(completion_ids[N,Tc] i64, eos_id) -> (eos_idx[N] i64, mask[N,Tc] i32)   K3a
   o3v::gspo_objective(logp, ref, mask, rewards_per_func, old?, G, beta, eps_lo, eps_hi, gspo)
         -> (loss[], grad_logp[N,Tc], advantages[N], mean_kl[], completion_len[N] i32, reward_std[N])   K3

@@ -72,7 +72,7 @@ def test_argument_validation_without_gpu(lib):
     assert lib.o3v_parse_workspace_bytes(4, 2, 3, 1) == 4 * 40 + 16 + 4 * (2 + 3 + 1) * 4
     assert lib.o3v_set_tunable(b"nope", 1) == -1
     assert lib.o3v_lmhead_fwd_workspace_bytes(128, 1024, 64) == 4 * 3 * 128 * 4
-    assert lib.o3v_gspo_workspace_bytes(8) == (2 * 8 + 4 + 8 * 32 * 4) * 4
+    assert lib.o3v_gspo_workspace_bytes(8) == (3 * 8 + 4 + 8 * 32 * 4) * 4
 
 
 def test_sass_is_blackwell_native():

@@ -42,7 +42,7 @@ def test_ops_refuse_cpu_tensors():
 
 
 @pytest.mark.gpu
-def test_ops_match_the_wrappers_and_pass_opcheck():
+def test_ops_match_the_wrappers_and_pass_opcheck(monkeypatch):
     from open_o3_video_b200 import gspo, logprob, ops
     T, H, V = 200, 256, 5000
     hidden, weight, targets = synth.head_inputs(T, H, V, seed=3)
@@ -51,6 +51,9 @@ def test_ops_match_the_wrappers_and_pass_opcheck():
     t = targets.cuda()
     ha, wa = h.clone().requires_grad_(True), w.clone().requires_grad_(True)
     hb, wb = h.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    # the registered operators keep the bf16 LOGITS and run the in-place softmax-backward pass ("dlogits" mode of the
+    # wrappers: bit-identical); the wrappers' default "exp" mode keeps exp(z - ref) instead (same bf16 bar)
+    monkeypatch.setattr(logprob, "BACKWARD", "dlogits")
     la = logprob.fused_logprob(ha, wa, t)
     lb = ops.fused_logprob(hb, wb, t)
     assert torch.equal(la, lb)
@@ -58,6 +61,13 @@ def test_ops_match_the_wrappers_and_pass_opcheck():
     la.backward(g)
     lb.backward(g)
     assert torch.equal(ha.grad, hb.grad) and torch.equal(wa.grad, wb.grad)
+    monkeypatch.setattr(logprob, "BACKWARD", "exp")
+    hc, wc = h.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    lc = logprob.fused_logprob(hc, wc, t)
+    assert torch.equal(lc, lb)
+    lc.backward(g)
+    for a, b in ((hc.grad, hb.grad), (wc.grad, wb.grad)):
+        assert ((a.float() - b.float()).norm() / b.float().norm()).item() < 1e-2
     # recompute path of the backward operator (forward kept no logits) == saved-logits path
     lp, lse, _ = torch.ops.o3v.lmhead_logprob(h, w, t, 0, False)
     dh, dw = torch.ops.o3v.lmhead_logprob_backward(g, h, w, t, lse, torch.empty(0, V, dtype=torch.bfloat16, device="cuda"),
