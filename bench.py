@@ -42,6 +42,10 @@ CONFIGS = {
     "c3": dict(head="qwen3-vl-8b", H=4096, V=151936, prompts=16, G=8, Tc=4096),
     "c5": dict(head="qwen3-vl-8b", H=4096, V=151936, prompts=1, G=16, Tc=16384),
     "c1": dict(head="qwen2.5-vl-7b", H=3584, V=152064, prompts=1, G=4, Tc=512),
+    # diagnostics: ONE rank's share of c2 / c3 at 8 GPUs (its 1/8 vocabulary slice, every token) on a single GPU, i.e.
+    # the per-rank kernel shapes of the 8-GPU run without any communication
+    "c2s8": dict(head="qwen2.5-vl-7b, 1/8 vocab slice", H=3584, V=19008, prompts=8, G=8, Tc=2048),
+    "c3s8": dict(head="qwen3-vl-8b, 1/8 vocab slice", H=4096, V=18992, prompts=16, G=8, Tc=4096),
     "tiny": dict(head="tiny", H=256, V=8192, prompts=2, G=4, Tc=128),
     # what ONE rank of the reference's own launch sees per step (per-device batch of 1 prompt x 8 generations)
     "dev": dict(head="qwen2.5-vl-7b", H=3584, V=152064, prompts=1, G=8, Tc=2048),
@@ -412,6 +416,12 @@ def run_ours(args):
 
     parity = dict(max_err_over_tol=None, skipped="--no-parity") if args.no_parity else \
         parity_check(out, hidden, ids, ref, mask, rpf, G, H, V, Tc, weight, v_off, rank, world, dev)
+    shares_ranks = None
+    if world > 1:                                           # every rank's per-kernel milliseconds (load balance / skew)
+        mine = {k: sum(v) / args.steps for k, v in durs.items()}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        shares_ranks = {k: [round(g.get(k, 0.0), 3) for g in gathered] for k in mine}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -445,8 +455,9 @@ def run_ours(args):
         config=dict(workload=workload_name(args.config, cfg),
                     parallelism="vocab-sharded x%d (%s exchange of softmax triples, %s of dHidden)"
                                 % (world, "fused NVLink peer-memory" if args.exchange == "peer" else "NCCL all-gather",
-                                   ("reduce-scatter fused into the K2a epilogue (NVLink stores to the token owners) + local slot sum"
-                                    if args.dh_collective == "reduce_scatter" else "one-shot P2P all-reduce beside the dW GEMM")
+                                   {"reduce_scatter": "reduce-scatter by peer-memory pull (owners load their token rows over NVLink) beside the dW GEMM",
+                                    "reduce_scatter_fused": "reduce-scatter fused into the K2a epilogue (NVLink stores to the token owners) + local slot sum",
+                                    "all_reduce": "one-shot P2P all-reduce beside the dW GEMM"}[args.dh_collective]
                                    if (args.exchange == "peer" and args.overlap_allreduce) else "NCCL all-reduce")
                     if world > 1 else "single GPU", chunk_tokens=args.chunk_tokens,
                     cache="inputs (%.1f GB) and per-chunk logits are far larger than the 126 MB L2; no flush needed"
@@ -457,7 +468,7 @@ def run_ours(args):
                       achieved=ach, peak=pk["sustained"], unit="TFLOP/s", frac=ach / pk["sustained"],
                       frac_of_burst=ach / pk["burst"], peak_source=pk["source"] + " (sustained: kernel timed inside a long step)",
                       ms_per_launch=k1_ms, traffic=traffic, traffic_detail=traffic_detail),
-        kernel_ms_per_step=shares,
+        kernel_ms_per_step=shares, **({"kernel_ms_per_step_ranks": shares_ranks} if shares_ranks else {}),
         e2e=dict(value=T / (ms_e2e * 1e-3), unit="tokens/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                  ms_per_step=ms_e2e, gather=gather),
         gpu_launches=launches, clocks=clocks, parity=parity, parity_max_err=parity["max_err_over_tol"])
@@ -490,9 +501,10 @@ def main():
                     help="N > 1: forward exchange of the softmax triples (peer = fused NVLink merge kernel)")
     ap.add_argument("--overlap-allreduce", type=int, default=1,
                     help="N > 1 with --exchange peer: one-shot P2P all-reduce of dHidden beside the dW GEMM (0 = NCCL)")
-    ap.add_argument("--dh-collective", default="reduce_scatter", choices=["reduce_scatter", "all_reduce"],
-                    help="N > 1: every rank gets ITS token rows of dHidden (data-parallel layout, SURVEY 8e; the K2a "
-                         "epilogue stores tiles at their owners) or the full dHidden (one-shot P2P all-reduce)")
+    ap.add_argument("--dh-collective", default="reduce_scatter", choices=["reduce_scatter", "reduce_scatter_fused", "all_reduce"],
+                    help="N > 1: every rank gets ITS token rows of dHidden (data-parallel layout, SURVEY 8e): owners pull "
+                         "their rows from the peers' partial buffers beside the dW GEMM (default), or the K2a epilogue "
+                         "stores tiles at their owners (fused); or the full dHidden (one-shot P2P all-reduce)")
     ap.add_argument("--tunable", action="append", default=[], help="name=value for o3v_set_tunable (diagnostics)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the torch fp32 self-check after the timed regions (profiling runs)")

@@ -119,6 +119,14 @@ int o3v_lmhead_merge_stats_peers(const float* const* part_ptrs, int64_t P, int64
 int o3v_allreduce_bf16_peers(void* const* bufs, int64_t P, int64_t rank, int64_t n_elems, int32_t num_ctas,
                              void* stream);
 
+/* Reduce-scatter (sum) by pull over the same replicated buffers: out[i] = sum_p bufs[p][elem_offset + i] for
+ * i in [0, n_elems), fp32 in rank order, one bf16 rounding, written to the LOCAL `out` only.  Each token owner
+ * calls it for ITS rows of dHidden (the data-parallel layout only needs the reduce-scatter half of
+ * the all-reduce: half the NVLink bytes, no write fan-out).  Same co-residency properties and the same barrier
+ * bracketing as o3v_allreduce_bf16_peers.  elem_offset % 8 == 0, n_elems % 8 == 0, out 16-byte aligned. */
+int o3v_reduce_scatter_bf16_peers(void* const* bufs, int64_t P, int64_t elem_offset, int64_t n_elems, void* out,
+                                  int32_t num_ctas, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * K2  chunked fused backward of K1 (replaces the autograd backward of
  * grpo_trainer.py:375-383: softmax-backward + two GEMMs).

@@ -237,6 +237,38 @@ allreduce_bf16_peers_kernel(const PeerBufs bufs, int P, int64_t v0, int64_t v1) 
   }
 }
 
+// Reduce-scatter by PULL: out[i] = sum_p bufs[p][v0 + i] for this rank's vectors, fp32 in rank order, one bf16 rounding,
+// stored LOCALLY only (no write fan-out: half the NVLink bytes of the all-reduce above).  Same footprint as the
+// all-reduce kernel (no shared memory, few registers) so that it runs beside the persistent dW GEMM.
+__global__ void __launch_bounds__(kArThreads, 4)
+reduce_scatter_bf16_peers_kernel(const PeerBufs bufs, int P, int64_t v0, int64_t n_vecs, uint4* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * kArThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kArThreads + threadIdx.x; i < n_vecs; i += stride) {
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int p0 = 0; p0 < P; p0 += 4) {
+      uint4 a[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (p0 + j < P) a[j] = __ldcv(bufs.p[p0 + j] + v0 + i);   // four NVLink loads in flight
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (p0 + j < P) {                                        // fixed rank order: deterministic
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a[j]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 f = __bfloat1622float2(h[k]);
+            s[2 * k] += f.x; s[2 * k + 1] += f.y;
+          }
+        }
+    }
+    uint4 r;
+    __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = __floats2bfloat162_rn(s[2 * k], s[2 * k + 1]);
+    out[i] = r;
+  }
+}
+
 // Sum of the P slot copies [P][slot_rows][H] (bf16, this rank's buffer: slot p was written by rank p's K2a epilogue over
 // NVLink) into out[rows][H]: fp32 in rank order (deterministic), one bf16 rounding.  Local HBM traffic only.
 __global__ void __launch_bounds__(256)
@@ -509,6 +541,28 @@ extern "C" int o3v_allreduce_bf16_peers(void* const* bufs, int64_t P, int64_t ra
   int ctas = num_ctas > 0 ? num_ctas : 2 * num_sms();
   ctas = (int)std::min<int64_t>(ctas, ceil_div(v1 - v0, kArThreads));
   allreduce_bf16_peers_kernel<<<ctas, kArThreads, 0, (cudaStream_t)stream>>>(pb, (int)P, v0, v1);
+  O3V_LAUNCH_CHECK();
+  return O3V_OK;
+}
+
+extern "C" int o3v_reduce_scatter_bf16_peers(void* const* bufs, int64_t P, int64_t elem_offset, int64_t n_elems,
+                                             void* out, int32_t num_ctas, void* stream) {
+  if (!bufs || !out || P <= 0 || P > 16 || elem_offset < 0 || n_elems < 0 || (n_elems % 8) != 0 || (elem_offset % 8) != 0)
+    return O3V_ERR_INVALID_ARG;
+  if (reinterpret_cast<uintptr_t>(out) & 15u) return O3V_ERR_ALIGNMENT;
+  int rc = check_device();
+  if (rc) return rc;
+  if (n_elems == 0) return O3V_OK;
+  PeerBufs pb = {};
+  for (int64_t i = 0; i < P; ++i) {
+    if (!bufs[i] || (reinterpret_cast<uintptr_t>(bufs[i]) & 15u)) return O3V_ERR_ALIGNMENT;
+    pb.p[i] = reinterpret_cast<uint4*>(bufs[i]);
+  }
+  const int64_t nvec = n_elems / 8;
+  int ctas = num_ctas > 0 ? num_ctas : 2 * num_sms();
+  ctas = (int)std::min<int64_t>(ctas, ceil_div(nvec, kArThreads));
+  reduce_scatter_bf16_peers_kernel<<<ctas, kArThreads, 0, (cudaStream_t)stream>>>(pb, (int)P, elem_offset / 8, nvec,
+                                                                                  reinterpret_cast<uint4*>(out));
   O3V_LAUNCH_CHECK();
   return O3V_OK;
 }

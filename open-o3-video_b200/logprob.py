@@ -397,7 +397,7 @@ def fused_logprob_gspo(hidden: torch.Tensor, weight: torch.Tensor, completion_id
     hidden [N, Tc, H] bf16: final hidden states at the positions that PREDICT each completion
     token; completion_ids / ref / mask / old: [N, Tc]; rewards_per_func [N, F].
     Returns dict(loss, per_token_logps, advantages, mean_kl, completion_length, reward_std,
-    d_hidden [N, Tc, H] bf16, d_weight [V, H] fp32).  With `group=` a `sharded.PeerExchange(dh_mode="reduce_scatter")`
+    d_hidden [N, Tc, H] bf16, d_weight [V, H] fp32).  With `group=` a `sharded.PeerExchange(dh_mode="reduce_scatter" / "reduce_scatter_fused")`
     d_hidden is [hi - lo, H]: the token rows `d_hidden_rows = (lo, hi)` this rank owns (data-parallel layout).
 
     Per chunk (`backward="exp"`, the default `BACKWARD`): row reference (K1 on 256 sampled vocabulary rows) -> K1 storing
@@ -432,8 +432,9 @@ def fused_logprob_gspo(hidden: torch.Tensor, weight: torch.Tensor, completion_id
     zbuf = torch.empty(seqs * Tc, V, dtype=torch.bfloat16, device=dev) if need_grad else None
     d_hidden = None
     peer_dh = False
-    scatter_dh = bool(need_grad and _is_peer(group) and getattr(group, "dh_mode", "") == "reduce_scatter"
-                      and group.hidden_size == H)
+    dh_mode = getattr(group, "dh_mode", "") if (need_grad and _is_peer(group) and group.hidden_size == H) else ""
+    scatter_dh = dh_mode == "reduce_scatter_fused"          # K2a epilogue stores tiles at their owners
+    pull_dh = dh_mode == "reduce_scatter"                   # owners pull their rows beside the dW GEMM
     if scatter_dh and fuse_dlogits:
         raise ValueError("fuse_dlogits and the reduce-scatter K2a cannot be combined")
     if need_grad and not scatter_dh:
@@ -467,7 +468,9 @@ def fused_logprob_gspo(hidden: torch.Tensor, weight: torch.Tensor, completion_id
                 dh_owned[0] = group.dhidden_reduce_async(N * Tc)
         else:
             bwd_dhidden_exp(z, rows, weight, out=d_hidden[s:e])
-        if peer_dh:
+        if pull_dh:
+            dh_owned[0] = group.reduce_scatter_dh_async(s, e - s, N * Tc)
+        elif peer_dh:
             group.allreduce_dh_async(s, e - s)
         bwd_dweight_exp(z, rows, order, hidden2[s:e], d_weight, (ci > 0) or (d_weight_out is not None), scratch)
 
@@ -478,7 +481,9 @@ def fused_logprob_gspo(hidden: torch.Tensor, weight: torch.Tensor, completion_id
                 dh_owned[0] = group.dhidden_reduce_async(N * Tc)   # barrier + local slot sum beside the dW GEMM below
         else:
             bwd_dhidden(z, weight, out=d_hidden[s:e], softmax_bwd=sb)
-        if peer_dh:
+        if pull_dh:
+            dh_owned[0] = group.reduce_scatter_dh_async(s, e - s, N * Tc)   # runs beside the dW GEMM below
+        elif peer_dh:
             group.allreduce_dh_async(s, e - s)                # runs beside the dW GEMM below
         bwd_dweight(z, hidden2[s:e], d_weight, accumulate=(ci > 0) or (d_weight_out is not None), softmax_bwd=sb)
 
@@ -528,7 +533,7 @@ def fused_logprob_gspo(hidden: torch.Tensor, weight: torch.Tensor, completion_id
         main.wait_event(pending[-1])
         backward_gemms(*pending[:4])
     rows = None
-    if scatter_dh:
+    if scatter_dh or pull_dh:
         group.wait_allreduce()
         d_hidden = dh_owned[0]
         rows = group.owner_rows(N * Tc)[1:]
@@ -539,7 +544,7 @@ def fused_logprob_gspo(hidden: torch.Tensor, weight: torch.Tensor, completion_id
         dist.all_reduce(d_hidden, group=_pg(group))
     return dict(loss=state["loss"].reshape(()), per_token_logps=logp, advantages=state["adv"],
                 mean_kl=state["mean_kl"].reshape(()), completion_length=state["clen"], reward_std=state["rstd"],
-                d_hidden=None if d_hidden is None else (d_hidden if scatter_dh else d_hidden.view(N, Tc, H)),
+                d_hidden=None if d_hidden is None else (d_hidden if (scatter_dh or pull_dh) else d_hidden.view(N, Tc, H)),
                 d_hidden_rows=rows, d_weight=d_weight)
 
 

@@ -53,17 +53,23 @@ class PeerExchange:
 
     def __init__(self, group, capacity_tokens: int, hidden_size: int = 0, device=None, allreduce_ctas: int = 0,
                  dh_mode: str = "all_reduce"):
-        """`hidden_size` > 0 also allocates peer-mapped dHidden storage [capacity, hidden] bf16, used in one of two ways:
+        """`hidden_size` > 0 also allocates peer-mapped dHidden storage [capacity, hidden] bf16, used in one of three ways:
 
         dh_mode="all_reduce": every rank ends with the full dHidden.  The partial dHidden of every token chunk is
         all-reduced by `o3v_allreduce_bf16_peers` on a side stream WHILE the dW GEMM of the chunk runs (the kernel
         has no smem and ~43 registers, so its CTAs share SMs with the persistent GEMM CTAs).
 
         dh_mode="reduce_scatter" (the data-parallel layout of the reference's launch: rank r owns token
-        rows [r * ceil(T / P), ...) and only needs ITS rows of dHidden): the K2a epilogue itself stores every output
-        tile into the owner's slot buffer over NVLink (`o3v_lmhead_bwd_dhidden_scatter`: GEMM and transfer are one
-        kernel, half the NVLink bytes of an all-reduce, no collective kernel beside the GEMMs); after one barrier
-        each owner sums its P slots locally (`o3v_sum_slots_bf16`, deterministic) while the dW GEMM runs."""
+        rows [r * ceil(T / P), ...) and only needs ITS rows of dHidden): same partial buffers, but every owner PULLS
+        its rows from all peers (`o3v_reduce_scatter_bf16_peers`: NVLink loads, fp32 sum in rank order, local
+        store) on the side stream beside the dW GEMM: half the NVLink bytes of the all-reduce and no write fan-out.
+
+        dh_mode="reduce_scatter_fused": the K2a epilogue itself stores every output tile into the owner's slot buffer
+        over NVLink (`o3v_lmhead_bwd_dhidden_scatter`: GEMM and transfer are ONE kernel); after one barrier each
+        owner sums its P slots locally (`o3v_sum_slots_bf16`).  Bit-identical to "reduce_scatter"; measured on
+        8 x B200 (profiles/r2_ab_dh_collective_n8.jsonl) the remote stores stall the epilogue of the 256x512 tiles
+        (one accumulator stage: no MMA runs under it): 48.7 ms per c2 step against 39.6 ms, so it is an option, not
+        the default."""
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
@@ -80,11 +86,12 @@ class PeerExchange:
         self._calls = 0
         self.hidden_size = int(hidden_size)
         self.dh = None
-        if dh_mode not in ("all_reduce", "reduce_scatter"):
-            raise ValueError("dh_mode must be 'all_reduce' or 'reduce_scatter'")
+        if dh_mode not in ("all_reduce", "reduce_scatter", "reduce_scatter_fused"):
+            raise ValueError("dh_mode must be 'all_reduce', 'reduce_scatter' or 'reduce_scatter_fused'")
         self.dh_mode = dh_mode
         self.slot_rows = -(-self.cap // self.world)
-        if self.hidden_size > 0 and dh_mode == "reduce_scatter":
+        self._owned = None
+        if self.hidden_size > 0 and dh_mode == "reduce_scatter_fused":
             self.dh_slots = symm.empty((self.world, self.slot_rows, self.hidden_size), dtype=torch.bfloat16, device=device)
             self.dh_handle = symm.rendezvous(self.dh_slots, group)
             self._slot_ptrs = [int(p) for p in self.dh_handle.buffer_ptrs]
@@ -167,6 +174,35 @@ class PeerExchange:
                           self.rank, rows * self.hidden_size, self.ar_ctas,
                           ctypes.c_void_p(self.side.cuda_stream))
             self.dh_handle.barrier(channel=3)          # every rank's results have landed in every buffer
+
+    def reduce_scatter_dh_async(self, row0: int, rows: int, tokens_total: int):
+        """dh_mode="reduce_scatter": after K2a of the chunk [row0, row0 + rows) has written this rank's partial sums
+        into the peer-mapped buffer, the owners of those rows pull and sum them (side stream, beside the dW GEMM).
+        Returns the [rows_owned, hidden] bf16 tensor of the step (complete after the last chunk + wait_allreduce())."""
+        import ctypes
+        import torch
+        from . import _lib
+        from .gspo import _p
+        _, lo, hi = self.owner_rows(tokens_total)
+        if row0 == 0 or self._owned is None or self._owned.shape[0] != hi - lo:
+            self._owned = torch.empty(hi - lo, self.hidden_size, dtype=torch.bfloat16, device=self.dh.device)
+        out = self._owned
+        a, b = max(lo, row0), min(hi, row0 + rows)
+        cur = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        arr = (ctypes.c_void_p * self.world)(*self._dh_ptrs)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ev)
+            self.dh_handle.barrier(channel=2)          # every rank has written its partial sums of these rows
+            if b > a:
+                with torch.cuda.device(self.dh.device):
+                    _lib.call("o3v_reduce_scatter_bf16_peers", 1, _lib.load().o3v_reduce_scatter_bf16_peers, arr,
+                              self.world, a * self.hidden_size, (b - a) * self.hidden_size, _p(out[a - lo:b - lo]),
+                              self.ar_ctas, ctypes.c_void_p(self.side.cuda_stream))
+            self.dh_handle.barrier(channel=3)          # nobody overwrites its partial sums (next step) before all have read
+        out.record_stream(self.side)
+        return out
 
     def wait_allreduce(self):
         import torch

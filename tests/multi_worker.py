@@ -77,9 +77,23 @@ def small_case(dev, rank, world):
     lo, hi = outr["d_hidden_rows"]
     assert (lo, hi) == ex3.owner_rows(T)[1:] and outr["d_hidden"].shape == (hi - lo, H)
     check("reduce-scatter", outr, (lo, hi))
+    ex4 = sharded.PeerExchange(dist.group.WORLD, capacity_tokens=T, hidden_size=H, dh_mode="reduce_scatter_fused")
+    for _ in range(2):
+        outf = logprob.fused_logprob_gspo(h, w_local, ids, *args, v_offset=v0, group=ex4, chunk_tokens=2 * Tc)
+    torch.cuda.synchronize()
+    assert outf["d_hidden_rows"] == (lo, hi)
+    check("reduce-scatter-fused", outf, (lo, hi))
+    # pull (owners load their rows from the peers) and push (K2a epilogue stores at the owners): same sum, same order
+    errs["rs pull == fused"] = 0.0 if (torch.equal(outf["d_hidden"], outr["d_hidden"]) and
+                                       torch.equal(outf["d_weight"], outr["d_weight"])) else 2.0
     # same arithmetic in the same rank order as the NCCL path up to the reduction tree of bf16 partials
-    errs["rs-vs-nccl dH"] = rel(outr["d_hidden"], out["d_hidden"].reshape(-1, H)[lo:hi]) / 4e-3
-    errs["ar-vs-nccl dH"] = rel(outq["d_hidden"], out["d_hidden"]) / 4e-3
+    # (ours: fp32 sum of the P bf16 partials in rank order, ONE rounding; NCCL's ring rounds the running sum to bf16 at
+    # each of its P - 1 hops: a random walk of 2^-9 relative roundings, so the bar grows with sqrt(P - 1).  Measured
+    # on hardware: identical at P = 2, 3.0e-3 at P = 4, 3.2e-3 .. 4.4e-3 at P = 8; both are checked against the oracle
+    # above, where the one-rounding sum is the closer one)
+    ring_tol = 2.0 ** -8 * max(1.0, (world - 1) ** 0.5)
+    errs["rs-vs-nccl dH"] = rel(outr["d_hidden"], out["d_hidden"].reshape(-1, H)[lo:hi]) / ring_tol
+    errs["ar-vs-nccl dH"] = rel(outq["d_hidden"], out["d_hidden"]) / ring_tol
     # bit-identical where the arithmetic and its order are the same
     same = (torch.equal(outp["per_token_logps"], out["per_token_logps"]) and torch.equal(outp["loss"], out["loss"])
             and torch.equal(outp["d_hidden"], out["d_hidden"]) and torch.equal(outq["d_weight"], out["d_weight"])
@@ -135,12 +149,12 @@ def head_case(dev, rank, world):
     dH_ref = P @ w.float()
     dW_ref = (P[:, v_a:v_b].T @ h.view(T, H).float())
     del P
-    for mode in ("all_reduce", "reduce_scatter"):
+    for mode in ("all_reduce", "reduce_scatter", "reduce_scatter_fused"):
         ex = sharded.PeerExchange(dist.group.WORLD, capacity_tokens=T, hidden_size=H, dh_mode=mode)
         out = logprob.fused_logprob_gspo(h, w_local, ids, ref, mask.to(dev), rpf, G, 0.04, v_offset=v0, group=ex,
                                          chunk_tokens=T // 2)
         torch.cuda.synchronize()
-        lo, hi = out["d_hidden_rows"] if mode == "reduce_scatter" else (0, T)
+        lo, hi = out["d_hidden_rows"] if mode != "all_reduce" else (0, T)
         errs[mode + " logp"] = ((out["per_token_logps"] - lp_ref).abs() / lp_ref.abs().clamp(min=1e-6)).max().item() / 1e-3
         errs[mode + " loss"] = abs(out["loss"].item() - exp["loss"].item()) / (1e-3 * abs(exp["loss"].item()) + 1e-7)
         errs[mode + " dH"] = rel(out["d_hidden"].reshape(-1, H), dH_ref[lo:hi]) / 1e-2
