@@ -504,11 +504,33 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (int nt = t_begin; nt < t_end; ++nt, ++acc_iter) {
         const uint32_t a = acc_iter % S::ACC_STAGES, aphase = (acc_iter / S::ACC_STAGES) & 1u;
         if constexpr (kXform) xform_tile(m_blk, xstage, xphase);
-        ptx::mbar_wait(&tfull[a], aphase);
-        ptx::tc_fence_after();
         const int64_t n0 = (int64_t)nt * S::TILE_N;
         const int64_t n_left = p.N - n0;
         const int n_valid = n_left < (int64_t)S::TILE_N ? (int)n_left : S::TILE_N;          // columns of this tile inside N
+        // EPI_STORE with the softmax epilogue: this row's segment of W[tcol] is gathered one 32-column chunk AHEAD of
+        // its use (a dependent L2 / HBM load per chunk inside `process` cost ~1 us x 16 chunks per tile: 7 % of K2a
+        // when the vocabulary slice, i.e. the K loop, is 1/8 of the full one); the segment is pulled into L2 and its
+        // first chunk loaded while the tile's MMAs still run
+        uint4 wa[4] = {}, wb[4] = {};
+        auto gather_w = [&](uint4 (&wq)[4], const int c) {
+          if constexpr (kEpi == EPI_STORE) {
+            if (sm_tcol >= 0 && c * 32 < n_valid) {
+              const uint4* wrow = reinterpret_cast<const uint4*>(p.sm_weight + (int64_t)sm_tcol * p.N + n0 + c * 32);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (c * 32 + j * 8 < n_valid) wq[j] = __ldg(wrow + j);
+            }
+          }
+        };
+        if constexpr (kEpi == EPI_STORE) {
+          if (sm_tcol >= 0) {
+            const __nv_bfloat16* wseg = p.sm_weight + (int64_t)sm_tcol * p.N + n0;
+            for (int cc = 64; cc < n_valid; cc += 64) ptx::prefetch_l2(wseg + cc);       // 128-byte lines
+          }
+          gather_w(wa, 0);
+        }
+        ptx::mbar_wait(&tfull[a], aphase);
+        ptx::tc_fence_after();
         const int tgt_in_tile = (tgt_col >= n0 && tgt_col < n0 + S::TILE_N) ? (int)(tgt_col - n0) : -1;
         const uint32_t tmem_tile = tmem_row + a * S::TILE_N;
 
@@ -550,7 +572,7 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         };
 
         // one 32-column chunk of this thread's accumulator row
-        auto process = [&](uint32_t (&v)[32], const int c) {
+        auto process = [&](uint32_t (&v)[32], const int c, const uint4 (&wq)[4]) {
           const int cbase = c * 32;                       // first column of the chunk within the tile
           if constexpr (kEpi == EPI_STATS) {
             if (p.logits != nullptr && p.row_ref == nullptr) store_chunk(v, c, false, 1.0f);     // bf16 logits (dlogits path)
@@ -600,11 +622,10 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(sm_a * __uint_as_float(v[j]));
                 if (sm_tcol >= 0 && cbase < n_valid) {
-                  const uint4* wrow = reinterpret_cast<const uint4*>(p.sm_weight + (int64_t)sm_tcol * p.N + n0 + cbase);
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
                     if (cbase + j * 8 < n_valid) {         // N % 8 == 0: whole 16-byte groups
-                      const uint4 w8 = __ldg(wrow + j);
+                      const uint4 w8 = wq[j];              // W[tcol, n0 + cbase + 8 j ..], loaded one chunk ahead
                       const uint32_t ww[4] = {w8.x, w8.y, w8.z, w8.w};
 #pragma unroll
                       for (int k = 0; k < 4; ++k) {
@@ -674,10 +695,14 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int c = 0; c < kChunks; c += 2) {
           ptx::tmem_ld_wait();
           ptx::tmem_ld_32x32b_x32(tmem_tile + (c + 1) * 32, vb);
-          process(va, c);
+          gather_w(wb, c + 1);
+          process(va, c, wa);
           ptx::tmem_ld_wait();
-          if (c + 2 < kChunks) ptx::tmem_ld_32x32b_x32(tmem_tile + (c + 2) * 32, va);
-          process(vb, c + 1);
+          if (c + 2 < kChunks) {
+            ptx::tmem_ld_32x32b_x32(tmem_tile + (c + 2) * 32, va);
+            gather_w(wa, c + 2);
+          }
+          process(vb, c + 1, wb);
         }
         // all tcgen05.ld of this warp have completed (wait::ld above): hand the accumulator back
         ptx::tc_fence_before();

@@ -149,6 +149,9 @@ __device__ __forceinline__ void red_add_v4_f32(float* p, float a, float b, float
 }
 
 // ------------------------------------------------------------------------------ TMA
+__device__ __forceinline__ void prefetch_l2(const void* gptr) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(gptr) : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }

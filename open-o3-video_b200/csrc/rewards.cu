@@ -12,6 +12,7 @@
 // Arithmetic follows the reference's float64 operation order; explicit __d*_rn intrinsics
 // keep nvcc from contracting mul+add into FMA so that results are bit-identical to numpy's.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -67,8 +68,8 @@ __host__ __device__ inline size_t gt_bytes_per_prompt(const o3v_rewards_soa& s) 
   return (size_t)gt_doubles(s) * 8 + (((size_t)gt_ints(s) * 4 + 15) & ~(size_t)15);
 }
 
-template <bool kStageGT>
-__global__ void __launch_bounds__(kRewardThreads, 2)
+template <bool kStageGT, int kMinBlocks>
+__global__ void __launch_bounds__(kRewardThreads, kMinBlocks)
 rewards_kernel(const o3v_rewards_soa s, double* __restrict__ out) {
   extern __shared__ double smem_gt[];
   const int lane = threadIdx.x & (kLanes - 1);
@@ -135,7 +136,7 @@ rewards_kernel(const o3v_rewards_soa s, double* __restrict__ out) {
   double ct_mine = 0.0;
   int cnb_mine = 0;
   unsigned cval_mine = 0u;
-  double cb0_mine[4] = {0, 0, 0, 0}, cb1_mine[4] = {0, 0, 0, 0};
+  double cb0_mine[4] = {0, 0, 0, 0}, cb1_mine[4] = {0, 0, 0, 0};   // claim boxes 0 / 1, or (visual QA) this lane's think box
   if (do_claims && lane < nc) {
     ct_mine = s.claim_t[r * s.C + lane];
     cnb_mine = s.claim_nbox[r * s.C + lane];
@@ -143,9 +144,9 @@ rewards_kernel(const o3v_rewards_soa s, double* __restrict__ out) {
     const double* cb = s.claim_box + ((r * s.C + lane) * (int64_t)s.Bc) * 4;   // slots exist up to Bc whatever the count
     if (s.Bc > 0) load4(cb, cb0_mine);
     if (s.Bc > 1) load4(cb + 4, cb1_mine);
+  } else if (do_vthink && lane < ntb) {
+    load4(s.think_box + (r * s.Tb + lane) * 4, cb0_mine);
   }
-  double tb_mine[4] = {0, 0, 0, 0};
-  if (do_vthink && lane < ntb) load4(s.think_box + (r * s.Tb + lane) * 4, tb_mine);
 
   if constexpr (kStageGT) __syncthreads();
   if (!live) return;   // whole 16-lane group leaves together
@@ -226,7 +227,7 @@ rewards_kernel(const o3v_rewards_soa s, double* __restrict__ out) {
       for (int b = lane; b < ntb; b += kLanes) {
         if (b < 32 ? ((tvalid >> b) & 1u) != 0u : box_slot_valid(s.think_box + (r * s.Tb + b) * 4)) {
           if (b == lane) {
-            best = fmax(best, box_iou(gvb, tb_mine));
+            best = fmax(best, box_iou(gvb, cb0_mine));
           } else {
             double pb[4];
             load4(s.think_box + (r * s.Tb + b) * 4, pb);
@@ -283,17 +284,19 @@ rewards_kernel(const o3v_rewards_soa s, double* __restrict__ out) {
               load4(gtb + (((kf * s.O + o) * s.Gb) + gi) * 4, nb4);
               g4[0] = dmul(nb4[0], W); g4[1] = dmul(nb4[1], H);         // :337-346
               g4[2] = dmul(nb4[2], W); g4[3] = dmul(nb4[3], H);
+              // :592-593 max(list): boxes 0 and 1 (the common case) as two INDEPENDENT chains, selected afterwards
+              const double v0 = box_iou(g4, cb0), v1 = box_iou(g4, cb1);
               double best = 0.0;
-              bool first = true;
-              for (int b = 0; b < nb; ++b) {                            // :592-593 max(list)
+              if (nb > 0) best = (valid & 1u) ? v0 : 0.0;
+              if (nb > 1) best = fmax(best, (valid & 2u) ? v1 : 0.0);
+              for (int b = 2; b < nb; ++b) {
                 double v = 0.0;
                 if (b < 32 ? ((valid >> b) & 1u) != 0u : box_slot_valid(cb + b * 4)) {
-                  if (b == 0) v = box_iou(g4, cb0);
-                  else if (b == 1) v = box_iou(g4, cb1);
-                  else { double pb[4]; load4(cb + b * 4, pb); v = box_iou(g4, pb); }
+                  double pb[4];
+                  load4(cb + b * 4, pb);
+                  v = box_iou(g4, pb);
                 }
-                best = first ? v : fmax(best, v);
-                first = false;
+                best = fmax(best, v);
               }
               acc = dadd(acc, best);                                    // :597 sum(...)
             }
@@ -338,10 +341,15 @@ extern "C" int o3v_grounded_rewards(const o3v_rewards_soa* soa, double* out, voi
   // prompts a CTA of 16 consecutive rollouts can touch
   const int64_t span = std::min<int64_t>(per_cta, (per_cta + s.G - 1) / s.G + 1);
   const size_t smem = (size_t)span * o3v::gt_bytes_per_prompt(s);
+  // resident CTAs per SM the kernel is compiled for (diagnostic override: O3V_REWARDS_MIN_BLOCKS=2|3)
+  static const int min_blocks = [] { const char* e = getenv("O3V_REWARDS_MIN_BLOCKS"); return (e && e[0] == '2') ? 2 : 3; }();
+  cudaStream_t st = (cudaStream_t)stream;
   if (smem <= 40 * 1024) {
-    o3v::rewards_kernel<true><<<grid, o3v::kRewardThreads, smem, (cudaStream_t)stream>>>(s, out);
+    if (min_blocks == 2) o3v::rewards_kernel<true, 2><<<grid, o3v::kRewardThreads, smem, st>>>(s, out);
+    else o3v::rewards_kernel<true, 3><<<grid, o3v::kRewardThreads, smem, st>>>(s, out);
   } else {   // very large K x O x Gb: read the ground truth through L2 instead
-    o3v::rewards_kernel<false><<<grid, o3v::kRewardThreads, 0, (cudaStream_t)stream>>>(s, out);
+    if (min_blocks == 2) o3v::rewards_kernel<false, 2><<<grid, o3v::kRewardThreads, 0, st>>>(s, out);
+    else o3v::rewards_kernel<false, 3><<<grid, o3v::kRewardThreads, 0, st>>>(s, out);
   }
   O3V_LAUNCH_CHECK();
   return O3V_OK;
