@@ -46,6 +46,8 @@ CONFIGS = {
     # the per-rank kernel shapes of the 8-GPU run without any communication
     "c2s8": dict(head="qwen2.5-vl-7b, 1/8 vocab slice", H=3584, V=19008, prompts=8, G=8, Tc=2048),
     "c3s8": dict(head="qwen3-vl-8b, 1/8 vocab slice", H=4096, V=18992, prompts=16, G=8, Tc=4096),
+    "c3s4a": dict(head="qwen3-vl-8b, 149 of 594 vocab tiles (ranks 0-1 of 4)", H=4096, V=38144, prompts=16, G=8, Tc=4096),
+    "c3s4b": dict(head="qwen3-vl-8b, 148 of 594 vocab tiles (ranks 2-3 of 4)", H=4096, V=37888, prompts=16, G=8, Tc=4096),
     "tiny": dict(head="tiny", H=256, V=8192, prompts=2, G=4, Tc=128),
     # what ONE rank of the reference's own launch sees per step (per-device batch of 1 prompt x 8 generations)
     "dev": dict(head="qwen2.5-vl-7b", H=3584, V=152064, prompts=1, G=8, Tc=2048),

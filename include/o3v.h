@@ -147,6 +147,12 @@ int o3v_lmhead_bwd_dweight(const void* dlogits, int64_t ld_dlogits, const void* 
                            int64_t T, int64_t V, int64_t H,
                            float* d_weight, int32_t accumulate, void* stream);
 
+/* out[i] += slabs[0][i] + slabs[1][i] + ... + slabs[S-1][i]  (fp32, slab order: deterministic).  The host layer splits
+ * the K (token) range of the LAST vocabulary tiles of K2b over the SMs that would otherwise idle in the final, nearly
+ * empty wave of the persistent grid: S plain o3v_lmhead_bwd_dweight launches on S streams write their partial dW tiles
+ * into S slabs, this kernel folds them into dW.  n_elems % 4 == 0, 16-byte aligned pointers. */
+int o3v_add_slabs_f32(const float* slabs, int64_t S, int64_t n_elems, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Exp-store backward (default path of round 2): no elementwise pass over the [T, V] chunk at all.
  *

@@ -54,6 +54,7 @@ SIGNATURES = {
     "o3v_lmhead_merge_stats": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "o3v_lmhead_merge_stats_peers": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "o3v_allreduce_bf16_peers": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int32, c_void_p]),
+    "o3v_add_slabs_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "o3v_reduce_scatter_bf16_peers": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int32, c_void_p]),
     "o3v_lmhead_dlogits": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                    c_int64, c_void_p]),

@@ -20,6 +20,7 @@ static int g_bwd_sync = 1;      // K2a / K2b: wave-boundary rendezvous of the TM
 static int g_dh_mfast = 0;      // K2a item order (0 = n fastest)
 static int g_dw_mfast = 0;      // K2b item order
 static int g_fwd_groups = 0;    // n-groups (vocab splits) per m-block in K1; 0 = auto
+static int g_fwd_rotate = 1;    // K1: rotate the vocab group a worker takes from wave to wave
 static int g_max_ctas = 0;      // cap on the persistent grid; 0 = all SMs
 static int g_bwd_prefetch = 0;  // K2a / K2b: L2 prefetch distance (k-blocks) for the A operand streamed from HBM
 // L2 eviction hints (0 none, 1 evict first, 2 evict last): K1 hidden / W loads and logits store, K2 P / other operand
@@ -131,8 +132,8 @@ static void plan_tiles(GemmParams& p, int ncta, int n_groups_hint, int acc = 1) 
   p.num_n_tiles = (int32_t)ceil_div(p.N, 256 * acc);
   int groups = n_groups_hint < 1 ? 1 : n_groups_hint;
   if (groups > p.num_n_tiles) groups = p.num_n_tiles;
+  p.num_n_groups = groups;
   p.tiles_per_group = (int32_t)ceil_div(p.num_n_tiles, groups);
-  p.num_n_groups = (int32_t)ceil_div(p.num_n_tiles, p.tiles_per_group);
 }
 
 // Number of vocab splits per m-block in K1.  Few splits keep the concurrently swept A panels
@@ -293,6 +294,20 @@ sum_slots_bf16_kernel(const uint4* __restrict__ slots, int P, int64_t slot_vecs,
   }
 }
 
+// out[i] += sum_s slabs[s][i] in slab order (the K-split partial sums of the dW tail tiles: deterministic)
+__global__ void __launch_bounds__(256)
+add_slabs_f32_kernel(const float4* __restrict__ slabs, int S, int64_t n_vecs, float4* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vecs; i += stride) {
+    float4 acc = out[i];
+    for (int sidx = 0; sidx < S; ++sidx) {
+      const float4 v = __ldcs(slabs + (int64_t)sidx * n_vecs + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    out[i] = acc;
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // exp-store backward: P = a * E + g * onehot, so  dH = a * (E . W) + g * W[tcol]   (K2a epilogue)
 //                                                 dW = E^T . (a * hidden) + scatter_t g_t * hidden_t into row tcol_t
@@ -425,6 +440,7 @@ extern "C" int o3v_set_tunable(const char* name, int value) {
   else if (n == "dh_mfast") g_dh_mfast = value ? 1 : 0;
   else if (n == "dw_mfast") g_dw_mfast = value ? 1 : 0;
   else if (n == "fwd_groups") g_fwd_groups = value;
+  else if (n == "fwd_rotate") g_fwd_rotate = value ? 1 : 0;
   else if (n == "max_ctas") g_max_ctas = value;
   else if (n == "bwd_prefetch") g_bwd_prefetch = value < 0 ? 0 : value;
   else if (n == "hint_fwd_a") g_hint_fwd_a = value;
@@ -468,6 +484,14 @@ static int lmhead_fwd_impl(const void* hidden, const void* weight, const int64_t
   p.targets = targets; p.v_offset = v_offset; p.parts = reinterpret_cast<float*>(workspace);
   p.logits = reinterpret_cast<__nv_bfloat16*>(logits); p.ld_logits = ld_logits;
   p.row_ref = row_ref; p.row_keep = row_keep;
+  {
+    // group rotation per wave of the persistent grid (only when a wave holds whole m-blocks)
+    int sms = num_sms();
+    if (g_max_ctas > 0 && g_max_ctas < sms) sms = g_max_ctas;
+    const int64_t workers = std::min<int64_t>(sms / ncta, (int64_t)p.num_m_blocks * p.num_n_groups);
+    if (g_fwd_rotate && p.num_n_groups > 1 && workers >= p.num_n_groups && workers % p.num_n_groups == 0)
+      p.rotate_groups = (int32_t)(workers / p.num_n_groups);
+  }
   p.hint_a = g_hint_fwd_a; p.hint_b = g_hint_fwd_b; p.hint_store = g_hint_fwd_store;
   CUtensorMap tmA, tmB, tmC = {};
   if ((rc = make_tmap_bf16(&tmA, hidden, H, T, H, 128))) return rc;
@@ -767,6 +791,20 @@ extern "C" int o3v_lmhead_bwd_dweight(const void* dlogits, int64_t ld_dlogits, c
                                       int64_t T, int64_t V, int64_t H, float* d_weight, int32_t accumulate,
                                       void* stream) {
   return bwd_dweight_impl(dlogits, ld_dlogits, hidden, T, V, H, d_weight, accumulate, nullptr, stream);
+}
+
+extern "C" int o3v_add_slabs_f32(const float* slabs, int64_t S, int64_t n_elems, float* out, void* stream) {
+  if (!slabs || !out || S < 0 || n_elems < 0 || (n_elems % 4) != 0) return O3V_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(slabs) & 15u) || (reinterpret_cast<uintptr_t>(out) & 15u)) return O3V_ERR_ALIGNMENT;
+  int rc = check_device();
+  if (rc) return rc;
+  if (S == 0 || n_elems == 0) return O3V_OK;
+  const int64_t nvec = n_elems / 4;
+  const int ctas = (int)std::min<int64_t>(4 * (int64_t)num_sms(), ceil_div(nvec, 256));
+  add_slabs_f32_kernel<<<ctas, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(slabs), (int)S, nvec,
+                                                               reinterpret_cast<float4*>(out));
+  O3V_LAUNCH_CHECK();
+  return O3V_OK;
 }
 
 extern "C" int o3v_lmhead_bwd_dweight_exp(const void* expz, int64_t ld_expz, const void* rows, const int64_t* order,

@@ -33,8 +33,13 @@ struct GemmParams {
   int64_t M, N, K;
   int32_t num_m_blocks;     // ceil(M / (128 * ncta))
   int32_t num_n_tiles;      // ceil(N / 256)
-  int32_t tiles_per_group;  // consecutive n-tiles per work item (online softmax state lives across them)
-  int32_t num_n_groups;     // ceil(num_n_tiles / tiles_per_group)
+  int32_t tiles_per_group;  // most consecutive n-tiles of one work item (online softmax state lives across them)
+  int32_t num_n_groups;     // work items per m-block: group g covers the n-tiles [g * tiles / groups, (g + 1) * tiles / groups)
+                            // (balanced: sizes differ by at most one tile)
+  int32_t rotate_groups;    // K1: m-blocks per wave of the persistent grid (0 = off).  The group a worker takes
+                            // rotates from wave to wave, so that workers whose groups are one tile longer do not fall
+                            // behind for the whole launch (CTAs that drift apart stop sharing W tiles and hidden
+                            // panels in L2: profiles/r2_notes.md section 7)
   int32_t m_fast;           // item order: 0 = n-groups fastest (CTAs running together share A panels),
                             //             1 = m-blocks fastest (they share B panels)
   unsigned int* wave_sync;  // optional pair of global words {arrivals, abandoned} (zeroed before launch): the TMA
@@ -102,7 +107,14 @@ struct SoftmaxBwdRow {
 //           feeds twice the MMAs (L2->SM bytes per flop -25 %, half as many sweeps over the other
 //           operand); the epilogue is not overlapped, fine when the K loop is hundreds of blocks.
 __device__ __forceinline__ int item_n(const GemmParams& p, int item) {
-  return p.m_fast ? item / p.num_m_blocks : item % p.num_n_groups;
+  if (p.m_fast) return item / p.num_m_blocks;
+  const int j = item % p.num_n_groups;
+  if (p.rotate_groups <= 0) return j;
+  return (j + (item / p.num_n_groups) / p.rotate_groups) % p.num_n_groups;
+}
+__device__ __forceinline__ void group_tiles(const GemmParams& p, int n_grp, int& t_begin, int& t_end) {
+  t_begin = (int)(((int64_t)n_grp * p.num_n_tiles) / p.num_n_groups);
+  t_end = (int)(((int64_t)(n_grp + 1) * p.num_n_tiles) / p.num_n_groups);
 }
 __device__ __forceinline__ int item_m(const GemmParams& p, int item) {
   return p.m_fast ? item % p.num_m_blocks : item / p.num_n_groups;
@@ -333,8 +345,8 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
       const int n_grp = item_n(p, item), m_blk = item_m(p, item);
       const int m0 = m_blk * S::UMMA_M + (int)rank * BM;
-      const int t_begin = n_grp * p.tiles_per_group;
-      const int t_end = min(t_begin + p.tiles_per_group, p.num_n_tiles);
+      int t_begin, t_end;
+      group_tiles(p, n_grp, t_begin, t_end);
       for (int nt = t_begin; nt < t_end; ++nt) {
         const int n0 = nt * S::TILE_N + (int)rank * S::LOAD_BN;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
@@ -420,8 +432,8 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       int stage = 0; uint32_t phase = 0; uint32_t acc_iter = 0;
       for (int item = worker; item < num_items; item += num_workers) {
         const int n_grp = item_n(p, item);
-        const int t_begin = n_grp * p.tiles_per_group;
-        const int t_end = min(t_begin + p.tiles_per_group, p.num_n_tiles);
+        int t_begin, t_end;
+        group_tiles(p, n_grp, t_begin, t_end);
         for (int nt = t_begin; nt < t_end; ++nt, ++acc_iter) {
           const uint32_t a = acc_iter % S::ACC_STAGES, aphase = (acc_iter / S::ACC_STAGES) & 1u;
           ptx::mbar_wait(&tempty[a], aphase ^ 1u);           // epilogue has drained this accumulator
@@ -460,8 +472,8 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     int xstage = 0; uint32_t xphase = 0;
     for (int item = worker; item < num_items; item += num_workers) {
       const int n_grp = item_n(p, item), m_blk = item_m(p, item);
-      const int t_begin = n_grp * p.tiles_per_group;
-      const int t_end = min(t_begin + p.tiles_per_group, p.num_n_tiles);
+      int t_begin, t_end;
+      group_tiles(p, n_grp, t_begin, t_end);
       for (int nt = t_begin; nt < t_end; ++nt) xform_tile(m_blk, xstage, xphase);
     }
   } else if (warp >= 4) {
@@ -477,8 +489,8 @@ lmhead_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int n_grp = item_n(p, item), m_blk = item_m(p, item);
       const int64_t row = (int64_t)m_blk * S::UMMA_M + (int64_t)rank * BM + row_in_tile;
       const bool row_ok = row < p.M;
-      const int t_begin = n_grp * p.tiles_per_group;
-      const int t_end = min(t_begin + p.tiles_per_group, p.num_n_tiles);
+      int t_begin, t_end;
+      group_tiles(p, n_grp, t_begin, t_end);
 
       float run_max = -INFINITY, run_sum = 0.f, tgt_logit = 0.f;
       int64_t tgt_col = -1;

@@ -133,15 +133,76 @@ def bwd_dhidden_exp(expz, rows, weight, out=None, fp32=False, scatter=None):
     return None
 
 
+# K2b runs 256-row x 512-column tiles on a persistent grid of #SM / 2 CTA pairs.  When the vocabulary slice has one or
+# two 256-row blocks more than a whole number of waves (19200 rows x 3584: 75 x 7 = 7 x 74 + 7 tiles), the last wave keeps
+# 7 of 74 pairs busy for a full tile time: 12 % of the kernel at 8 GPUs.  The host layer then runs the main launch on
+# the rows that fill whole waves and splits the K (token) range of the remaining rows over the idle pairs: S plain
+# launches on S streams into S fp32 slabs, summed into dW in slab order (o3v_add_slabs_f32: deterministic).
+DW_TAIL_SPLIT = True
+_tail_streams = {}
+
+
+def _dw_tail_plan(V: int, H: int, T: int, dev):
+    """-> (rows of the main launch, K splits) or None when the tile count already fills its waves."""
+    if not DW_TAIL_SPLIT:
+        return None
+    workers = torch.cuda.get_device_properties(dev).multi_processor_count // 2
+    mb, nt = -(-V // 256), -(-H // 512)
+    for tail in (1, 2):
+        m_main = mb - tail
+        if m_main >= 1 and (m_main * nt) % workers == 0 and 2 * tail * nt <= workers:
+            splits = min(workers // (tail * nt), T // 4096)       # at least 64 k-blocks per split
+            return (m_main * 256, splits) if splits >= 2 else None
+    return None
+
+
 def bwd_dweight_exp(expz, rows, order, hidden, d_weight, accumulate, scratch=None):
-    """dW (+)= E^T . (a * hidden) + one-hot scatter (pre-scale, K2b, scatter: three launches)."""
+    """dW (+)= E^T . (a * hidden) + one-hot scatter (pre-scale, K2b, scatter: three launches; plus the K-split
+    launches of the last vocabulary rows when they would otherwise run as a nearly empty wave, `_dw_tail_plan`)."""
     T, V = expz.shape
     H = hidden.shape[1]
+    dev = expz.device
     if scratch is None or scratch.numel() < T * H:
-        scratch = torch.empty(T, H, dtype=torch.bfloat16, device=expz.device)
-    with torch.cuda.device(expz.device):
-        _lib.call("o3v_lmhead_bwd_dweight_exp", 3, _lib.load().o3v_lmhead_bwd_dweight_exp, _p(expz), expz.stride(0),
-                  _p(rows), _p(order), _p(hidden), T, V, H, _p(d_weight), 1 if accumulate else 0, _p(scratch), _stream())
+        scratch = torch.empty(T, H, dtype=torch.bfloat16, device=dev)
+    lib = _lib.load()
+    plan = _dw_tail_plan(V, H, T, dev)
+    with torch.cuda.device(dev):
+        if plan is None:
+            _lib.call("o3v_lmhead_bwd_dweight_exp", 3, lib.o3v_lmhead_bwd_dweight_exp, _p(expz), expz.stride(0),
+                      _p(rows), _p(order), _p(hidden), T, V, H, _p(d_weight), 1 if accumulate else 0, _p(scratch), _stream())
+            return d_weight
+        v_main, splits = plan
+        if not accumulate:
+            d_weight[v_main:].zero_()                      # the scatter and the slab sum below accumulate into these rows
+        # rows [0, v_main): pre-scale of ALL token rows into `scratch`, main GEMM, one-hot scatter (every row of dW)
+        _lib.call("o3v_lmhead_bwd_dweight_exp", 3, lib.o3v_lmhead_bwd_dweight_exp, _p(expz), expz.stride(0),
+                  _p(rows), _p(order), _p(hidden), T, v_main, H, _p(d_weight), 1 if accumulate else 0, _p(scratch), _stream())
+        main = torch.cuda.current_stream(dev)
+        key = torch.device(dev).index
+        pool = _tail_streams.setdefault(key, [])
+        while len(pool) < splits:
+            pool.append(torch.cuda.Stream(device=dev))
+        ready = torch.cuda.Event()
+        ready.record(main)
+        slabs = torch.empty(splits, V - v_main, H, dtype=torch.float32, device=dev)
+        scaled = scratch.view(-1)[: T * H].view(T, H)
+        per = -(-T // splits)
+        step = -(-per // 64) * 64                          # token ranges in whole 64-row k-blocks
+        used = 0
+        for i in range(splits):
+            t0, t1 = i * step, min(T, (i + 1) * step)
+            if t1 <= t0:
+                break
+            st = pool[i]
+            with torch.cuda.stream(st):
+                st.wait_event(ready)
+                _lib.call("o3v_lmhead_bwd_dweight_tail", 1, lib.o3v_lmhead_bwd_dweight, _p(expz[t0:t1, v_main:]),
+                          expz.stride(0), _p(scaled[t0:t1]), t1 - t0, V - v_main, H, _p(slabs[i]), 0,
+                          ctypes.c_void_p(st.cuda_stream))
+            main.wait_stream(st)
+            used += 1
+        _lib.call("o3v_add_slabs_f32", 1, lib.o3v_add_slabs_f32, _p(slabs), used, (V - v_main) * H, _p(d_weight[v_main:]),
+                  _stream())
     return d_weight
 
 

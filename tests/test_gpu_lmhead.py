@@ -241,7 +241,8 @@ def test_fused_softmax_backward_needs_the_default_tile_mode():
 
 
 EXP_CASES = [(128, 64, 256, 0, 0.0), (300, 192, 1000, 0, 3.0), (1100, 512, 5000, 0, -20.0), (640, 256, 2376, 4752, 40.0),
-             (2900, 1792, 9496, 9496, 0.0)]
+             (2900, 1792, 9496, 9496, 0.0),
+             (8256, 512, 19096, 0, 0.0)]      # 75 vocabulary blocks x 1 column tile = one wave of 74 + 1: K-split tail (ragged)
 
 
 @pytest.mark.parametrize("T,H,V,v_off,shift", EXP_CASES)
@@ -297,3 +298,42 @@ def test_exp_store_backward(T, H, V, v_off, shift):
     assert torch.equal(dW, dW2)
     logprob.bwd_dweight_exp(E[:, :V], rows, order, Hd, dW, accumulate=True)
     assert (dW - 2 * dW_ref).norm() <= 4e-3 * (2 * dW_ref).norm()
+
+
+def test_dweight_tail_split_matches_the_single_launch(monkeypatch):
+    """K2b with the K range of the last vocabulary rows split over the idle CTA pairs (logprob._dw_tail_plan) against the
+    single launch: same sums up to the fp32 order of the K partials, deterministic, accumulating; ragged last block."""
+    from open_o3_video_b200 import logprob
+    T, H, V = 12352, 1024, 2 * 37 * 256 + 200            # 75 blocks x 2 column tiles = 2 waves of 74 + 2; 3 K splits
+    assert logprob._dw_tail_plan(V, H, T, "cuda") == (74 * 256, 3)
+    g0 = torch.Generator().manual_seed(5)
+    Hd = torch.randn(T, H, generator=g0).bfloat16().cuda()
+    E = (torch.rand(T, V, generator=g0) * 1e-3).bfloat16().cuda()
+    lse = torch.zeros(T, device="cuda")
+    ref = torch.zeros(T, device="cuda")
+    grad = (torch.randn(T, generator=g0) * 0.01).cuda()
+    grad[100:400] = 0
+    targets = torch.randint(0, V, (T,), generator=g0).cuda()
+    targets[:50] = V - 3                                  # a scatter run inside the tail rows
+    rows, order = logprob.softmax_rows(lse, grad, targets, ref, 0, V)
+    out = {}
+    for split in (True, False):
+        monkeypatch.setattr(logprob, "DW_TAIL_SPLIT", split)
+        dW = torch.full((V, H), float("nan"), device="cuda")
+        logprob.bwd_dweight_exp(E, rows, order, Hd, dW, accumulate=False)
+        dW2 = torch.full((V, H), float("nan"), device="cuda")
+        logprob.bwd_dweight_exp(E, rows, order, Hd, dW2, accumulate=False)
+        assert torch.equal(dW, dW2)
+        logprob.bwd_dweight_exp(E, rows, order, Hd, dW2, accumulate=True)
+        out[split] = (dW, dW2)
+    torch.cuda.synchronize()
+    a, b = out[True][0], out[False][0]
+    assert torch.equal(a[:74 * 256], b[:74 * 256])        # rows of the main launch: same kernel, same order
+    assert (a - b).abs().max() <= 1e-5 * b.abs().max()
+    assert (out[True][1] - 2 * b).abs().max() <= 2e-5 * b.abs().max()
+    # against torch fp32 from the definition: dW = E^T (a * hidden) + scatter(g * hidden)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    a_t = -grad * torch.exp(ref - lse)
+    dW_ref = E.float().T @ (a_t[:, None] * Hd.float()).bfloat16().float()
+    dW_ref.index_add_(0, targets, grad[:, None] * Hd.float())
+    assert (a - dW_ref).norm() <= 2e-3 * dW_ref.norm()
