@@ -276,6 +276,8 @@ def run_ours(args):
         k, v = kv.split("=")
         _lib.set_tunable(k, int(v))
 
+    if args.no_chunk_plan:
+        logprob.PLAN_CHUNKS = False
     H, V, G, Tc = cfg["H"], cfg["V"], cfg["G"], cfg["Tc"]
     N = cfg["prompts"] * G
     T = N * Tc
@@ -292,9 +294,12 @@ def run_ours(args):
     if world > 1 and args.exchange == "peer":
         group = sharded.PeerExchange(dist.group.WORLD, capacity_tokens=T, hidden_size=H if args.overlap_allreduce else 0,
                                      dh_mode=args.dh_collective)
-    if not args.chunk_tokens:
-        per_seq = max(1, min(N, logprob.auto_chunk_tokens(weight.shape[0]) // Tc))
-        args.chunk_tokens = -(-N // (-(-N // per_seq))) * Tc      # evened out over whole sequences
+    # chunking: 0 = the library's own plan (a 10 GB logits buffer cut into whole sequences, logprob.plan_chunks)
+    call_chunk_tokens = args.chunk_tokens
+    v_plan = logprob._plan_vocab(weight.shape[0], pg, dev)
+    seq_plan = logprob.plan_chunks(N, Tc, H, weight.shape[0], args.chunk_tokens or logprob.auto_chunk_tokens(v_plan), dev,
+                                   tune=world == 1)
+    args.chunk_tokens = max(seq_plan) * Tc
     del w_full
     # reference-model log-probs = policy log-probs + N(0, 0.1^2) (forward-only pass, untimed)
     ref = logprob.fused_logprob(hidden.view(T, H), weight, ids.view(T), v_offset=v_off, group=group).view(N, Tc)
@@ -305,7 +310,7 @@ def run_ours(args):
 
     def step(h, i, r, m, rw):
         return logprob.fused_logprob_gspo(h, weight, i, r, m, rw, G, BETA, EPS, EPS, True, None, v_offset=v_off,
-                                          group=group, chunk_tokens=args.chunk_tokens, d_weight_out=None,
+                                          group=group, chunk_tokens=call_chunk_tokens, d_weight_out=None,
                                           overlap_dlogits=bool(args.overlap_dlogits),
                                           **({"backward": "exp"} if args.backward == "exp" else
                                              {"fuse_dlogits": args.backward == "smem"}))
@@ -461,7 +466,7 @@ def run_ours(args):
                                     "reduce_scatter_fused": "reduce-scatter fused into the K2a epilogue (NVLink stores to the token owners) + local slot sum",
                                     "all_reduce": "one-shot P2P all-reduce beside the dW GEMM"}[args.dh_collective]
                                    if (args.exchange == "peer" and args.overlap_allreduce) else "NCCL all-reduce")
-                    if world > 1 else "single GPU", chunk_tokens=args.chunk_tokens,
+                    if world > 1 else "single GPU", chunk_tokens=args.chunk_tokens, chunk_sequences=seq_plan,
                     cache="inputs (%.1f GB) and per-chunk logits are far larger than the 126 MB L2; no flush needed"
                           % ((hidden.numel() * 2 + weight.numel() * 2) / 1e9), loss=loss),
         frac_of_bf16_peak=dict(burst=flop_tok * value / world / 1e12 / pk["burst"],
@@ -508,6 +513,7 @@ def main():
                          "their rows from the peers' partial buffers beside the dW GEMM (default), or the K2a epilogue "
                          "stores tiles at their owners (fused); or the full dHidden (one-shot P2P all-reduce)")
     ap.add_argument("--tunable", action="append", default=[], help="name=value for o3v_set_tunable (diagnostics)")
+    ap.add_argument("--no-chunk-plan", action="store_true", help="even chunks only (logprob.PLAN_CHUNKS = False)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the torch fp32 self-check after the timed regions (profiling runs)")
     args = ap.parse_args()

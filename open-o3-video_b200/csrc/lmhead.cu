@@ -137,7 +137,10 @@ static void plan_tiles(GemmParams& p, int ncta, int n_groups_hint, int acc = 1) 
 }
 
 // Number of vocab splits per m-block in K1.  Few splits keep the concurrently swept A panels
-// (hidden rows) L2-resident and W re-reads low; enough splits fill the persistent grid.
+// (hidden rows) L2-resident and W re-reads low; enough splits fill the persistent grid.  Four is the measured
+// optimum when the work fills its waves (profiles/r1_sweep_T32768_7b.log); another count (up to 16) is taken only
+// when the wave arithmetic says it saves >= 4 %: time ~ ceil(m_blocks * g / workers) waves x ceil(tiles / g) tiles,
+// e.g. 272 m-blocks x 594 tiles: g = 4 -> 8 x 149, g = 7 -> 13 x 85 (-7 %).
 static int fwd_groups(int64_t T, int64_t V, int ncta) {
   if (g_fwd_groups > 0) return g_fwd_groups;
   const int64_t num_m = ceil_div(T, 128 * ncta);
@@ -146,6 +149,13 @@ static int fwd_groups(int64_t T, int64_t V, int ncta) {
   int64_t g = 4;
   while (num_m * g < 2 * workers && g < n_tiles) g *= 2;     // small T: split the vocab further
   if (g > n_tiles) g = n_tiles;
+  if (g == 4 && num_m * g >= 4 * workers) {
+    auto cost = [&](int64_t gg) { return ceil_div(num_m * gg, workers) * ceil_div(n_tiles, gg); };
+    int64_t best = g, best_cost = cost(g);
+    for (int64_t gg = 5; gg <= 16 && gg <= n_tiles; ++gg)
+      if (cost(gg) < best_cost) { best = gg; best_cost = cost(gg); }
+    if (best_cost * 100 <= cost(g) * 96) g = best;
+  }
   return (int)g;
 }
 

@@ -32,6 +32,68 @@ SAVE_LOGITS_BYTES = 24 << 30
 SAVE_LOGITS_FREE_FRACTION = 0.25
 
 
+PLAN_CHUNKS = False     # measured on c2 (profiles/r2_ab_chunk_plan_c2.jsonl): no gain under the power cap, see plan_chunks
+
+
+_plan_vocab_cache = {}
+
+
+def _plan_vocab(V: int, group, dev) -> int:
+    """Rows of the LARGEST vocabulary slice of the group (slices differ by one 256-row tile): the chunk size derived
+    from it is the same on every rank.  One all-reduce per (group, V), then cached."""
+    if group is None:
+        return V
+    key = (id(group), V)
+    if key not in _plan_vocab_cache:
+        import torch.distributed as dist
+        t = torch.tensor([V], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=_pg(group))
+        _plan_vocab_cache[key] = int(t.item())
+    return _plan_vocab_cache[key]
+
+
+def plan_chunks(N: int, Tc: int, H: int, V: int, chunk_tokens: int, dev=None, tune: bool = True):
+    """Sequences per token chunk of the fused step.  Chunks hold whole sequences and at most `chunk_tokens` tokens; among
+    the few ways to cut N sequences the one with the least WAVE QUANTISATION of the persistent grids is taken: K2a runs
+    ceil(T_c / 256) x ceil(H / 512) tiles on #SM / 2 CTA pairs and K1 ceil(T_c / 128) x g items of ceil(tiles / g) tiles
+    on #SM CTAs (g as chosen by the library, csrc/lmhead.cu:fwd_groups).  c2 on one GPU: 4 x 16 sequences = 128 x 7 =
+    12.1 -> 13 waves of K2a (7 % idle); 17 + 17 + 17 + 13 sequences = 12.9 -> 13 and 9.8 -> 10 waves.
+    OFF by default (PLAN_CHUNKS): measured on c2, K2a does get 3-5 % faster with the better cuts, but the step does not
+    (300-306 ms for every cut): under the 1 kW cap the step is energy-bound, SMs that idle in a tail wave cost no energy
+    and their power goes to the busy ones, so removing idle time only moves clock between kernels."""
+    s_max = max(1, min(N, chunk_tokens // Tc))
+    n_min = -(-N // s_max)
+    even = -(-N // n_min)
+    base = [even] * (N // even) + ([N % even] if N % even else [])
+    if not (PLAN_CHUNKS and tune) or N == 1:
+        return base
+    sms = 148 if dev is None or not torch.cuda.is_available() else torch.cuda.get_device_properties(dev).multi_processor_count
+    pairs, tiles = sms // 2, -(-V // 256)
+
+    def cost(seqs):                                           # wave-quantised time of K1 + K2a, in units of one
+        t = seqs * Tc                                         # 128 x 256 x H tile of MMA work
+        mb, nt = -(-t // 256), -(-H // 512)
+        k2a = -(-(mb * nt) // pairs) * tiles * 4 / 2          # waves x (256x512 pair tile over V) per SM
+        m = -(-t // 128)
+        k1 = min(-(-(m * g) // sms) * -(-tiles // g) for g in range(4, 17))
+        g4 = -(-(m * 4) // sms) * -(-tiles // 4)
+        if k1 * 100 > g4 * 96:
+            k1 = g4                                           # the library keeps 4 groups unless another count saves 4 %
+        return k1 + k2a
+
+    best, best_cost = base, sum(cost(c) for c in base)
+    for n_chunks in (n_min, n_min + 1):
+        for first in range(max(1, s_max - 3), s_max + 1):     # k full-size chunks + one remainder
+            k, rest = divmod(N, first)
+            plan = [first] * k + ([rest] if rest else [])
+            if len(plan) != n_chunks:
+                continue
+            c = sum(cost(x) for x in plan)
+            if c * 100 < best_cost * 98:                      # only for a clear (>= 2 %) gain
+                best, best_cost = plan, c
+    return best
+
+
 def save_logits_budget(device) -> int:
     free, _ = torch.cuda.mem_get_info(device)
     return int(min(SAVE_LOGITS_BYTES, free * SAVE_LOGITS_FREE_FRACTION))
@@ -485,10 +547,11 @@ def fused_logprob_gspo(hidden: torch.Tensor, weight: torch.Tensor, completion_id
     mask = completion_mask.to(torch.int32).contiguous()
 
     if not chunk_tokens:
-        chunk_tokens = auto_chunk_tokens(V)
-    seqs = max(1, min(N, chunk_tokens // Tc))
-    n_chunks = -(-N // seqs)
-    seqs = -(-N // n_chunks)                                  # even out the chunks
+        chunk_tokens = auto_chunk_tokens(_plan_vocab(V, group, dev))
+    # sequences per chunk (whole sequences only); vocab-sharded ranks must all cut the step the same way
+    seq_plan = plan_chunks(N, Tc, H, V, chunk_tokens, dev, tune=group is None)
+    seqs = max(seq_plan)
+    n_chunks = len(seq_plan)
     logp = torch.empty(N, Tc, dtype=torch.float32, device=dev)
     zbuf = torch.empty(seqs * Tc, V, dtype=torch.bfloat16, device=dev) if need_grad else None
     d_hidden = None
@@ -549,8 +612,9 @@ def fused_logprob_gspo(hidden: torch.Tensor, weight: torch.Tensor, completion_id
         bwd_dweight(z, hidden2[s:e], d_weight, accumulate=(ci > 0) or (d_weight_out is not None), softmax_bwd=sb)
 
     pending = None                                            # chunk whose backward GEMMs are still to be enqueued
-    for ci, n0 in enumerate(range(0, N, seqs)):
-        n1 = min(N, n0 + seqs)
+    starts = [sum(seq_plan[:i]) for i in range(n_chunks)]
+    for ci, n0 in enumerate(starts):
+        n1 = n0 + seq_plan[ci]
         s, e = n0 * Tc, n1 * Tc
         z = None
         if need_grad:
