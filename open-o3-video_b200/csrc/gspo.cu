@@ -113,13 +113,44 @@ __device__ __forceinline__ void group_advantage(const GspoParams& p, int64_t n, 
   adv = (mine - mean) / (sd + 1e-4f);
 }
 
+// Same, computed by the whole CTA: thread j < G sums the F rewards of rollout j of the group (independent loads) into
+// shared memory, thread 0 reduces the G values in index order (same arithmetic and order as group_advantage).
+constexpr int kMaxGroupSmem = 256;
+__device__ __forceinline__ void group_advantage_cta(const GspoParams& p, int64_t n, float* s_r, float& adv, float& sd) {
+  const int64_t g0 = (n / p.G) * p.G;
+  if (p.G > kMaxGroupSmem) {                     // (never in practice: G = 4 .. 16)
+    if (threadIdx.x == 0) { group_advantage(p, n, adv, sd); s_r[0] = adv; s_r[1] = sd; }
+    __syncthreads();
+    adv = s_r[0]; sd = s_r[1];
+    __syncthreads();
+    return;
+  }
+  for (int64_t j = threadIdx.x; j < p.G; j += kGspoThreads) {
+    float r = 0.f;
+    for (int64_t f = 0; f < p.F; ++f) r += p.rpf[(g0 + j) * p.F + f];
+    s_r[j] = r;
+  }
+  __syncthreads();
+  float mean = 0.f;
+  for (int64_t j = 0; j < p.G; ++j) mean += s_r[j];
+  mean /= (float)p.G;
+  float var = 0.f;
+  for (int64_t j = 0; j < p.G; ++j) var += (s_r[j] - mean) * (s_r[j] - mean);
+  sd = sqrtf(var / (float)(p.G - 1));            // unbiased; G == 1 -> NaN like torch.std
+  adv = (s_r[n - g0] - mean) / (sd + 1e-4f);
+  __syncthreads();
+}
+
 // One launch: masked partial sums of (slice, sequence); the last CTA to arrive for a sequence finishes it.
 __global__ void __launch_bounds__(kGspoThreads)
 gspo_kernel(const GspoParams p) {
   __shared__ float s_red[kGspoThreads / 32];
   __shared__ float s_tot[8];
+  __shared__ float s_r[kMaxGroupSmem];
   __shared__ bool s_last;
   const int64_t nl = blockIdx.y, n = p.seq_offset + nl;
+  float A_seq, sd_seq;
+  group_advantage_cta(p, n, s_r, A_seq, sd_seq);
   const int64_t Tc = p.Tc;
   const float* __restrict__ lp_row = p.logp + nl * Tc;
   const float* __restrict__ old_row = p.old_logp ? p.old_logp + nl * Tc : nullptr;
@@ -129,9 +160,7 @@ gspo_kernel(const GspoParams p) {
   {
     // ---- this CTA's slice: masked partial sums -> partials[n][slice][4]
     const int64_t t0 = (int64_t)blockIdx.x * p.slice_len, t1 = min(t0 + p.slice_len, Tc);
-    if (threadIdx.x == 0) { float a, sd; group_advantage(p, n, a, sd); s_tot[0] = a; }
-    __syncthreads();
-    const float A = s_tot[0];
+    const float A = A_seq;
     float cnt = 0.f, sum_lr = 0.f, sum_kl = 0.f, sum_obj = 0.f;
 #pragma unroll 4
     for (int64_t t = t0 + threadIdx.x; t < t1; t += kGspoThreads) {
@@ -173,8 +202,7 @@ gspo_kernel(const GspoParams p) {
       const float* part = p.partials + (n * kMaxSlices + sidx) * 4;
       cnt += __ldcg(part + 0); sum_lr += __ldcg(part + 1); sum_kl += __ldcg(part + 2); sum_obj += __ldcg(part + 3);
     }
-    float A, sd;
-    group_advantage(p, n, A, sd);
+    const float A = A_seq, sd = sd_seq;
     const float denom = fmaxf(cnt, 1.f);                      // .clamp(min=1.0) :693, :706
     float c1_seq = 1.f, gate_seq = 1.f;
     if (p.gspo) {
@@ -203,23 +231,48 @@ gspo_kernel(const GspoParams p) {
     // and ds/dlogp_t = mask_t/denom, so the factor is (cnt/denom) * mask_t/denom.
     const float w = p.gspo ? (cnt / denom) : 1.f;
     float* __restrict__ g_row = p.grad + nl * Tc;
-#pragma unroll 4
-    for (int64_t t = threadIdx.x; t < Tc; t += kGspoThreads) {
-      const float lp = lp_row[t], rf = ref_row[t];
-      const float m = (float)m_row[t];
+    auto grad_of = [&](float lp, float rf, float mf, float ol) -> float {
       float kl, dkl;
       kl_and_grad(lp, rf, kl, dkl);
       float dobj;
       if (p.gspo) {
         dobj = -A * c1_seq * gate_seq;
       } else {
-        const float lr = old_row ? (lp - old_row[t]) : 0.f;
+        const float lr = old_row ? (lp - ol) : 0.f;
         const float c1 = expf(lr);
         const float gate = (A > 0.f) ? (c1 <= 1.f + p.eps_hi ? 1.f : 0.f)
                          : (A < 0.f) ? (c1 >= 1.f - p.eps_lo ? 1.f : 0.f) : 1.f;
         dobj = -A * c1 * gate;
       }
-      g_row[t] = m * scale * (dobj * w + p.beta * dkl);
+      return mf * scale * (dobj * w + p.beta * dkl);
+    };
+    // one CTA walks the whole sequence (its inputs are L2 hits by now): 16-byte vectors, two independent vectors per
+    // thread and iteration, so a 16384-token sequence is 8 memory round trips per thread instead of 64
+    const bool vec = ((Tc & 3) == 0) &&
+                     ((((uintptr_t)lp_row | (uintptr_t)ref_row | (uintptr_t)m_row | (uintptr_t)g_row |
+                        (uintptr_t)(old_row ? old_row : lp_row)) & 15u) == 0);
+    if (vec) {
+      const int64_t nv = Tc >> 2;
+      const float4* lp4 = reinterpret_cast<const float4*>(lp_row);
+      const float4* rf4 = reinterpret_cast<const float4*>(ref_row);
+      const int4* m4 = reinterpret_cast<const int4*>(m_row);
+      const float4* ol4 = reinterpret_cast<const float4*>(old_row ? old_row : lp_row);
+      float4* g4 = reinterpret_cast<float4*>(g_row);
+#pragma unroll 2
+      for (int64_t i = threadIdx.x; i < nv; i += kGspoThreads) {
+        const float4 a = lp4[i], b = rf4[i], o = ol4[i];
+        const int4 mm = m4[i];
+        float4 r;
+        r.x = grad_of(a.x, b.x, (float)mm.x, o.x);
+        r.y = grad_of(a.y, b.y, (float)mm.y, o.y);
+        r.z = grad_of(a.z, b.z, (float)mm.z, o.z);
+        r.w = grad_of(a.w, b.w, (float)mm.w, o.w);
+        g4[i] = r;
+      }
+    } else {
+#pragma unroll 4
+      for (int64_t t = threadIdx.x; t < Tc; t += kGspoThreads)
+        g_row[t] = grad_of(lp_row[t], ref_row[t], (float)m_row[t], old_row ? old_row[t] : 0.f);
     }
   }
   // ---- deterministic final reduction by the CTA that finishes the last sequence of the step (across range calls)

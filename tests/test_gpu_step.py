@@ -160,7 +160,26 @@ def test_c1_shape_known_answer():
         z = h[s:s + 512].float() @ w.float().T
         ref[s:s + 512] = z.log_softmax(-1).gather(1, t[s:s + 512, None])[:, 0]
     assert ((lp.view(-1) - ref).abs() / ref.abs()).max().item() < 1e-3
-    assert out["d_hidden"].float().abs().max().item() > 0 and torch.isfinite(out["d_weight"]).all()
+    # ... and the BACKWARD at the full head against fp32 on the GPU: d loss / d logp from the oracle's autograd on the
+    # library's log-probs, P = g (onehot - softmax) from fp32 logits, dHidden of every token, 512 columns of dW
+    lpc = lp.detach().cpu().requires_grad_(True)
+    exp = ogspo.gspo_step(lpc, (lp + 0.1).cpu(), mask.cpu(), rpf.cpu(), 4, 0.04)
+    exp["loss"].backward()
+    g = lpc.grad.cuda().view(-1)
+    wf = w.float()
+    cols = torch.arange(70000, 70512, device="cuda")
+    dH_ref = torch.empty(N * Tc, H, device="cuda")
+    dW_ref = torch.zeros(512, H, device="cuda")
+    for s in range(0, N * Tc, 512):
+        z = h[s:s + 512].float() @ wf.T
+        P = torch.softmax(z, -1).mul_(-g[s:s + 512, None])
+        P[torch.arange(512, device="cuda"), t[s:s + 512]] += g[s:s + 512]
+        dH_ref[s:s + 512] = P @ wf
+        dW_ref += P[:, cols].T @ h[s:s + 512].float()
+        del z, P
+    dH = out["d_hidden"].float().view(N * Tc, H)
+    assert ((dH - dH_ref).norm() / dH_ref.norm()).item() < 1e-2
+    assert ((out["d_weight"][cols] - dW_ref).norm() / dW_ref.norm()).item() < 1e-2
 
 
 def test_trainer_mixin_keeps_reference_contract():
