@@ -153,7 +153,7 @@ static int fwd_groups(int64_t T, int64_t V, int ncta) {
     auto cost = [&](int64_t gg) { return ceil_div(num_m * gg, workers) * ceil_div(n_tiles, gg); };
     int64_t best = g, best_cost = cost(g);
     for (int64_t gg = 5; gg <= 16 && gg <= n_tiles; ++gg)
-      if (cost(gg) < best_cost) { best = gg; best_cost = cost(gg); }
+      if (cost(gg) * 100 < best_cost * 99) { best = gg; best_cost = cost(gg); }   // near-ties: the smaller count
     if (best_cost * 100 <= cost(g) * 96) g = best;
   }
   return (int)g;

@@ -208,7 +208,8 @@ def _dw_tail_plan(V: int, H: int, T: int, dev):
     """-> (rows of the main launch, K splits) or None when the tile count already fills its waves."""
     if not DW_TAIL_SPLIT:
         return None
-    workers = torch.cuda.get_device_properties(dev).multi_processor_count // 2
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count if torch.cuda.is_available() else 148
+    workers = sms // 2
     mb, nt = -(-V // 256), -(-H // 512)
     for tail in (1, 2):
         m_main = mb - tail

@@ -72,6 +72,11 @@ def test_argument_validation_without_gpu(lib):
     assert lib.o3v_parse_workspace_bytes(4, 2, 3, 1) == 4 * 40 + 16 + 4 * (2 + 3 + 1) * 4
     assert lib.o3v_set_tunable(b"nope", 1) == -1
     assert lib.o3v_lmhead_fwd_workspace_bytes(128, 1024, 64) == 4 * 3 * 128 * 4
+    # K1 vocab-group count (csrc/lmhead.cu:fwd_groups; 148 SMs assumed without a device): 4 when the work fills
+    # its waves, another count only for a >= 4 % saving by the wave arithmetic, the smaller one on near-ties
+    groups = lambda T, V: lib.o3v_lmhead_fwd_workspace_bytes(T, V, 3584) // (12 * T)
+    assert groups(32768, 152064) == 4 and groups(131072, 19200) == 4 and groups(131072, 38144) == 4
+    assert groups(34816, 152064) == 7 and groups(26624, 152064) == 7
     assert lib.o3v_gspo_workspace_bytes(8) == (3 * 8 + 4 + 8 * 32 * 4) * 4
 
 
