@@ -19,7 +19,12 @@
 namespace o3v {
 
 constexpr int kLanes = 16;             // lanes per rollout
-constexpr int kRewardThreads = 256;    // 16 rollouts per CTA
+// Threads per CTA (template parameter of the kernel; 24 resident warps per SM in every variant).  A warp holds two
+// rollouts of one prompt, i.e. of one task, and only some tasks are expensive (the claim / proximity branches: ~7 us of
+// dependent fp64 chains per warp against ~2 us), so a CTA keeps its SM slots until its slowest warp is done.  Measured
+// at 65536 rollouts x 16 (tools/k4_ab.py, L2 flushed): 256 threads 70.5 us, 128 threads 67.5 us, 64 threads 81.9 us
+// (the per-CTA ground-truth staging and launch cost outweigh the better packing).
+constexpr int kRewardThreadsDefault = 128;
 
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
@@ -68,8 +73,8 @@ __host__ __device__ inline size_t gt_bytes_per_prompt(const o3v_rewards_soa& s) 
   return (size_t)gt_doubles(s) * 8 + (((size_t)gt_ints(s) * 4 + 15) & ~(size_t)15);
 }
 
-template <bool kStageGT, int kMinBlocks>
-__global__ void __launch_bounds__(kRewardThreads, kMinBlocks)
+template <bool kStageGT, int kRewardThreads>
+__global__ void __launch_bounds__(kRewardThreads, 768 / kRewardThreads)      // 24 resident warps per SM
 rewards_kernel(const o3v_rewards_soa s, double* __restrict__ out) {
   extern __shared__ double smem_gt[];
   const int lane = threadIdx.x & (kLanes - 1);
@@ -336,21 +341,27 @@ extern "C" int o3v_grounded_rewards(const o3v_rewards_soa* soa, double* out, voi
   int rc = o3v::check_device();
   if (rc) return rc;
   if (s.R == 0) return O3V_OK;
-  const int per_cta = o3v::kRewardThreads / o3v::kLanes;
+  // threads per CTA (diagnostic override: O3V_REWARDS_CTA=64|128|256)
+  static const int cta = [] {
+    const char* e = getenv("O3V_REWARDS_CTA");
+    const int v = e ? atoi(e) : o3v::kRewardThreadsDefault;
+    return (v == 64 || v == 128 || v == 256) ? v : o3v::kRewardThreadsDefault;
+  }();
+  const int per_cta = cta / o3v::kLanes;
   const unsigned grid = (unsigned)((s.R + per_cta - 1) / per_cta);
-  // prompts a CTA of 16 consecutive rollouts can touch
+  // prompts a CTA of `per_cta` consecutive rollouts can touch
   const int64_t span = std::min<int64_t>(per_cta, (per_cta + s.G - 1) / s.G + 1);
   const size_t smem = (size_t)span * o3v::gt_bytes_per_prompt(s);
-  // resident CTAs per SM the kernel is compiled for (diagnostic override: O3V_REWARDS_MIN_BLOCKS=2|3)
-  static const int min_blocks = [] { const char* e = getenv("O3V_REWARDS_MIN_BLOCKS"); return (e && e[0] == '2') ? 2 : 3; }();
   cudaStream_t st = (cudaStream_t)stream;
-  if (smem <= 40 * 1024) {
-    if (min_blocks == 2) o3v::rewards_kernel<true, 2><<<grid, o3v::kRewardThreads, smem, st>>>(s, out);
-    else o3v::rewards_kernel<true, 3><<<grid, o3v::kRewardThreads, smem, st>>>(s, out);
-  } else {   // very large K x O x Gb: read the ground truth through L2 instead
-    if (min_blocks == 2) o3v::rewards_kernel<false, 2><<<grid, o3v::kRewardThreads, 0, st>>>(s, out);
-    else o3v::rewards_kernel<false, 3><<<grid, o3v::kRewardThreads, 0, st>>>(s, out);
+  const bool stage = smem <= (size_t)(40 * 1024) * cta / 256;     // very large K x O x Gb: read the ground truth through L2
+#define O3V_REWARDS_LAUNCH(STAGE, THREADS) \
+  o3v::rewards_kernel<STAGE, THREADS><<<grid, THREADS, (STAGE) ? smem : 0, st>>>(s, out)
+  if (stage) {
+    if (cta == 64) O3V_REWARDS_LAUNCH(true, 64); else if (cta == 128) O3V_REWARDS_LAUNCH(true, 128); else O3V_REWARDS_LAUNCH(true, 256);
+  } else {
+    if (cta == 64) O3V_REWARDS_LAUNCH(false, 64); else if (cta == 128) O3V_REWARDS_LAUNCH(false, 128); else O3V_REWARDS_LAUNCH(false, 256);
   }
+#undef O3V_REWARDS_LAUNCH
   O3V_LAUNCH_CHECK();
   return O3V_OK;
 }

@@ -1,5 +1,5 @@
 """K4 at BASELINE config 4 (65536 rollouts x 16): kernel time with L2 flushed between iterations (one process per
-O3V_REWARDS_MIN_BLOCKS setting; run under gpurun)."""
+O3V_REWARDS_CTA setting (threads per CTA); run under gpurun)."""
 import json, os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -20,5 +20,5 @@ for i in range(13):
     a.record(); rewards.grounded_rewards_device(dev_arrays, dims, out); b.record(); torch.cuda.synchronize()
     if i >= 3:
         ts.append(a.elapsed_time(b) * 1e3)
-print(json.dumps(dict(kernel="K4 c4", min_blocks=os.environ.get("O3V_REWARDS_MIN_BLOCKS", "3"), best_us=min(ts),
-                      mean_us=sum(ts) / len(ts), soa_bytes=nbytes, frac_of_hbm=nbytes / min(ts) / 1e6 / 6532.2)))
+print(json.dumps(dict(kernel="K4 c4", cta_threads=os.environ.get("O3V_REWARDS_CTA", "64"), best_us=min(ts),
+                      mean_us=sum(ts) / len(ts), soa_bytes=nbytes, frac_of_hbm=nbytes / min(ts) / 1e3 / 6532.2)))
