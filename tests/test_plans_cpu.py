@@ -41,3 +41,23 @@ def test_plan_chunks_whole_sequences_within_the_budget(monkeypatch):
     assert logprob.plan_chunks(64, 2048, 3584, 152064, logprob.auto_chunk_tokens(152064)) == [17, 17, 17, 13]
     # vocab-sharded ranks never tune (every rank must cut the step the same way)
     assert logprob.plan_chunks(64, 2048, 3584, 152064, logprob.auto_chunk_tokens(152064), tune=False) == [16] * 4
+
+
+def test_reduce_scatter_rows_cover_every_token_once():
+    """dh_mode="reduce_scatter": after K2a of the chunk [row0, row0 + rows) every owner pulls the intersection of ITS rows
+    with the chunk (sharded.PeerExchange.reduce_scatter_dh_async); over the chunks of a step and the ranks of the group
+    every token row must be pulled exactly once, into the right place of the owner's [hi - lo, H] result."""
+    for T, world, chunk in ((131072, 8, 131072), (524288, 8, 262144), (524288, 4, 131072), (101, 2, 40), (7, 8, 3), (1000, 3, 999)):
+        seen = [0] * T
+        for rank in range(world):
+            rpo, lo, hi = sharded.token_owner_rows(T, world, rank)
+            assert rpo == -(-T // world) and 0 <= lo <= hi <= T
+            filled = [0] * (hi - lo)
+            for row0 in range(0, T, chunk):
+                rows = min(chunk, T - row0)
+                a, b = max(lo, row0), min(hi, row0 + rows)          # as in reduce_scatter_dh_async
+                for t in range(a, b):
+                    seen[t] += 1
+                    filled[t - lo] += 1
+            assert all(f == 1 for f in filled)
+        assert all(s == 1 for s in seen)
